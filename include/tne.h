@@ -1,0 +1,169 @@
+/*
+ * tne.h -- C ABI of the B200-native engine for TensorNetworkEvolve.jl's hot path.
+ *
+ * The reference has no FFI; its plug-in point is Julia multiple dispatch on the tensor
+ * array type (both in-tree examples hook `OMEinsum.einsum`: src/TensorAD/rules.jl:1-8,
+ * src/cracker.jl:4-8).  Each entry point below names the reference call it stands behind;
+ * the Julia-side `ccall` stubs are in INTEGRATION.md / julia/TensorNetworkEvolveB200.jl.
+ *
+ * Conventions
+ *  - every tensor is ComplexF64 (interleaved re,im; 16 bytes), column-major, owned by the
+ *    library and named by an opaque 64-bit handle (`tne_buf`, 0 = null).  Real-valued
+ *    Julia arrays (norms, singular values) are carried with zero imaginary part.
+ *  - host pointers are borrowed for the duration of the call only.
+ *  - every function returns 0 on success and a non-zero `tne_status` otherwise; it never
+ *    throws or aborts.  `tne_last_error` gives the message (the Julia shim raises
+ *    ErrorException with it, mirroring `error(...)`/`@assert` at src/peps.jl:74,259,330,356).
+ *  - one context per GPU / per process, driven from one host thread; all work is enqueued
+ *    on the context's stream and is asynchronous until tne_download / tne_sync.
+ *  - there is no CPU fallback: without a CUDA device tne_ctx_create fails.
+ */
+#ifndef TNE_H
+#define TNE_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tne_ctx tne_ctx;
+typedef int64_t tne_buf;
+
+enum tne_status {
+    TNE_OK = 0,
+    TNE_ERR_INVALID = 1,
+    TNE_ERR_CUDA = 2,
+    TNE_ERR_OOM = 3,
+    TNE_ERR_UNSUPPORTED = 4,
+    TNE_ERR_NCCL = 5
+};
+
+#define TNE_MAX_RANK 32
+
+/* ---- context (new; the reference is single-process CPU code) ------------------------- */
+int tne_version(void);
+int tne_ctx_create(int device, tne_ctx** out);
+int tne_ctx_destroy(tne_ctx* ctx);
+const char* tne_last_error(tne_ctx* ctx);
+int tne_sync(tne_ctx* ctx);
+/* workspace budget for tree programs (bytes); default = 85% of the device memory */
+int tne_set_mem_limit(tne_ctx* ctx, int64_t bytes);
+int tne_mem_info(tne_ctx* ctx, int64_t* in_use, int64_t* peak, int64_t* workspace);
+/* cudaStream_t of the context (for CUDA-event timing by the caller) */
+void* tne_stream(tne_ctx* ctx);
+/* number of kernels this library has launched on the context so far */
+int64_t tne_launch_count(tne_ctx* ctx);
+/* statistics of the most recent tree program: [0] algorithmic real flops, [1] algorithmic bytes,
+ * [2] contraction kernels launched, [3] workspace bytes, [4] recomputed flops, [5] number of values */
+int tne_last_program_stats(tne_ctx* ctx, double* stats6);
+/* option knobs: "recompute_threshold_bytes", "force_generic_kernel", "debug" */
+int tne_set_option(tne_ctx* ctx, const char* key, int64_t value);
+
+/* ---- device tensors: Array{ComplexF64,N} as used at src/peps.jl:41,132 ---------------- */
+int tne_alloc(tne_ctx* ctx, int rank, const int64_t* dims, tne_buf* out);
+int tne_free(tne_ctx* ctx, tne_buf buf);
+int tne_shape(tne_ctx* ctx, tne_buf buf, int* rank, int64_t* dims);
+int tne_upload(tne_ctx* ctx, tne_buf buf, const void* host_c128);      /* Array -> device */
+int tne_download(tne_ctx* ctx, tne_buf buf, void* host_c128);          /* Array(x); synchronises */
+void* tne_device_ptr(tne_ctx* ctx, tne_buf buf);
+
+/* ---- OMEinsum.einsum(code, xs, size_dict), unary and binary ----------------------------
+ * Call sites: src/peps.jl:334,344,373,376,392-393,429; src/TensorAD/rules.jl:2-5 (forward and
+ * einsum_grad); src/timeevolve.jl:38.  `labels_flat` concatenates the inputs' labels,
+ * `conj_flags[i] != 0` conjugates input i while it is loaded (fuses the conj copies of
+ * src/peps.jl:107 and of einsum_grad).  Repeated labels inside one tensor are unsupported. */
+int tne_einsum(tne_ctx* ctx, int n_in, const int32_t* labels_flat, const int32_t* ranks,
+               const tne_buf* in, const int32_t* conj_flags,
+               const int32_t* out_labels, int out_rank, tne_buf* out);
+
+/* ---- Base / broadcast methods used by src/TensorAD/rules.jl and src/peps.jl:283-295 ----- */
+enum tne_map_op {
+    TNE_COPY = 0, TNE_CONJ = 1, TNE_REAL = 2, TNE_IMAG = 3, TNE_ABS = 4, TNE_SQRT = 5, TNE_INV = 6,
+    TNE_NEG = 7, TNE_SCALE = 8,   /* x * s */
+    TNE_POW = 9,                  /* x .^ s (s real), principal branch */
+    TNE_SIN = 10, TNE_COS = 11, TNE_SAFE_INV = 12 /* src/peps.jl:419-426 */
+};
+enum tne_map2_op { TNE_ADD = 0, TNE_SUB = 1, TNE_MUL = 2, TNE_DIV = 3 };
+int tne_map(tne_ctx* ctx, int op, tne_buf in, double s_re, double s_im, tne_buf* out);
+/* elementwise binary; an operand with exactly one element broadcasts (0-dim * tensor, rules.jl:79-88) */
+int tne_map2(tne_ctx* ctx, int op, tne_buf a, tne_buf b, tne_buf* out);
+int tne_reduce_sum(tne_ctx* ctx, tne_buf in, tne_buf* out);                     /* sum(x) -> 0-dim */
+int tne_fill(tne_ctx* ctx, tne_buf scalar0, int rank, const int64_t* dims, tne_buf* out); /* fill(x[], dims) */
+/* x[lo+1 : lo+count] of the flattened tensor as a new rank-1 tensor (variables[a:b], src/peps.jl:217) */
+int tne_slice(tne_ctx* ctx, tne_buf in, int64_t lo, int64_t count, tne_buf* out);
+/* accum(zero(x), lo+1:lo+count, y): a zero vector of `total` with y added at the range (rules.jl:46-55) */
+int tne_embed(tne_ctx* ctx, tne_buf y, int64_t lo, int64_t total, tne_buf* out);
+int tne_reshape(tne_ctx* ctx, tne_buf in, int rank, const int64_t* dims, tne_buf* out);    /* shares storage */
+int tne_concat(tne_ctx* ctx, int n, const tne_buf* in, tne_buf* out);            /* vcat(vec.(xs)...) (src/peps.jl:202) */
+
+/* ---- (::NestedEinsum)(xs...) / (::SlicedEinsum)(xs...) fast path: src/peps.jl:109,321 ---- */
+typedef struct {
+    int32_t n_leaves;
+    int32_t n_nodes;                 /* binary nodes in post-order (children before parents) */
+    const int32_t* leaf_rank;        /* [n_leaves] */
+    const int32_t* leaf_labels;      /* concatenated leaf labels */
+    const int32_t* node_children;    /* [2*n_nodes]; id < n_leaves is a leaf, otherwise n_leaves + node index */
+    const int32_t* node_out_rank;    /* [n_nodes] */
+    const int32_t* node_out_labels;  /* concatenated; the order is honoured for the root only */
+    int32_t n_sliced;                /* SlicedEinsum: labels looped over and summed */
+    const int32_t* sliced_labels;
+    int32_t shard_rank, shard_world; /* this process takes work items with index % world == rank */
+} tne_tree;
+
+int tne_contract_tree(tne_ctx* ctx, const tne_tree* tree, const tne_buf* leaves,
+                      const int32_t* leaf_conj, tne_buf* out);
+
+/* ---- Yao.expect(op::Add, pa, pb) + its TensorAD pullback: src/peps.jl:469-477,
+ * src/timeevolve.jl:55-64.  A term replaces up to 4 leaves of the network (h_k applied to the ket
+ * tensors) and carries a scalar coefficient; value = sum_k coef_k * tree(leaves with term k's
+ * replacements).  Terms share every sub-contraction that does not contain a replaced leaf, and
+ * completed terms are summed into one running partial result.  With n_terms == 0 the plain tree is
+ * evaluated.  If n_grad > 0 the pullback for cotangent `seed` (convention g = dL/dre + i dL/dim)
+ * w.r.t. the listed leaves is returned in new buffers shaped like those leaves.
+ * Work is sharded over (sliced-label assignments) with index % shard_world == shard_rank; the
+ * caller all-reduces `value` and the gradients (tne_allreduce_sum or torch.distributed). */
+typedef struct {
+    int32_t n_repl;
+    int32_t leaf[4];
+    tne_buf repl[4];
+    double coef_re, coef_im;
+} tne_term;
+
+int tne_expect_terms(tne_ctx* ctx, const tne_tree* tree, const tne_buf* leaves, const int32_t* leaf_conj,
+                     int n_terms, const tne_term* terms,
+                     int n_grad, const int32_t* grad_leaves, double seed_re, double seed_im,
+                     tne_buf* value_out, tne_buf* grads_out);
+
+/* ---- LinearAlgebra.svd + truncation and the fused apply_onbond!: src/peps.jl:353-417 ------
+ * A is m x n column-major.  Keeps D = min(Dmax, first index with S < eps minus one) (src/peps.jl:383-390);
+ * U is m x D, S has D entries (real), V is n x D with A ~= U diag(S) V^H.  `kept` and `trunc_err`
+ * (sum of the discarded singular values, the @info of src/peps.jl:386) are host outputs. */
+int tne_svd_trunc(tne_ctx* ctx, tne_buf A, int Dmax, double eps,
+                  tne_buf* U, tne_buf* S, tne_buf* V, int32_t* kept, double* trunc_err);
+
+typedef struct {
+    tne_buf ti, tj;            /* site tensors, physical leg first (src/peps.jl:253-254) */
+    int32_t axis_i, axis_j;    /* 0-based position of the shared bond in ti / tj */
+    double gate[32];           /* 4x4 complex, column-major, M[o_i + 2 o_j, i_i + 2 i_j] */
+    int32_t Dmax;
+    double eps;
+    int32_t vidal;             /* 0: SimplePEPS (sqrt(S) into both); 1: VidalPEPS */
+    tne_buf lambda_i[TNE_MAX_RANK]; /* Vidal: bond vector per axis of ti (entry for axis 0 ignored) */
+    tne_buf lambda_j[TNE_MAX_RANK];
+    /* outputs */
+    tne_buf ti_out, tj_out, s_out;
+    int32_t kept;
+    double trunc_err;
+} tne_bond_job;
+
+int tne_apply_onbond_batched(tne_ctx* ctx, int n_jobs, tne_bond_job* jobs);
+
+/* ---- multi-GPU: sum of partial energies / gradients (serial `sum` at src/peps.jl:470) ------
+ * comm is created from an NCCL unique id broadcast by the host program. */
+int tne_nccl_unique_id(void* id128);
+int tne_comm_init(tne_ctx* ctx, const void* id128, int rank, int world);
+int tne_allreduce_sum(tne_ctx* ctx, int n, const tne_buf* bufs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TNE_H */

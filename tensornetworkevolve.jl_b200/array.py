@@ -1,0 +1,279 @@
+"""``B200Array``: the device array type that slots in behind the reference's array-generic
+code (``vertex_tensors::Vector{<:AbstractArray{T}}``, src/peps.jl:41; ``DiffTensor`` wraps any
+``AbstractArray``, src/TensorAD/TensorAD.jl:30-40).  Storage is ComplexF64, column-major, owned
+by the library; ``is_real`` mirrors Julia's real element types (norms, singular values).
+"""
+import ctypes as C
+import os
+import weakref
+
+import numpy as np
+
+from . import _lib
+from ._lib import TneError
+
+# tne_map_op / tne_map2_op
+COPY, CONJ, REAL, IMAG, ABS, SQRT, INV, NEG, SCALE, POW, SIN, COS, SAFE_INV = range(13)
+ADD, SUB, MUL, DIV = range(4)
+
+
+class Context:
+    """One context per process / GPU (``tne_ctx_create``)."""
+
+    def __init__(self, device=None):
+        L = _lib.lib()
+        if device is None:
+            device = int(os.environ.get("LOCAL_RANK", "0"))
+        h = C.c_void_p()
+        rc = L.tne_ctx_create(int(device), C.byref(h))
+        if rc != 0:
+            raise TneError("tne_ctx_create failed: %s" % (L.tne_last_error(None) or b"").decode())
+        self.h = h
+        self.L = L
+        self.device = int(device)
+        self._fin = weakref.finalize(self, L.tne_ctx_destroy, h)
+
+    def check(self, rc):
+        if rc != 0:
+            raise TneError((self.L.tne_last_error(self.h) or b"?").decode())
+
+    def sync(self):
+        self.check(self.L.tne_sync(self.h))
+
+    def set_option(self, key, value):
+        self.check(self.L.tne_set_option(self.h, key.encode(), int(value)))
+
+    def set_mem_limit(self, nbytes):
+        self.check(self.L.tne_set_mem_limit(self.h, int(nbytes)))
+
+    def launch_count(self):
+        return int(self.L.tne_launch_count(self.h))
+
+    def stream(self):
+        return self.L.tne_stream(self.h)
+
+    def program_stats(self):
+        s = (C.c_double * 6)()
+        self.check(self.L.tne_last_program_stats(self.h, s))
+        return dict(flops=s[0], bytes=s[1], contractions=int(s[2]), workspace_bytes=int(s[3]),
+                    recompute_flops=s[4], values=int(s[5]))
+
+    def mem_info(self):
+        a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
+        self.check(self.L.tne_mem_info(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return dict(in_use=a.value, peak=b.value, workspace=c.value)
+
+
+_CTX = None
+
+
+def context():
+    """The process-wide context (created on first use; needs a B200)."""
+    global _CTX
+    if _CTX is None:
+        _CTX = Context()
+    return _CTX
+
+
+def _i64(seq):
+    return (C.c_int64 * max(1, len(seq)))(*[int(x) for x in seq])
+
+
+def _i32(seq):
+    return (C.c_int32 * max(1, len(seq)))(*[int(x) for x in seq])
+
+
+class B200Array:
+    """Device tensor handle.  Immutable from the host's point of view (ops return new arrays)."""
+
+    __array_priority__ = 900
+    __array_ufunc__ = None
+
+    def __init__(self, handle, shape, is_real=False, ctx=None):
+        self.ctx = ctx or context()
+        self.handle = int(handle)
+        self.shape = tuple(int(s) for s in shape)
+        self.is_real = bool(is_real)
+        self._fin = weakref.finalize(self, _free, self.ctx, self.handle)
+
+    # -- construction / transfer -------------------------------------------------------
+    @staticmethod
+    def from_numpy(x, ctx=None):
+        ctx = ctx or context()
+        x = np.asarray(x)
+        is_real = not np.iscomplexobj(x)
+        host = np.array(x, dtype=np.complex128, order="F")  # keeps 0-dim arrays 0-dim
+        h = C.c_int64()
+        ctx.check(ctx.L.tne_alloc(ctx.h, host.ndim, _i64(host.shape), C.byref(h)))
+        if host.size:
+            ctx.check(ctx.L.tne_upload(ctx.h, h.value, host.ctypes.data_as(C.c_void_p)))
+        return B200Array(h.value, host.shape, is_real, ctx)
+
+    def to_numpy(self):
+        out = np.empty(self.shape, dtype=np.complex128, order="F")
+        if out.size:
+            self.ctx.check(self.ctx.L.tne_download(self.ctx.h, self.handle, out.ctypes.data_as(C.c_void_p)))
+        return out.real.copy() if self.is_real else out
+
+    @property
+    def ndim(self):
+        return len(self.shape)
+
+    @property
+    def size(self):
+        return int(np.prod(self.shape, dtype=np.int64)) if self.shape else 1
+
+    @property
+    def dtype(self):
+        return np.dtype(np.float64 if self.is_real else np.complex128)
+
+    def item(self):
+        v = self.to_numpy().reshape(-1)[0]
+        return float(v) if self.is_real else complex(v)
+
+    def __repr__(self):
+        return "B200Array(%s, %s)" % ("x".join(map(str, self.shape)) or "0-dim", "Float64" if self.is_real else "ComplexF64")
+
+    # -- elementwise ---------------------------------------------------------------------
+    def _map(self, op, s=0.0, is_real=None):
+        h = C.c_int64()
+        s = complex(s)
+        self.ctx.check(self.ctx.L.tne_map(self.ctx.h, op, self.handle, s.real, s.imag, C.byref(h)))
+        return B200Array(h.value, self.shape, self.is_real if is_real is None else is_real, self.ctx)
+
+    def _map2(self, op, other):
+        h = C.c_int64()
+        self.ctx.check(self.ctx.L.tne_map2(self.ctx.h, op, self.handle, other.handle, C.byref(h)))
+        shape = self.shape if self.size >= other.size and not (self.size == 1 and other.ndim > self.ndim) else other.shape
+        return B200Array(h.value, shape, self.is_real and other.is_real, self.ctx)
+
+    def copy(self):
+        return self._map(COPY)
+
+    def conj(self):
+        return self._map(CONJ)
+
+    def real(self):
+        return self._map(REAL, is_real=True)
+
+    def imag(self):
+        return self._map(IMAG, is_real=True)
+
+    def abs(self):
+        return self._map(ABS, is_real=True)
+
+    def sqrt(self):
+        return self._map(SQRT)
+
+    def inv(self):
+        return self._map(INV)
+
+    def safe_inv(self):
+        return self._map(SAFE_INV)
+
+    def sin(self):
+        return self._map(SIN)
+
+    def cos(self):
+        return self._map(COS)
+
+    def pow(self, p):
+        return self._map(POW, float(p))
+
+    def scale(self, s):
+        s = complex(s)
+        return self._map(SCALE, s, is_real=self.is_real and s.imag == 0.0)
+
+    def to_complex(self):
+        return B200Array.view_of(self, self.shape, is_real=False) if self.is_real else self
+
+    def __neg__(self):
+        return self._map(NEG)
+
+    def __add__(self, o):
+        return self._map2(ADD, o)
+
+    def __sub__(self, o):
+        return self._map2(SUB, o)
+
+    def bmul(self, o):
+        return self._map2(MUL, o)
+
+    def bdiv(self, o):
+        return self._map2(DIV, o)
+
+    def __mul__(self, o):
+        if isinstance(o, B200Array):
+            if o.ndim == 0 or self.ndim == 0:
+                return self._map2(MUL, o)
+            raise TypeError("* between tensors is only defined with a 0-dim operand")
+        return self.scale(o)
+
+    __rmul__ = __mul__
+
+    def sum(self):
+        h = C.c_int64()
+        self.ctx.check(self.ctx.L.tne_reduce_sum(self.ctx.h, self.handle, C.byref(h)))
+        return B200Array(h.value, (), self.is_real, self.ctx)
+
+    # -- structure -----------------------------------------------------------------------
+    @staticmethod
+    def view_of(x, shape, is_real=None):
+        h = C.c_int64()
+        x.ctx.check(x.ctx.L.tne_reshape(x.ctx.h, x.handle, len(shape), _i64(shape), C.byref(h)))
+        return B200Array(h.value, shape, x.is_real if is_real is None else is_real, x.ctx)
+
+    def reshape(self, shape):
+        """Column-major reshape; shares storage (Julia ``reshape``)."""
+        return B200Array.view_of(self, tuple(shape))
+
+    def slice(self, lo, count):
+        """``x[lo+1 : lo+count]`` of the flattened tensor (0-based ``lo``)."""
+        h = C.c_int64()
+        self.ctx.check(self.ctx.L.tne_slice(self.ctx.h, self.handle, int(lo), int(count), C.byref(h)))
+        return B200Array(h.value, (int(count),), self.is_real, self.ctx)
+
+    def embed(self, lo, total):
+        """``accum(zeros(total), lo+1:lo+len, self)`` (src/TensorAD/rules.jl:46-55)."""
+        h = C.c_int64()
+        self.ctx.check(self.ctx.L.tne_embed(self.ctx.h, self.handle, int(lo), int(total), C.byref(h)))
+        return B200Array(h.value, (int(total),), self.is_real, self.ctx)
+
+    def fill(self, shape):
+        h = C.c_int64()
+        self.ctx.check(self.ctx.L.tne_fill(self.ctx.h, self.handle, len(shape), _i64(shape), C.byref(h)))
+        return B200Array(h.value, shape, self.is_real, self.ctx)
+
+
+def _free(ctx, handle):
+    try:
+        ctx.L.tne_free(ctx.h, handle)
+    except Exception:
+        pass
+
+
+def concat(arrays):
+    """``vcat(vec.(xs)...)`` (src/peps.jl:202)."""
+    ctx = arrays[0].ctx
+    h = C.c_int64()
+    ctx.check(ctx.L.tne_concat(ctx.h, len(arrays), _i64([a.handle for a in arrays]), C.byref(h)))
+    return B200Array(h.value, (sum(a.size for a in arrays),), all(a.is_real for a in arrays), ctx)
+
+
+def zeros(shape, ctx=None):
+    return B200Array.from_numpy(np.zeros(shape, dtype=np.complex128), ctx)
+
+
+def einsum_device(ixs, xs, iy, conj=None):
+    """``OMEinsum.einsum(EinCode(ixs, iy), xs, size_dict)`` for one or two device tensors."""
+    ctx = xs[0].ctx
+    flat = [l for ix in ixs for l in ix]
+    h = C.c_int64()
+    cj = _i32(conj if conj is not None else [0] * len(xs))
+    ctx.check(ctx.L.tne_einsum(ctx.h, len(xs), _i32(flat), _i32([len(ix) for ix in ixs]),
+                               _i64([x.handle for x in xs]), cj, _i32(iy), len(iy), C.byref(h)))
+    sizes = {}
+    for ix, x in zip(ixs, xs):
+        for l, s in zip(ix, x.shape):
+            sizes[l] = s
+    return B200Array(h.value, tuple(sizes[l] for l in iy), all(x.is_real for x in xs), ctx)

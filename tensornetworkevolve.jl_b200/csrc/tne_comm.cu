@@ -1,0 +1,75 @@
+// Multi-GPU sum of partial energies / gradients over NCCL (K6).  libnccl is loaded lazily with
+// dlopen so that single-GPU use has no NCCL dependency.
+#include <dlfcn.h>
+
+#include "tne_internal.h"
+
+namespace {
+typedef struct { char internal[128]; } nccl_uid;
+typedef int (*fn_get_uid)(nccl_uid*);
+typedef int (*fn_comm_init)(void**, int, nccl_uid, int);
+typedef int (*fn_allreduce)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*fn_group)(void);
+typedef const char* (*fn_errstr)(int);
+struct NcclApi {
+    void* lib = nullptr;
+    fn_get_uid get_uid = nullptr;
+    fn_comm_init comm_init = nullptr;
+    fn_allreduce allreduce = nullptr;
+    fn_group group_start = nullptr, group_end = nullptr;
+    fn_errstr errstr = nullptr;
+};
+NcclApi g_nccl;
+
+int load_nccl(tne_ctx* ctx) {
+    if (g_nccl.lib) return TNE_OK;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+        g_nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (g_nccl.lib) break;
+    }
+    if (!g_nccl.lib) return tne_fail(ctx, TNE_ERR_NCCL, "cannot load libnccl.so.2: %s", dlerror());
+    g_nccl.get_uid = (fn_get_uid)dlsym(g_nccl.lib, "ncclGetUniqueId");
+    g_nccl.comm_init = (fn_comm_init)dlsym(g_nccl.lib, "ncclCommInitRank");
+    g_nccl.allreduce = (fn_allreduce)dlsym(g_nccl.lib, "ncclAllReduce");
+    g_nccl.group_start = (fn_group)dlsym(g_nccl.lib, "ncclGroupStart");
+    g_nccl.group_end = (fn_group)dlsym(g_nccl.lib, "ncclGroupEnd");
+    g_nccl.errstr = (fn_errstr)dlsym(g_nccl.lib, "ncclGetErrorString");
+    if (!g_nccl.get_uid || !g_nccl.comm_init || !g_nccl.allreduce || !g_nccl.group_start || !g_nccl.group_end)
+        return tne_fail(ctx, TNE_ERR_NCCL, "libnccl is missing required symbols");
+    return TNE_OK;
+}
+}  // namespace
+
+extern "C" int tne_nccl_unique_id(void* id128) {
+    TNE_TRY(load_nccl(nullptr));
+    int rc = g_nccl.get_uid((nccl_uid*)id128);
+    return rc == 0 ? TNE_OK : tne_fail(nullptr, TNE_ERR_NCCL, "ncclGetUniqueId failed (%d)", rc);
+}
+
+extern "C" int tne_comm_init(tne_ctx* ctx, const void* id128, int rank, int world) {
+    TNE_TRY(load_nccl(ctx));
+    TNE_CUDA(ctx, cudaSetDevice(ctx->device));
+    nccl_uid uid;
+    memcpy(&uid, id128, sizeof(uid));
+    int rc = g_nccl.comm_init(&ctx->nccl, world, uid, rank);
+    if (rc != 0) return tne_fail(ctx, TNE_ERR_NCCL, "ncclCommInitRank failed: %s", g_nccl.errstr ? g_nccl.errstr(rc) : "?");
+    ctx->rank = rank;
+    ctx->world = world;
+    return TNE_OK;
+}
+
+extern "C" int tne_allreduce_sum(tne_ctx* ctx, int n, const tne_buf* bufs) {
+    if (ctx->world <= 1) return TNE_OK;
+    if (!ctx->nccl) return tne_fail(ctx, TNE_ERR_NCCL, "tne_comm_init has not been called");
+    const int NCCL_DOUBLE = 8, NCCL_SUM = 0;
+    int rc = g_nccl.group_start();
+    for (int i = 0; i < n && rc == 0; ++i) {
+        Buf* b = buf_get(ctx, bufs[i]);
+        if (!b) { g_nccl.group_end(); return TNE_ERR_INVALID; }
+        rc = g_nccl.allreduce(b->ptr(), b->ptr(), (size_t)(2 * b->nelem), NCCL_DOUBLE, NCCL_SUM, ctx->nccl, ctx->stream);
+    }
+    int rc2 = g_nccl.group_end();
+    if (rc != 0 || rc2 != 0) return tne_fail(ctx, TNE_ERR_NCCL, "ncclAllReduce failed: %s", g_nccl.errstr ? g_nccl.errstr(rc ? rc : rc2) : "?");
+    return TNE_OK;
+}

@@ -1,0 +1,103 @@
+// Internal declarations shared by the translation units of libtne_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "tne.h"
+
+typedef double2 cplx;  // interleaved (re, im), identical to Julia's ComplexF64
+
+struct Block {          // one device allocation; views (reshape / slice) share it
+    void* ptr = nullptr;
+    int64_t bytes = 0;
+    struct tne_ctx* ctx = nullptr;
+    ~Block();
+};
+
+struct Buf {
+    std::shared_ptr<Block> block;
+    int64_t offset = 0;                 // in elements
+    std::vector<int64_t> dims;
+    int64_t nelem = 1;
+    cplx* ptr() const { return reinterpret_cast<cplx*>(block->ptr) + offset; }
+};
+
+struct tne_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    std::unordered_map<int64_t, Buf> bufs;
+    int64_t next_handle = 1;
+    // caching allocator for user tensors
+    std::multimap<int64_t, void*> free_blocks;
+    int64_t in_use = 0, peak = 0, reserved = 0;
+    // workspace arena for tree programs
+    void* ws = nullptr;
+    int64_t ws_bytes = 0;
+    int64_t mem_limit = 0;
+    int64_t total_mem = 0;
+    int sm_count = 148;
+    int64_t launches = 0;
+    double stats[6] = {0, 0, 0, 0, 0, 0};
+    // options
+    int64_t opt_recompute_threshold = -1;  // -1: automatic
+    int64_t opt_force_generic = 0;
+    int64_t opt_debug = 0;
+    cplx* one_dev = nullptr;               // device constant 1+0i
+    void* nccl = nullptr;                  // ncclComm_t
+    void* nccl_lib = nullptr;
+    int world = 1, rank = 0;
+};
+
+// ---- error helpers ---------------------------------------------------------------------
+int tne_fail(tne_ctx* ctx, int code, const char* fmt, ...);
+#define TNE_CUDA(ctx, call)                                                                   \
+    do {                                                                                      \
+        cudaError_t e__ = (call);                                                             \
+        if (e__ != cudaSuccess)                                                               \
+            return tne_fail(ctx, e__ == cudaErrorMemoryAllocation ? TNE_ERR_OOM : TNE_ERR_CUDA, \
+                            "CUDA error '%s' at %s:%d", cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+#define TNE_TRY(call)             \
+    do {                          \
+        int rc__ = (call);        \
+        if (rc__ != TNE_OK) return rc__; \
+    } while (0)
+#define TNE_LAUNCH_CHECK(ctx)                 \
+    do {                                      \
+        (ctx)->launches++;                    \
+        TNE_CUDA(ctx, cudaGetLastError());    \
+    } while (0)
+
+// ---- buffers ---------------------------------------------------------------------------
+int buf_new(tne_ctx* ctx, const std::vector<int64_t>& dims, tne_buf* out);
+Buf* buf_get(tne_ctx* ctx, tne_buf h);
+int buf_view(tne_ctx* ctx, const Buf& src, int64_t offset, const std::vector<int64_t>& dims, tne_buf* out);
+int ws_reserve(tne_ctx* ctx, int64_t bytes);
+
+// ---- contraction (tne_contract.cu) ------------------------------------------------------
+struct TensorRef {                  // a tensor operand: labels in memory order (fastest first)
+    cplx* ptr = nullptr;
+    std::vector<int32_t> labels;
+    std::vector<int64_t> dims;
+    std::vector<int64_t> strides;   // in elements; empty = column-major contiguous
+    bool conj = false;
+    int64_t nelem() const { int64_t n = 1; for (auto d : dims) n *= d; return n; }
+};
+// C (+)= A * B over the labels; C's layout is given by its labels/strides.
+int contract_launch(tne_ctx* ctx, const TensorRef& A, const TensorRef& B, const TensorRef& C, bool accumulate,
+                    double alpha_re = 1.0, double alpha_im = 0.0);
+// algorithmic cost of one contraction (SURVEY.md 8(d) accounting)
+void contract_cost(const TensorRef& A, const TensorRef& B, const TensorRef& C, double* flops, double* bytes);
+
+// ---- elementwise helpers used across units ---------------------------------------------
+int launch_fill_zero(tne_ctx* ctx, cplx* p, int64_t n);
+int launch_scale_inplace(tne_ctx* ctx, cplx* p, int64_t n, double re, double im);
+int launch_axpy_dev(tne_ctx* ctx, cplx* y, const cplx* x, int64_t n, const cplx* alpha_dev);

@@ -1,0 +1,321 @@
+"""Host mirror of the OMEinsum objects the reference holds (``EinCode``, ``NestedEinsum``,
+``SlicedEinsum``, ``optimize_code``; used at src/peps.jl:1,84-93,109,321) with the device
+executor behind them.
+
+* ``EinCode(ixs, iy)(xs...)``         -> one ``tne_einsum`` call (unary or binary);
+* ``NestedEinsum`` / ``SlicedEinsum`` -> one ``tne_contract_tree`` call: the whole tree runs as a
+  chain of contraction kernels on the device, intermediates never leave HBM;
+* on ``DiffTensor`` operands the calls are recorded on the TensorAD tape
+  (src/TensorAD/rules.jl:1-8): per binary einsum (second-order capable) or, when
+  ``FUSED_TREES`` is on, as one instruction whose pullback is the fused device reverse pass.
+
+``optimize_code`` offers a deterministic greedy order (``GreedyMethod`` semantics:
+minimise ``size(out) - size(a) - size(b)``) and an explicit left-deep order (boundary sweep).
+"""
+import ctypes as C
+import itertools
+
+import numpy as np
+
+from . import _lib
+from .array import B200Array, einsum_device, _i32, _i64
+
+FUSED_TREES = True          # one tape instruction per tree (first-order only)
+_DIFF_HOOK = None           # installed by .tensorad
+
+
+class EinCode:
+    def __init__(self, ixs, iy):
+        self.ixs = [list(ix) for ix in ixs]
+        self.iy = list(iy)
+
+    def __call__(self, *xs):
+        return einsum(self.ixs, list(xs), self.iy)
+
+
+def einsum(ixs, xs, iy, conj=None):
+    """The single dispatch point (``OMEinsum.einsum``)."""
+    if _DIFF_HOOK is not None and all(_DIFF_HOOK["is"](x) for x in xs):
+        return _DIFF_HOOK["einsum"](ixs, xs, iy)
+    xs = [x if isinstance(x, B200Array) else B200Array.from_numpy(np.asarray(x)) for x in xs]
+    return einsum_device(ixs, xs, iy, conj)
+
+
+class NestedEinsum:
+    """Binary contraction tree; a leaf has ``tensorindex >= 0`` (0-based)."""
+
+    def __init__(self, args=None, eins=None, tensorindex=-1):
+        self.args = args or []
+        self.eins = eins
+        self.tensorindex = tensorindex
+        self._ser = None
+
+    def isleaf(self):
+        return self.tensorindex >= 0
+
+    def leaf_ixs(self):
+        """labels of every leaf, by tensor index, recovered from the tree."""
+        out = {}
+
+        def walk(nd):
+            if nd.isleaf():
+                return
+            for a, ix in zip(nd.args, nd.eins.ixs):
+                if a.isleaf():
+                    out[a.tensorindex] = list(ix)
+                else:
+                    walk(a)
+        walk(self)
+        return [out[i] for i in range(len(out))]
+
+    def __call__(self, *xs):
+        return run_tree(self, [], list(xs))
+
+
+class SlicedEinsum:
+    def __init__(self, slicing, eins):
+        self.slicing = list(slicing)
+        self.eins = eins
+
+    def __call__(self, *xs):
+        return run_tree(self.eins, self.slicing, list(xs))
+
+
+def _unwrap(code):
+    if isinstance(code, SlicedEinsum):
+        return code.eins, code.slicing
+    return code, []
+
+
+# -- serialisation to the C ABI's tne_tree ----------------------------------------------
+class SerializedTree:
+    def __init__(self, nested, slicing, shard=(0, 1)):
+        leaf_ixs = nested.leaf_ixs()
+        n = len(leaf_ixs)
+        children, out_rank, out_labels = [], [], []
+        counter = [n]
+
+        def walk(nd):
+            if nd.isleaf():
+                return nd.tensorindex
+            ids = [walk(a) for a in nd.args]
+            if len(ids) != 2:
+                raise ValueError("only binary trees are supported")
+            children.extend(ids)
+            out_rank.append(len(nd.eins.iy))
+            out_labels.extend(nd.eins.iy)
+            me = counter[0]
+            counter[0] += 1
+            return me
+        walk(nested)
+        self.n_leaves = n
+        self.leaf_ixs = leaf_ixs
+        self._keep = dict(
+            leaf_rank=_i32([len(ix) for ix in leaf_ixs]),
+            leaf_labels=_i32([l for ix in leaf_ixs for l in ix]),
+            node_children=_i32(children),
+            node_out_rank=_i32(out_rank),
+            node_out_labels=_i32(out_labels),
+            sliced=_i32(slicing),
+        )
+        t = _lib.TneTree()
+        t.n_leaves = n
+        t.n_nodes = len(out_rank)
+        t.leaf_rank = self._keep["leaf_rank"]
+        t.leaf_labels = self._keep["leaf_labels"]
+        t.node_children = self._keep["node_children"]
+        t.node_out_rank = self._keep["node_out_rank"]
+        t.node_out_labels = self._keep["node_out_labels"]
+        t.n_sliced = len(slicing)
+        t.sliced_labels = self._keep["sliced"]
+        t.shard_rank, t.shard_world = shard
+        self.struct = t
+        self.root_iy = list(nested.eins.iy)
+
+
+def serialize(code, shard=(0, 1)):
+    nested, slicing = _unwrap(code)
+    key = (tuple(slicing), shard)
+    if nested._ser is None or nested._ser[0] != key:
+        nested._ser = (key, SerializedTree(nested, slicing, shard))
+    return nested._ser[1]
+
+
+def run_tree(nested, slicing, xs, conj=None):
+    if _DIFF_HOOK is not None and all(_DIFF_HOOK["is"](x) for x in xs):
+        return _DIFF_HOOK["tree"](nested, slicing, xs)
+    xs = [x if isinstance(x, B200Array) else B200Array.from_numpy(np.asarray(x)) for x in xs]
+    return contract_tree_device(SlicedEinsum(slicing, nested) if slicing else nested, xs, conj)
+
+
+def contract_tree_device(code, xs, conj=None, shard=(0, 1)):
+    """``tne_contract_tree``: the whole NestedEinsum/SlicedEinsum on the device."""
+    ser = serialize(code, shard)
+    ctx = xs[0].ctx
+    h = C.c_int64()
+    cj = _i32(conj if conj is not None else [0] * len(xs))
+    ctx.check(ctx.L.tne_contract_tree(ctx.h, C.byref(ser.struct), _i64([x.handle for x in xs]), cj, C.byref(h)))
+    sizes = {}
+    for ix, x in zip(ser.leaf_ixs, xs):
+        for l, s in zip(ix, x.shape):
+            sizes[l] = s
+    return B200Array(h.value, tuple(sizes[l] for l in ser.root_iy), all(x.is_real for x in xs), ctx)
+
+
+def expect_terms_device(code, xs, conj, terms, grad_leaves=(), seed=1.0 + 0j, shard=(0, 1)):
+    """``tne_expect_terms``: value (0-dim) and pullbacks w.r.t. ``grad_leaves``.
+
+    ``terms``: list of ``(coef, [(leaf_index, B200Array replacement), ...])``."""
+    ser = serialize(code, shard)
+    ctx = xs[0].ctx
+    arr = (_lib.TneTerm * max(1, len(terms)))()
+    keep = []
+    for k, (coef, repl) in enumerate(terms):
+        coef = complex(coef)
+        arr[k].n_repl = len(repl)
+        for r, (leaf, t) in enumerate(repl):
+            arr[k].leaf[r] = int(leaf)
+            arr[k].repl[r] = t.handle
+            keep.append(t)
+        arr[k].coef_re, arr[k].coef_im = coef.real, coef.imag
+    hv = C.c_int64()
+    hg = (C.c_int64 * max(1, len(grad_leaves)))()
+    cj = _i32(conj if conj is not None else [0] * len(xs))
+    seed = complex(seed)
+    ctx.check(ctx.L.tne_expect_terms(ctx.h, C.byref(ser.struct), _i64([x.handle for x in xs]), cj, len(terms), arr,
+                                     len(grad_leaves), _i32(list(grad_leaves)), seed.real, seed.imag,
+                                     C.byref(hv), hg))
+    sizes = {}
+    for ix, x in zip(ser.leaf_ixs, xs):
+        for l, s in zip(ix, x.shape):
+            sizes[l] = s
+    val = B200Array(hv.value, tuple(sizes[l] for l in ser.root_iy), False, ctx)
+    grads = [B200Array(hg[i], xs[g].shape, False, ctx) for i, g in enumerate(grad_leaves)]
+    return val, grads
+
+
+# -- contraction order ------------------------------------------------------------------
+def optimize_greedy(ixs, iy, size_dict):
+    ixs = [list(ix) for ix in ixs]
+    iy = list(iy)
+    n = len(ixs)
+    nodes = {i: NestedEinsum(tensorindex=i) for i in range(n)}
+    labels = {i: list(ixs[i]) for i in range(n)}
+    count = {}
+    for ix in ixs:
+        for l in set(ix):
+            count[l] = count.get(l, 0) + 1
+    for l in iy:
+        count[l] = count.get(l, 0) + 1
+    size = lambda ls: float(np.prod([size_dict[l] for l in ls])) if ls else 1.0
+    nxt = n
+    while len(nodes) > 1:
+        keys = sorted(nodes)
+        lsets = {k: set(labels[k]) for k in keys}
+        pairs = [(a, b) for ai, a in enumerate(keys) for b in keys[ai + 1:] if lsets[a] & lsets[b]]
+        if not pairs:
+            pairs = [(a, b) for ai, a in enumerate(keys) for b in keys[ai + 1:]]
+        best = None
+        for a, b in pairs:
+            la, lb = labels[a], labels[b]
+            out = [l for l in dict.fromkeys(la + lb) if count[l] - (l in lsets[a]) - (l in lsets[b]) > 0]
+            cost = size(out) - size(la) - size(lb)
+            if best is None or cost < best[0]:
+                best = (cost, a, b, out)
+        _, a, b, out = best
+        if len(nodes) == 2:
+            out = iy
+        for l in lsets[a]:
+            count[l] -= 1
+        for l in lsets[b]:
+            count[l] -= 1
+        for l in set(out):
+            count[l] += 1
+        nodes[nxt] = NestedEinsum([nodes[a], nodes[b]], EinCode([labels[a], labels[b]], out))
+        labels[nxt] = list(out)
+        del nodes[a], nodes[b], labels[a], labels[b]
+        nxt += 1
+    return nodes[max(nodes)]
+
+
+def optimize_sequence(ixs, iy, order):
+    """Left-deep tree absorbing tensors in ``order`` (boundary sweep)."""
+    ixs = [list(ix) for ix in ixs]
+    count = {}
+    for ix in ixs:
+        for l in set(ix):
+            count[l] = count.get(l, 0) + 1
+    for l in iy:
+        count[l] = count.get(l, 0) + 1
+    cur = NestedEinsum(tensorindex=order[0])
+    lab = list(ixs[order[0]])
+    for step, t in enumerate(order[1:]):
+        lb = ixs[t]
+        for l in set(lab):
+            count[l] -= 1
+        for l in set(lb):
+            count[l] -= 1
+        out = [l for l in dict.fromkeys(lab + lb) if count[l] > 0]
+        if step == len(order) - 2:
+            out = list(iy)
+        for l in set(out):
+            count[l] += 1
+        cur = NestedEinsum([cur, NestedEinsum(tensorindex=t)], EinCode([lab, lb], out))
+        lab = out
+    return cur
+
+
+def pick_slices(nested, iy, size_dict, nslices):
+    inter = []
+
+    def walk(nd):
+        if nd.isleaf():
+            return
+        for a in nd.args:
+            walk(a)
+        inter.append(nd.eins.iy)
+    walk(nested)
+    inter.sort(key=lambda ls: -float(np.prod([size_dict[l] for l in ls])) if ls else 0)
+    chosen = []
+    for ls in inter:
+        for l in ls:
+            if l not in chosen and l not in iy and len(chosen) < nslices:
+                chosen.append(l)
+    return chosen
+
+
+def optimize_code(ixs, iy, size_dict, optimizer="greedy", nslices=0, slicing=None):
+    """``optimize_code(EinCode(ixs, iy), size_dict, optimizer, simplifier)`` (src/peps.jl:87,91).
+
+    ``optimizer``: ``"greedy"`` or an explicit leaf order (list).  ``nslices`` / ``slicing``
+    produce a ``SlicedEinsum`` (the role of ``TreeSA(nslices=k)``, test/peps.jl:9)."""
+    if len(ixs) == 1:
+        raise ValueError("a single-tensor network needs no order")
+    if isinstance(optimizer, (list, tuple)):
+        nested = optimize_sequence(ixs, iy, list(optimizer))
+    else:
+        nested = optimize_greedy(ixs, iy, size_dict)
+    if slicing:
+        return SlicedEinsum(list(slicing), nested)
+    if nslices > 0:
+        return SlicedEinsum(pick_slices(nested, iy, size_dict, nslices), nested)
+    return nested
+
+
+def tree_cost(code, size_dict):
+    """(flops, bytes, largest intermediate) with SURVEY.md 8(d)'s accounting."""
+    nested, _ = _unwrap(code)
+    tot = [0.0, 0.0, 0.0]
+    size = lambda ls: float(np.prod([size_dict[l] for l in ls])) if ls else 1.0
+
+    def walk(nd):
+        if nd.isleaf():
+            return
+        for a in nd.args:
+            walk(a)
+        ia, ib = nd.eins.ixs
+        tot[0] += 8.0 * size(list(dict.fromkeys(ia + ib)))
+        tot[1] += 16.0 * (size(ia) + size(ib) + size(nd.eins.iy))
+        tot[2] = max(tot[2], size(nd.eins.iy))
+    walk(nested)
+    return tuple(tot)

@@ -1,0 +1,517 @@
+"""PEPS state layer on the device: same names, argument meaning and error behaviour as
+``src/peps.jl`` (Julia's ``f!`` is spelled ``f_``), with ``vertex_tensors`` holding
+:class:`B200Array` (or ``DiffTensor`` of them).  Sites, labels and bond numbering are 1-based
+exactly like the reference.
+
+Every tensor operation is a call into ``libtne_b200.so``:
+``inner_product`` / ``statetensor`` run the PEPS's optimised code as one device tree program,
+``expect`` over an ``Add`` is one ``tne_expect_terms`` call (terms share sub-contractions),
+``apply_onbond_`` is the fused device bond update (gate + SVD truncation).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from . import array as _arr
+from . import einsum as es
+from . import tensorad as ad
+from . import yao
+from .array import B200Array
+from .tensorad import DiffTensor
+
+LOG = []  # truncation messages (@info at src/peps.jl:386)
+
+
+def _isdiff(x):
+    return isinstance(x, DiffTensor)
+
+
+def _dev(x):
+    """numpy / B200Array / DiffTensor -> B200Array data."""
+    if isinstance(x, DiffTensor):
+        return x.data
+    if isinstance(x, B200Array):
+        return x
+    return B200Array.from_numpy(np.asarray(x))
+
+
+def _conj(x):
+    return ad.conj(x) if _isdiff(x) else x.conj()
+
+
+def _reshape(x, shape):
+    return ad.reshape(x, tuple(shape)) if _isdiff(x) else x.reshape(tuple(shape))
+
+
+class PEPS:
+    """``PEPS{T,NF,LT}`` (src/peps.jl:4); fields as in ``SimplePEPS`` (src/peps.jl:36-50)."""
+
+    kind = "simple"
+
+    def __init__(self, physical_labels, virtual_labels, vertex_labels, vertex_tensors, max_index,
+                 code_statetensor, code_inner_product, Dmax, eps, nflavor=2, bond_tensors=None):
+        self.physical_labels = list(physical_labels)
+        self.virtual_labels = list(virtual_labels)
+        self.vertex_labels = [list(l) for l in vertex_labels]
+        self.vertex_tensors = list(vertex_tensors)
+        self.max_index = max_index
+        self.code_statetensor = code_statetensor
+        self.code_inner_product = code_inner_product
+        self.Dmax = Dmax
+        self.eps = eps
+        self.nflavor = nflavor
+        if bond_tensors is not None:
+            self.bond_tensors = list(bond_tensors)
+
+    def alllabels(self):  # src/peps.jl:96, 171
+        if self.kind == "vidal":
+            return self.vertex_labels + [[l] for l in self.virtual_labels]
+        return self.vertex_labels
+
+    def alltensors(self):  # src/peps.jl:98, 172
+        if self.kind == "vidal":
+            return self.vertex_tensors + self.bond_tensors
+        return self.vertex_tensors
+
+    def copy(self):  # src/peps.jl:99-101 (the Vidal method at :175-177 reads a missing field upstream)
+        return replace_tensors(self, [ad.copy(t) if _isdiff(t) else t.copy() for t in self.alltensors()])
+
+    def __repr__(self):  # src/peps.jl:236-241
+        return "%s (Dmax = %d, ϵ = %g)\n # of spins = %d\n # of virtual degrees = %d" % (
+            type(self).__name__, self.Dmax, self.eps, nsite(self), len(self.virtual_labels))
+
+
+class SimplePEPS(PEPS):
+    kind = "simple"
+
+
+class VidalPEPS(PEPS):
+    kind = "vidal"
+
+
+def _optimized_code(alllabels, physical_labels, virtual_labels, max_ind, nflavor, D, optimizer, nslices):
+    """src/peps.jl:84-93."""
+    size_dict = {l: nflavor for l in physical_labels}
+    size_dict.update({l: D for l in virtual_labels})
+    st_opt = "greedy" if isinstance(optimizer, (list, tuple)) else optimizer
+    code_st = es.optimize_code(alllabels, physical_labels, size_dict, st_opt, nslices) if len(alllabels) > 1 else None
+    rep = {l: max_ind + i + 1 for i, l in enumerate(virtual_labels)}
+    for l in rep.values():
+        size_dict[l] = D
+    ixs = [list(l) for l in alllabels] + [[rep.get(x, x) for x in l] for l in alllabels]
+    code_ip = es.optimize_code(ixs, [], size_dict, optimizer, nslices)
+    return code_st, code_ip
+
+
+def make_peps(kind, vertex_labels, vertex_tensors, virtual_labels, Dmax, eps, nflavor=2, bond_tensors=None,
+              optimizer="greedy", nslices=0):
+    """The label-deriving constructors, src/peps.jl:69-82 and :142-151."""
+    physical_labels = []
+    for vl in vertex_labels:
+        ph = [l for l in vl if l not in virtual_labels]
+        if len(ph) != 1:
+            raise ValueError("each vertex needs exactly one physical label")
+        physical_labels.append(ph[0])
+    for t, vl in zip(vertex_tensors, vertex_labels):  # src/peps.jl:73-75
+        for s, l in zip(t.shape, vl):
+            if (l in physical_labels and s != nflavor) or (l not in physical_labels and s > Dmax):
+                raise ValueError("Input tensor shape error, either: \n 1. physical degrees of freedom do not match, "
+                                 "\n 2. or input tensor virtual degrees of freedom larger than `Dmax = %d`." % Dmax)
+    max_ind = max(max(physical_labels), max(virtual_labels))
+    alll = [list(l) for l in vertex_labels]
+    if kind == "vidal":
+        alll = alll + [[l] for l in virtual_labels]
+    cst, cip = _optimized_code(alll, physical_labels, virtual_labels, max_ind, nflavor, Dmax, optimizer, nslices)
+    cls = VidalPEPS if kind == "vidal" else SimplePEPS
+    return cls(physical_labels, virtual_labels, vertex_labels, vertex_tensors, max_ind, cst, cip, Dmax, eps,
+               nflavor, bond_tensors)
+
+
+def replace_tensors(peps, tensors):  # src/peps.jl:222-234
+    tensors = list(tensors)
+    if peps.kind == "vidal":
+        nv = nsite(peps)
+        return VidalPEPS(peps.physical_labels, peps.virtual_labels, peps.vertex_labels, tensors[:nv], peps.max_index,
+                         peps.code_statetensor, peps.code_inner_product, peps.Dmax, peps.eps, peps.nflavor,
+                         tensors[nv:])
+    return SimplePEPS(peps.physical_labels, peps.virtual_labels, peps.vertex_labels, tensors, peps.max_index,
+                      peps.code_statetensor, peps.code_inner_product, peps.Dmax, peps.eps, peps.nflavor)
+
+
+def conj(peps):  # src/peps.jl:178-180
+    return replace_tensors(peps, [_conj(t) for t in peps.alltensors()])
+
+
+# -- label API, src/peps.jl:183-199 -----------------------------------------------------
+def getvlabel(peps, i):
+    return peps.vertex_labels[i - 1]
+
+
+def getphysicallabel(peps, i):
+    return peps.physical_labels[i - 1]
+
+
+def newlabel(peps, offset):
+    return peps.max_index + offset
+
+
+def virtualbonds(peps):
+    bs = []
+    for b in peps.virtual_labels:
+        i, j = [k + 1 for k, l in enumerate(peps.vertex_labels) if b in l]
+        bs.append((i, j))
+    return bs
+
+
+def findbondtensor(peps, b):
+    return peps.bond_tensors[peps.virtual_labels.index(b)]
+
+
+def nsite(peps):
+    return len(peps.physical_labels)
+
+
+def nflavor(peps):
+    return peps.nflavor
+
+
+def Dmax(peps):
+    return peps.Dmax
+
+
+# -- variables, src/peps.jl:202-220 -----------------------------------------------------
+def variables(peps):
+    """``vcat(vec.(alltensors(peps))...)`` as a device vector."""
+    return _arr.concat([_dev(t) for t in peps.alltensors()])
+
+
+def load_variables_(peps, variables):
+    variables = _dev(variables)
+    k = 0
+    nv = len(peps.vertex_tensors)
+    for idx, t in enumerate(peps.alltensors()):
+        new = variables.slice(k, t.size).reshape(t.shape).copy()
+        if idx < nv:
+            peps.vertex_tensors[idx] = new
+        else:
+            peps.bond_tensors[idx - nv] = new
+        k += t.size
+    return peps
+
+
+def load_variables(peps, variables):
+    if peps.kind != "simple":
+        raise TypeError("load_variables is only defined for SimplePEPS (src/peps.jl:212)")
+    if not isinstance(variables, (DiffTensor, B200Array)):
+        variables = B200Array.from_numpy(np.asarray(variables))
+    ats = peps.alltensors()
+    tensors, k = [], 0
+    for t in ats:
+        if _isdiff(variables):
+            tensors.append(ad.reshape(variables[k:k + t.size], t.shape))
+        else:
+            tensors.append(variables.slice(k, t.size).reshape(t.shape))
+        k += t.size
+    return replace_tensors(peps, tensors)
+
+
+# -- factories, src/peps.jl:244-280 -----------------------------------------------------
+def _peps_zero_state(kind, g, D, nflavor=2, Dmax=None, eps=1e-12, optimizer="greedy", nslices=0):
+    Dmax = D if Dmax is None else Dmax
+    nv, ne = g.nv(), g.ne()
+    virtual_labels = list(range(nv + 1, nv + ne + 1))
+    edge_map = dict(zip(g.edges(), virtual_labels))
+    vertex_labels, vertex_tensors = [], []
+    for i in range(1, nv + 1):
+        labs = [i] + [edge_map.get((i, nb), edge_map.get((nb, i), 0)) for nb in g.neighbors(i)]
+        t = np.zeros([nflavor] + [D] * g.degree(i), dtype=np.complex128)
+        t[(0,) * t.ndim] = 1
+        vertex_labels.append(labs)
+        vertex_tensors.append(B200Array.from_numpy(t))
+    if any(0 in vl for vl in vertex_labels):
+        raise ValueError("incorrect input labels1")
+    bonds = [B200Array.from_numpy(np.ones(D, dtype=np.complex128)) for _ in range(ne)] if kind == "vidal" else None
+    return make_peps(kind, vertex_labels, vertex_tensors, virtual_labels, Dmax, eps, nflavor, bonds, optimizer, nslices)
+
+
+def zero_simplepeps(g, D, **kw):
+    return _peps_zero_state("simple", g, D, **kw)
+
+
+def zero_vidalpeps(g, D, **kw):
+    return _peps_zero_state("vidal", g, D, **kw)
+
+
+def randn_(peps, rng):
+    """``randn!(peps)`` (src/peps.jl:275-280): iid circular complex normal with unit variance, filled
+    in ``alltensors`` order, column-major, from a numpy Generator."""
+    new = []
+    for t in peps.alltensors():
+        n = t.size
+        z = (rng.standard_normal(n) + 1j * rng.standard_normal(n)) / np.sqrt(2.0)
+        new.append(B200Array.from_numpy(z.reshape(t.shape, order="F")))
+    nv = len(peps.vertex_tensors)
+    peps.vertex_tensors = new[:nv]
+    if peps.kind == "vidal":
+        peps.bond_tensors = new[nv:]
+    return peps
+
+
+def rand_simplepeps(g, D, rng, **kw):
+    return randn_(zero_simplepeps(g, D, **kw), rng)
+
+
+def rand_vidalpeps(g, D, rng, **kw):
+    return randn_(zero_vidalpeps(g, D, **kw), rng)
+
+
+def from_numpy_tensors(template, tensors):
+    """Load host arrays (Julia shapes) into a PEPS with ``template``'s structure."""
+    return replace_tensors(template, [B200Array.from_numpy(np.asarray(t)) for t in tensors])
+
+
+# -- scalar ops and norm, src/peps.jl:283-306 -------------------------------------------
+def rmul_(peps, c):
+    f = complex(c) ** (1.0 / nsite(peps)) if np.iscomplexobj(c) else c ** (1.0 / nsite(peps))
+    peps.vertex_tensors = [t * f for t in peps.vertex_tensors]
+    return peps
+
+
+def mul(peps, c):
+    """``peps * c`` for a number (src/peps.jl:288-291) or a 0-dim array (src/peps.jl:292-295)."""
+    n = nsite(peps)
+    if _isdiff(c):
+        f = ad.bpow(c, 1.0 / n)
+        tensors = [t * f for t in peps.vertex_tensors]
+    elif isinstance(c, B200Array):
+        f = c.pow(1.0 / n)
+        tensors = [t * (DiffTensor(f, requires_grad=False) if _isdiff(t) else f) for t in peps.vertex_tensors]
+    else:
+        f = c ** (1.0 / n)
+        tensors = [t * f for t in peps.vertex_tensors]
+    rest = peps.alltensors()[len(peps.vertex_tensors):]
+    return replace_tensors(peps, tensors + list(rest))
+
+
+def inner_product(p1, p2):  # src/peps.jl:106-110
+    p1c = conj(p1)
+    return p1.code_inner_product(*p1c.alltensors(), *p2.alltensors())
+
+
+def norm(peps):  # src/peps.jl:302
+    ip = inner_product(peps, peps)
+    if _isdiff(ip):
+        return ad.bsqrt(ad.babs(ip))
+    return ip.abs().sqrt()
+
+
+def normalize_(peps):  # src/peps.jl:303-306
+    nm = inner_product(peps, peps).abs().sqrt()
+    return rmul_(peps, 1.0 / nm.item())
+
+
+def statetensor(peps):  # src/peps.jl:320-322
+    if peps.code_statetensor is None:
+        return peps.alltensors()[0]
+    return peps.code_statetensor(*peps.alltensors())
+
+
+def vec(peps):  # src/peps.jl:319
+    return np.reshape(_dev(statetensor(peps)).to_numpy(), -1, order="F")
+
+
+statevec = vec
+
+
+# -- gates, src/peps.jl:329-430 ---------------------------------------------------------
+def _onsite_code(peps, i):
+    old = getvlabel(peps, i)
+    mlabel = [newlabel(peps, 1), getphysicallabel(peps, i)]
+    return es.EinCode([old, mlabel], [mlabel[0] if l == mlabel[1] else l for l in old])
+
+
+def _as_operand(peps, m):  # array_match_type, src/peps.jl:198-199
+    if isinstance(m, (DiffTensor, B200Array)):
+        return m
+    m = B200Array.from_numpy(np.asarray(m, dtype=np.complex128))
+    return DiffTensor(m) if _isdiff(peps.vertex_tensors[0]) else m
+
+
+def apply_onsite_(peps, i, mat):  # src/peps.jl:329-336
+    if mat.shape[0] != mat.shape[1]:
+        raise AssertionError("size(mat, 1) == size(mat, 2)")
+    peps.vertex_tensors[i - 1] = _onsite_code(peps, i)(peps.vertex_tensors[i - 1], _as_operand(peps, mat))
+    return peps
+
+
+def apply_onsite(peps, i, mat):  # src/peps.jl:338-347
+    if mat.shape[0] != mat.shape[1]:
+        raise AssertionError("size(mat, 1) == size(mat, 2)")
+    code = _onsite_code(peps, i)
+    m = _as_operand(peps, mat)
+    tensors = [code(t, m) if j == i - 1 else t for j, t in enumerate(peps.vertex_tensors)]
+    rest = peps.alltensors()[len(peps.vertex_tensors):]
+    return replace_tensors(peps, tensors + list(rest))
+
+
+def bond_job(peps, i, j, mat):
+    """Describe ``apply_onbond!(peps, i, j, mat)`` for ``tne_apply_onbond_batched``."""
+    li, lj = getvlabel(peps, i), getvlabel(peps, j)
+    shared = [l for l in li if l in lj]
+    if len(shared) != 1:
+        raise AssertionError("length(shared_label) == 1")
+    job = _lib.TneBondJob()
+    job.ti = _dev(peps.vertex_tensors[i - 1]).handle
+    job.tj = _dev(peps.vertex_tensors[j - 1]).handle
+    job.axis_i = li.index(shared[0])
+    job.axis_j = lj.index(shared[0])
+    g = np.asarray(mat, dtype=np.complex128).reshape(4, 4, order="F")  # (o_i + 2 o_j, i_i + 2 i_j)
+    flat = np.asfortranarray(g).reshape(-1, order="F").view(np.float64)
+    for q in range(32):
+        job.gate[q] = flat[q]
+    job.Dmax = peps.Dmax
+    job.eps = peps.eps
+    job.vidal = 1 if peps.kind == "vidal" else 0
+    if peps.kind == "vidal":
+        for q, b in enumerate(li):
+            job.lambda_i[q] = 0 if q == 0 else _dev(findbondtensor(peps, b)).handle
+        for q, b in enumerate(lj):
+            job.lambda_j[q] = 0 if q == 0 else _dev(findbondtensor(peps, b)).handle
+    return job, shared[0]
+
+
+def apply_onbond_(peps, i, j, mat):  # src/peps.jl:353-417
+    if getphysicallabel(peps, i) != getvlabel(peps, i)[0] or getphysicallabel(peps, j) != getvlabel(peps, j)[0]:
+        raise ValueError("the device bond update expects the physical leg first (src/peps.jl:253)")
+    job, shared = bond_job(peps, i, j, mat)
+    ctx = _dev(peps.vertex_tensors[i - 1]).ctx
+    jobs = (_lib.TneBondJob * 1)(job)
+    ctx.check(ctx.L.tne_apply_onbond_batched(ctx.h, 1, jobs))
+    job = jobs[0]
+    si = list(_dev(peps.vertex_tensors[i - 1]).shape)
+    sj = list(_dev(peps.vertex_tensors[j - 1]).shape)
+    full = min(int(np.prod(si)) // si[job.axis_i], int(np.prod(sj)) // sj[job.axis_j])
+    si[job.axis_i] = job.kept
+    sj[job.axis_j] = job.kept
+    if job.kept < full:
+        LOG.append("truncation error is %r" % job.trunc_err)
+    peps.vertex_tensors[i - 1] = B200Array(job.ti_out, si, False, ctx)
+    peps.vertex_tensors[j - 1] = B200Array(job.tj_out, sj, False, ctx)
+    s = B200Array(job.s_out, (job.kept,), True, ctx)
+    if peps.kind == "vidal":
+        peps.bond_tensors[peps.virtual_labels.index(shared)] = s
+    return peps
+
+
+# -- Yao glue, src/peps.jl:432-477 ------------------------------------------------------
+def apply_block_(peps, block):
+    """``YaoBlocks.unsafe_apply!`` methods, src/peps.jl:437-460."""
+    if isinstance(block, yao.Put) and len(block.locs) == 1:
+        return apply_onsite_(peps, block.locs[0], block.content)
+    if isinstance(block, yao.Kron):
+        for loc, m in zip(block.locs, block.subblocks):
+            peps = apply_onsite_(peps, loc, m)
+        return peps
+    if isinstance(block, yao.Control):
+        return apply_block_(peps, yao.Put(block.n, (block.ctrl, block.loc), block.two_site_matrix()))
+    if isinstance(block, yao.Scale):
+        return rmul_(apply_block_(peps, block.content), (1.0 + 0j) * block.factor)
+    if isinstance(block, yao.Put) and len(block.locs) == 2:
+        return apply_onbond_(peps, block.locs[0], block.locs[1], np.reshape(block.content, (2, 2, 2, 2), order="F"))
+    raise TypeError("no apply! method for %s" % type(block).__name__)
+
+
+def apply_block(peps, block):
+    """Non-mutating ``YaoBlocks.apply`` (src/peps.jl:437-455); a two-site ``put`` falls back to
+    ``apply!(copy(peps), block)`` like Yao's generic method (src/peps.jl:456)."""
+    if isinstance(block, yao.Put) and len(block.locs) == 1:
+        return apply_onsite(peps, block.locs[0], block.content)
+    if isinstance(block, yao.Kron):
+        for loc, m in zip(block.locs, block.subblocks):
+            peps = apply_onsite(peps, loc, m)
+        return peps
+    if isinstance(block, yao.Control):
+        return apply_block(peps, yao.Put(block.n, (block.ctrl, block.loc), block.two_site_matrix()))
+    if isinstance(block, yao.Scale):
+        return mul(apply_block(peps, block.content), (1.0 + 0j) * block.factor)
+    if isinstance(block, yao.Put) and len(block.locs) == 2:
+        return apply_block_(peps.copy(), block)
+    raise TypeError("no apply method for %s" % type(block).__name__)
+
+
+def _term_replacements(pb, block):
+    """(coef, {site: replacement tensor}) of one Hamiltonian term applied to the ket, or None if the
+    term is not a product of one-site operators (then the generic path is used)."""
+    coef = 1.0 + 0j
+    while isinstance(block, yao.Scale):
+        coef *= block.factor
+        block = block.content
+    if isinstance(block, yao.Put) and len(block.locs) == 1:
+        pairs = [(block.locs[0], block.content)]
+    elif isinstance(block, yao.Kron):
+        pairs = list(zip(block.locs, block.subblocks))
+    else:
+        return None
+    repl = {}
+    for loc, m in pairs:
+        base = repl.get(loc, _dev(pb.vertex_tensors[loc - 1]))
+        old = getvlabel(pb, loc)
+        mlabel = [newlabel(pb, 1), getphysicallabel(pb, loc)]
+        repl[loc] = es.einsum([old, mlabel], [base, B200Array.from_numpy(np.asarray(m, dtype=np.complex128))],
+                              [mlabel[0] if l == mlabel[1] else l for l in old])
+    return coef, repl
+
+
+def expect(op, pa, pb, shard=(0, 1)):  # src/peps.jl:469-477
+    """``expect(op, pa, pb)``.  An ``Add`` of one-site-product terms runs as ONE device program in which
+    the terms share sub-contractions; anything else follows the reference term by term.  ``shard =
+    (rank, world)`` keeps only this rank's terms (the caller sums the partial values)."""
+    if isinstance(op, yao.Add):
+        fused = es.FUSED_TREES and len(pa.alltensors()) == len(pb.alltensors())
+        terms = [_term_replacements(pb, t) for t in op.blocks] if fused else None
+        if fused and all(t is not None for t in terms) and all(_isdiff(t) for t in pa.alltensors()) == any(_isdiff(t) for t in pa.alltensors()):
+            return _expect_fused(terms, pa, pb, shard)
+        out = None
+        for k, term in enumerate(op.blocks):
+            if k % shard[1] != shard[0]:
+                continue
+            e = expect(term, pa, pb)
+            out = e if out is None else out + e
+        return out
+    opb = apply_block(pb, op)
+    return inner_product(pa, opb)
+
+
+def _expect_fused(terms, pa, pb, shard):
+    code = pa.code_inner_product
+    nt = len(pa.alltensors())
+    bra = pa.alltensors()
+    ket = pb.alltensors()
+    diff = any(_isdiff(t) for t in bra)
+    leaves = [_dev(t) for t in bra] + [_dev(t) for t in ket]
+    cj = [1] * nt + [0] * nt
+    tlist = []
+    for k, (coef, repl) in enumerate(terms):
+        if k % shard[1] != shard[0]:
+            continue
+        tlist.append((coef, [(nt + site - 1, t) for site, t in sorted(repl.items())]))
+    if not diff:
+        val, _ = es.expect_terms_device(code, leaves, cj, tlist)
+        return val
+    val, _ = es.expect_terms_device(code, leaves, cj, tlist)
+    cache = {}
+    gl = [i for i in range(nt) if ad.requires_grad(bra[i])]
+
+    def mk(i):
+        def back(dy):
+            key = id(dy)
+            if key not in cache:
+                cache.clear()
+                _, grads = es.expect_terms_device(code, leaves, cj, tlist, gl, 1.0 + 0j)
+                cache[key] = (dy, dict(zip(gl, grads)))
+            g = cache[key][1][i]
+            # bra leaves enter conjugated: the pullback is antilinear in the cotangent
+            return DiffTensor(g.bmul(dy.data.to_complex().conj()), requires_grad=False)
+        return back
+    return ad.difftensor(val, "expect", *[(bra[i], mk(i)) for i in range(nt)])

@@ -1,0 +1,62 @@
+"""TEBD driver on the device: ``rydberg_tebd!`` of src/tebd.jl with the same keyword arguments.
+Each edge's 4x4 gate ``exp(-i dt h_ij)`` is built on the host (it depends only on C, delta, omega
+and the two vertex degrees) and applied by the fused device bond update."""
+import numpy as np
+
+from . import yao
+from . import peps as P
+from .graphs import SimpleGraph
+
+
+def cterm(C):  # src/tebd.jl:3-5
+    return C * yao.kron_mat(yao.P1, yao.P1)
+
+
+def zterm(delta):  # src/tebd.jl:7-9 (Z, not n -- as in the reference)
+    return delta * yao.Z
+
+
+def xterm(omega):  # src/tebd.jl:11-13
+    return omega / 2 * yao.X
+
+
+def bond_hamiltonian(C, delta, omega, di, dj):
+    """``hi`` of src/tebd.jl:19 as a 4x4 matrix (first site = least-significant bit)."""
+    I = yao.I2
+    return (cterm(C) + yao.kron_mat(xterm(omega / di), I) + yao.kron_mat(I, xterm(omega / dj))
+            + yao.kron_mat(zterm(delta / di), I) + yao.kron_mat(I, zterm(delta / dj)))
+
+
+def rydberg_tebd_sweep_(reg, g, C, delta, omega, dt):  # src/tebd.jl:15-23
+    n = reg.n if isinstance(reg, yao.ArrayReg) else P.nsite(reg)
+    for (src, dst) in g.edges():
+        hi = bond_hamiltonian(C, delta, omega, g.degree(src), g.degree(dst))
+        block = yao.put(n, (src, dst), yao.time_evolve(hi, dt))
+        if isinstance(reg, yao.ArrayReg):
+            reg.apply_(block)
+        else:
+            P.apply_block_(reg, block)
+    return reg
+
+
+def rydberg_tebd_(reg, g=None, *, t, C, delta, omega, nstep):  # src/tebd.jl:25-38
+    if g is None:
+        g = SimpleGraph(P.nsite(reg))
+        for i, j in P.virtualbonds(reg):
+            g.add_edge(i, j)
+    dt = t / nstep
+    for _ in range(nstep - 1):  # sic: nstep-1 sweeps (src/tebd.jl:27)
+        rydberg_tebd_sweep_(reg, g, C, delta, omega, dt)
+    return reg
+
+
+def rydberg_hamiltonian(g, C, delta, omega):
+    """Synthetic benchmark Hamiltonian: ``C P1_i P1_j`` per edge as ``kron`` plus
+    ``(omega/2) X + delta Z`` per site as a one-site ``put`` -- the terms of src/tebd.jl:3-13."""
+    n = g.nv()
+    blocks = []
+    for (i, j) in g.edges():
+        blocks.append(yao.kron(n, (i, C * yao.P1), (j, yao.P1)))
+    for i in g.vertices():
+        blocks.append(yao.put(n, i, xterm(omega) + zterm(delta)))
+    return yao.Add(*blocks)
