@@ -53,3 +53,22 @@ def to_device_hamiltonian(tne, h):
             return Y.Control(b.n, b.ctrl, b.loc, b.content)
         raise TypeError(type(b))
     return conv(h)
+
+
+def dense_apply(block, psi):
+    """``mat(block) * psi`` without forming the 2^n x 2^n matrix (works up to ~20 sites)."""
+    if isinstance(block, OY.Add):
+        return sum(dense_apply(b, psi) for b in block.blocks)
+    if isinstance(block, OY.Scale):
+        return block.factor * dense_apply(block.content, psi)
+    reg = OY.ArrayReg(psi)
+    if isinstance(block, OY.Put):
+        reg._apply_locs(block.locs, block.content)
+    elif isinstance(block, OY.Kron):
+        for l, m in zip(block.locs, block.subblocks):
+            reg._apply_locs((l,), m)
+    elif isinstance(block, OY.Control):
+        reg._apply_locs((block.ctrl, block.loc), block.two_site_matrix())
+    else:
+        raise TypeError(type(block))
+    return reg.state

@@ -1,0 +1,183 @@
+"""Parity of the CUDA path (through the C ABI, via the ctypes host mirror) against the oracle on identical
+seeded inputs.  Tolerance: 1e-10 relative (BASELINE.json north_star) for energies, norms, gradients."""
+import numpy as np
+import pytest
+
+from oracle import einsum as OE, graphs as OG, peps as OP, tebd as OT, tensorad as OAD, timeevolve as OTE, yao as OY
+from helpers import (device_peps_like, oracle_peps, rel, seed_for, sweep_order, to_device_hamiltonian)
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+def crand(rng, shape):
+    return rng.standard_normal(shape) + 1j * rng.standard_normal(shape)
+
+
+# -- einsum (OMEinsum.einsum dispatch point) -------------------------------------------------------
+@pytest.mark.parametrize("force_generic", [0, 1])
+def test_binary_einsum_shapes(tne, force_generic):
+    ctx = tne.context()
+    ctx.set_option("force_generic_kernel", force_generic)
+    rng = np.random.default_rng(0)
+    cases = [
+        ([[1, 2, 3, 4], [4, 3, 5, 1]], [(3, 4, 2, 5), (5, 2, 6, 3)], [5, 2, 1]),      # batch label 1
+        ([[1, 2], [2, 3]], [(7, 5), (5, 9)], [1, 3]),                                   # plain matmul
+        ([[1, 2, 3], [3, 2, 1]], [(4, 3, 5), (5, 3, 4)], []),                            # full contraction
+        ([[1, 2], [3, 4]], [(3, 4), (2, 5)], [4, 1, 3, 2]),                              # outer product + permute
+        ([[1, 2, 3, 4, 5, 6], [2, 7, 5]], [(4, 4, 4, 4, 4, 4), (4, 2, 4)], [1, 3, 4, 6, 7]),  # absorb shape
+        ([[1, 2, 3], [1, 2, 4]], [(64, 64, 3), (64, 64, 5)], [3, 4]),                   # reduce shape (long K)
+        ([[1, 2, 3]], [(3, 4, 5)], [3, 1, 2]),                                           # unary permute
+        ([[1, 2, 3]], [(3, 4, 5)], [2]),                                                 # unary sum
+    ]
+    for ixs, shapes, iy in cases:
+        xs = [crand(rng, s) for s in shapes]
+        ref = OE.einsum_raw(ixs, xs, iy)
+        for conj in ([0] * len(xs), [1] * len(xs)):
+            got = tne.einsum.einsum(ixs, [tne.B200Array.from_numpy(x) for x in xs], iy, conj=conj).to_numpy()
+            want = ref if not conj[0] else OE.einsum_raw(ixs, [np.conj(x) for x in xs], iy)
+            assert rel(got, want) < 1e-13, (ixs, iy, conj)
+    ctx.set_option("force_generic_kernel", 0)
+
+
+def test_elementwise_ops(tne):
+    rng = np.random.default_rng(1)
+    a = crand(rng, (5, 7)) + 2
+    x = tne.B200Array.from_numpy(a)
+    assert rel(x.conj().to_numpy(), np.conj(a)) < 1e-15
+    assert rel(x.abs().to_numpy(), np.abs(a)) < 1e-15
+    assert rel(x.sqrt().to_numpy(), np.sqrt(a)) < 1e-14
+    assert rel(x.inv().to_numpy(), 1 / a) < 1e-14
+    assert rel(x.pow(1 / 9).to_numpy(), a ** (1 / 9)) < 1e-14
+    assert rel((x * (2 - 1j)).to_numpy(), a * (2 - 1j)) < 1e-15
+    assert rel((x + x).to_numpy(), 2 * a) < 1e-15
+    assert rel(x.slice(3, 10).to_numpy(), a.reshape(-1, order="F")[3:13]) < 1e-15
+
+
+# -- the reference's test graph (test/peps.jl) ------------------------------------------------------
+@pytest.mark.parametrize("kind", ["simple", "vidal"])
+def test_statevec_inner_norm(tne, kind):
+    g = OG.test_graph()
+    op1, op2 = oracle_peps(g, 2, 11, kind, Dmax=4), oracle_peps(g, 2, 12, kind, Dmax=4)
+    dp1, dp2 = device_peps_like(tne, op1, g, 2, Dmax=4), device_peps_like(tne, op2, g, 2, Dmax=4)
+    assert rel(tne.vec(dp1), OP.vec(op1)) < TOL
+    assert rel(tne.inner_product(dp1, dp2).to_numpy(), OP.inner_product(op1, op2)) < TOL
+    assert rel(tne.norm(dp1).to_numpy(), OP.norm(op1)) < TOL
+    tne.normalize_(dp1)
+    assert abs(tne.norm(dp1).item() - 1) < 1e-12
+
+
+def test_known_answers_on_device(tne):  # test/peps.jl:11,17
+    g = tne.graph_from_edges(5, OG.test_graph().edges())
+    p = tne.zero_vidalpeps(g, 2, nslices=3)
+    e1 = np.zeros(32, complex); e1[0] = 1
+    assert np.allclose(tne.vec(p), e1)
+    tne.apply_onsite_(p, 1, OY.X)
+    e2 = np.zeros(32, complex); e2[1] = 1
+    assert np.allclose(tne.vec(p), e2)
+
+
+def test_expect_generic_blocks(tne):  # test/peps.jl:88-110 on the device (one-site-product terms fused)
+    g = OG.test_graph()
+    rng = np.random.default_rng(5)
+    n = 5
+    blocks = []
+    for (i, j) in g.edges():
+        blocks.append(rng.random() * OY.kron(n, (i, OY.Y), (j, OY.Y)))
+    for i in g.vertices():
+        blocks.append(OY.put(n, i, rng.random() * OY.X))
+    h = OY.Add(*blocks)
+    op1, op2 = oracle_peps(g, 2, 21, Dmax=4), oracle_peps(g, 2, 22, Dmax=4)
+    dp1, dp2 = device_peps_like(tne, op1, g, 2, Dmax=4), device_peps_like(tne, op2, g, 2, Dmax=4)
+    hd = to_device_hamiltonian(tne, h)
+    ref = OP.expect(h, op1, op2)
+    assert rel(tne.expect(hd, dp1, dp2).to_numpy(), ref) < TOL
+    tne.einsum.FUSED_TREES = False
+    try:
+        assert rel(tne.expect(hd, dp1, dp2).to_numpy(), ref) < TOL
+    finally:
+        tne.einsum.FUSED_TREES = True
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_fvec_test_graph(tne, fused):  # test/timeevolve.jl:5-35
+    g = OG.test_graph()
+    h = OT.rydberg_hamiltonian(g, 10.0, 0.2, 0.3)
+    hd = to_device_hamiltonian(tne, h)
+    op1 = oracle_peps(g, 2, 11, Dmax=4)
+    dp1 = device_peps_like(tne, op1, g, 2, Dmax=4)
+    ref = OTE.fvec(op1, h).data
+    tne.einsum.FUSED_TREES = fused
+    try:
+        got = tne.fvec(dp1, hd).to_numpy()
+    finally:
+        tne.einsum.FUSED_TREES = True
+    assert rel(got, ref) < TOL
+
+
+def test_apply_smatrix(tne):  # test/timeevolve.jl:50-67
+    g = OG.test_graph()
+    rng = np.random.default_rng(3)
+    op1 = oracle_peps(g, 2, 11, Dmax=4)
+    dp1 = device_peps_like(tne, op1, g, 2, Dmax=4)
+    v = OP.variables(op1)
+    x = crand(rng, v.size) / np.sqrt(2)
+    ref = OTE.apply_smatrix(op1, OAD.DiffTensor(v.copy()), OAD.DiffTensor(v.copy()), OAD.DiffTensor(x, requires_grad=False)).data
+    got = tne.apply_smatrix(dp1, tne.DiffTensor(v.copy()), tne.DiffTensor(v.copy()), tne.DiffTensor(x, requires_grad=False)).to_numpy()
+    assert rel(got, ref) < 1e-9
+
+
+def test_normalized_overlap_gradient_zero(tne):  # test/timeevolve.jl:37-48
+    g = OG.test_graph()
+    op1 = oracle_peps(g, 2, 11, Dmax=4)
+    dp1 = device_peps_like(tne, op1, g, 2, Dmax=4)
+    v = OP.variables(op1)
+    v1 = tne.DiffTensor(v.copy(), requires_grad=False)
+    g1 = tne.gradient(lambda x: tne.normalized_overlap(dp1, v1, x), tne.DiffTensor(v.copy()))[0]
+    assert np.abs(g1.to_numpy()).max() < 1e-8
+
+
+# -- BASELINE.json configs 1 and 2: grids with the boundary-sweep tree -------------------------------
+@pytest.mark.parametrize("L,D", [(3, 2), (4, 3)])
+def test_grid_norm_energy_gradient(tne, L, D):
+    ctx = tne.context()
+    g = OG.grid([L, L])
+    order = sweep_order(L * L)
+    op = oracle_peps(g, D, seed_for(L, D), optimizer=order)
+    dp = device_peps_like(tne, op, g, D, optimizer=order)
+    assert rel(tne.norm(dp).to_numpy(), OP.norm(op)) < TOL
+    h = OT.rydberg_hamiltonian(g, 10.0, 0.2, 0.3)
+    hd = to_device_hamiltonian(tne, h)
+    assert rel(tne.expect(hd, dp, dp).to_numpy(), OP.expect(h, op, op)) < TOL
+    fref = OTE.fvec(op, h).data
+    assert rel(tne.fvec(dp, hd).to_numpy(), fref) < TOL
+    y, f = tne.energy_and_gradient(dp, hd)
+    assert rel(f.to_numpy(), fref) < TOL
+    assert rel(y.to_numpy(), OTE.iloss2(h, op, OP.variables(op))) < TOL
+    # globally sliced tree (SlicedEinsum, test/peps.jl:9): same numbers
+    ds = device_peps_like(tne, op, g, D, optimizer=order, nslices=2)
+    assert len(ds.code_inner_product.slicing) == 2
+    assert rel(tne.norm(ds).to_numpy(), OP.norm(op)) < TOL
+    assert rel(tne.fvec(ds, hd).to_numpy(), fref) < TOL
+    # term sharding: partial energies / forces of 2 ranks add up
+    parts = [tne.energy_and_gradient(dp, hd, shard=(r, 2)) for r in range(2)]
+    assert rel(sum(p[1].to_numpy() for p in parts), fref) < TOL
+    assert ctx.launch_count() > 0
+
+
+def test_linearity_and_scaling_properties(tne):
+    """size-independent properties: <a p|p> = conj(a) <p|p>; norm scales; gradient of a real loss is
+    orthogonal to the radial direction after normalisation (iloss2 is scale-invariant in x)."""
+    L, D = 4, 3
+    g = tne.grid([L, L])
+    rng = np.random.default_rng(9)
+    p = tne.rand_simplepeps(g, D, rng, optimizer=sweep_order(L * L))
+    h = tne.rydberg_hamiltonian(g, 10.0, 0.2, 0.3)
+    n0 = tne.norm(p).item().real
+    q = tne.peps.mul(p, 2.0)
+    assert abs(tne.norm(q).item().real / n0 - 2.0) < 1e-11
+    f = tne.fvec(p, h).to_numpy()
+    v = tne.variables(p).to_numpy()
+    # L(s x) = L(x) for real s > 0  =>  Re <x, grad> = 0 with grad = i * fvec
+    grad = 1j * f
+    assert abs(np.real(np.vdot(v, grad))) < 1e-9 * np.linalg.norm(v) * np.linalg.norm(grad)
