@@ -53,9 +53,10 @@ void* tne_stream(tne_ctx* ctx);
 /* number of kernels this library has launched on the context so far */
 int64_t tne_launch_count(tne_ctx* ctx);
 /* statistics of the most recent tree program: [0] algorithmic real flops, [1] algorithmic bytes,
- * [2] contraction kernels launched, [3] workspace bytes, [4] recomputed flops, [5] number of values */
+ * [2] contraction kernels launched, [3] workspace bytes, [4] flops of recomputed forward values (executed on
+ * top of [0]), [5] number of values */
 int tne_last_program_stats(tne_ctx* ctx, double* stats6);
-/* option knobs: "recompute_threshold_bytes", "force_generic_kernel", "debug" */
+/* option knobs: "force_generic_kernel", "debug" */
 int tne_set_option(tne_ctx* ctx, const char* key, int64_t value);
 
 /* ---- device tensors: Array{ComplexF64,N} as used at src/peps.jl:41,132 ---------------- */
@@ -107,6 +108,18 @@ typedef struct {
     int32_t n_sliced;                /* SlicedEinsum: labels looped over and summed */
     const int32_t* sliced_labels;
     int32_t shard_rank, shard_world; /* this process takes work items with index % world == rank */
+    /* Optional checkpointed segments (n_segments <= 1: the whole tree is one segment).  Segment s covers
+     * the post-order nodes [seg_first_node[s], seg_first_node[s+1]); seg_first_node[0] must be 0.  Values
+     * crossing a segment boundary are kept as checkpoints; the reverse pass walks the segments backwards
+     * and recomputes each segment's forward values from its checkpoints, so only one segment's tape is
+     * alive at a time.  Inside segment s the labels seg_sliced_labels[seg_sliced_off[s] .. seg_sliced_off[s+1])
+     * are looped over: every value of the segment that carries such a label is handled one index at a time
+     * (1/size of the memory); checkpoints keep their full shape and are read / written through strided
+     * views or accumulated.  A label that is open for the whole segment costs no extra flops this way. */
+    int32_t n_segments;
+    const int32_t* seg_first_node;   /* [n_segments] */
+    const int32_t* seg_sliced_off;   /* [n_segments + 1] */
+    const int32_t* seg_sliced_labels;
 } tne_tree;
 
 int tne_contract_tree(tne_ctx* ctx, const tne_tree* tree, const tne_buf* leaves,

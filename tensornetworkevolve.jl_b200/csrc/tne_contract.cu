@@ -224,19 +224,24 @@ void contract_cost(const TensorRef& A, const TensorRef& B, const TensorRef& C, d
 }
 
 
-int contract_launch(tne_ctx* ctx, const TensorRef& A0, const TensorRef& B0, const TensorRef& C, bool accumulate,
-                    double alpha_re, double alpha_im) {
+int contract_plan(tne_ctx* ctx, const TensorRef& A0, const TensorRef& B0, const TensorRef& C, bool accumulate,
+                  double alpha_re, double alpha_im, ContractPlan* plan) {
     const TensorRef* A = &A0;
     const TensorRef* B = &B0;
     Classified cl;
     TNE_TRY(classify(ctx, *A, *B, C, cl));
+    plan->swapped = false;
     if (cl.Nsz > cl.Msz) {  // keep the larger free side on M (grid.x)
         std::swap(A, B);
+        plan->swapped = true;
         cl = Classified();
         TNE_TRY(classify(ctx, *A, *B, C, cl));
     }
-    if (cl.Msz * cl.Nsz * cl.Bsz == 0) return TNE_OK;
-    GettDesc d;
+    contract_cost(A0, B0, C, &plan->flops, &plan->bytes);
+    plan->c_nelem = C.nelem();
+    plan->empty = (cl.Msz * cl.Nsz * cl.Bsz == 0);
+    if (plan->empty) return TNE_OK;
+    GettDesc& d = plan->d;
     memset(&d, 0, sizeof(d));
     TNE_TRY(fill_legset(ctx, d.M, cl.M, 0, 2, 3));
     TNE_TRY(fill_legset(ctx, d.N, cl.N, 1, 2, 3));
@@ -257,13 +262,11 @@ int contract_launch(tne_ctx* ctx, const TensorRef& A0, const TensorRef& B0, cons
     d.bKfast = unit_is_k(cl.K, cl.N, false);
     d.nsplit = 1;
     d.kPerSplit = d.Ksz;
-
+    plan->kernel = 0;
     if (!ctx->opt_force_generic) {
-        bool handled = false;
-        TNE_TRY(gett_try_fast(ctx, d, A->ptr, B->ptr, C.ptr, &handled));
-        if (handled) return TNE_OK;
+        TNE_TRY(gett_fast_plan(ctx, plan));
+        if (plan->kernel != 0) return TNE_OK;
     }
-
     constexpr int TM = 64, TN = 32, TK = 16;
     long long gm = (d.Msz + TM - 1) / TM, gn = (d.Nsz + TN - 1) / TN;
     long long tiles = gm * gn * d.Bsz;
@@ -280,21 +283,32 @@ int contract_launch(tne_ctx* ctx, const TensorRef& A0, const TensorRef& B0, cons
     }
     if (gn > 65535 || d.Bsz * d.nsplit > 65535)
         return tne_fail(ctx, TNE_ERR_UNSUPPORTED, "contraction grid too large (N tiles %lld, batch*split %lld)", gn, d.Bsz * d.nsplit);
-    if (d.nsplit > 1 && !accumulate) {
-        // atomics accumulate into C: clear it first (C is dense in its own layout)
-        TNE_TRY(launch_fill_zero(ctx, C.ptr, C.nelem()));
-    }
-    dim3 grid((unsigned)gm, (unsigned)gn, (unsigned)(d.Bsz * d.nsplit));
-    gett_generic<TM, TN, TK><<<grid, 256, 0, ctx->stream>>>(d, A->ptr, B->ptr, C.ptr);
+    plan->zero_first = d.nsplit > 1 && !accumulate;  // atomics accumulate into C: clear it first (C is dense)
+    plan->gx = (unsigned)gm; plan->gy = (unsigned)gn; plan->gz = (unsigned)(d.Bsz * d.nsplit);
+    return TNE_OK;
+}
+
+int contract_run(tne_ctx* ctx, const ContractPlan& plan, const cplx* A, const cplx* B, cplx* C) {
+    if (plan.empty) return TNE_OK;
+    if (plan.swapped) std::swap(A, B);
+    if (plan.kernel != 0) return gett_fast_run(ctx, plan, A, B, C);
+    if (plan.zero_first) TNE_TRY(launch_fill_zero(ctx, C, plan.c_nelem));
+    dim3 grid(plan.gx, plan.gy, plan.gz);
+    gett_generic<64, 32, 16><<<grid, 256, 0, ctx->stream>>>(plan.d, A, B, C);
     TNE_LAUNCH_CHECK(ctx);
     return TNE_OK;
 }
 
-#ifndef TNE_HAVE_DMMA
-int gett_try_fast(tne_ctx*, const GettDesc&, const cplx*, const cplx*, cplx*, bool* handled) {
-    *handled = false;
-    return TNE_OK;
+int contract_launch(tne_ctx* ctx, const TensorRef& A, const TensorRef& B, const TensorRef& C, bool accumulate,
+                    double alpha_re, double alpha_im) {
+    ContractPlan plan;
+    TNE_TRY(contract_plan(ctx, A, B, C, accumulate, alpha_re, alpha_im, &plan));
+    return contract_run(ctx, plan, A.ptr, B.ptr, C.ptr);
 }
+
+#ifndef TNE_HAVE_DMMA
+int gett_fast_plan(tne_ctx*, ContractPlan*) { return TNE_OK; }
+int gett_fast_run(tne_ctx* ctx, const ContractPlan&, const cplx*, const cplx*, cplx*) { return tne_fail(ctx, TNE_ERR_UNSUPPORTED, "no fast path built"); }
 #endif
 
 // ---------------------------------------------------------------------------------------

@@ -224,8 +224,7 @@ extern "C" int tne_last_program_stats(tne_ctx* ctx, double* s) {
 
 extern "C" int tne_set_option(tne_ctx* ctx, const char* key, int64_t value) {
     std::string k(key ? key : "");
-    if (k == "recompute_threshold_bytes") ctx->opt_recompute_threshold = value;
-    else if (k == "force_generic_kernel") ctx->opt_force_generic = value;
+    if (k == "force_generic_kernel") ctx->opt_force_generic = value;
     else if (k == "debug") ctx->opt_debug = value;
     else return tne_fail(ctx, TNE_ERR_INVALID, "unknown option '%s'", k.c_str());
     return TNE_OK;

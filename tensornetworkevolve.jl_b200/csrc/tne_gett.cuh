@@ -2,30 +2,6 @@
 #pragma once
 #include "tne_internal.h"
 
-#define MAXLEG 16
-
-struct LegSet {
-    int n;
-    int size[MAXLEG];
-    long long s0[MAXLEG];
-    long long s1[MAXLEG];
-    long long s2[MAXLEG];
-};
-
-struct GettDesc {
-    LegSet M;   // s0: A stride, s1: C stride
-    LegSet N;   // s0: B stride, s1: C stride
-    LegSet K;   // s0: A stride, s1: B stride
-    LegSet Bt;  // s0: A, s1: B, s2: C
-    long long Msz, Nsz, Ksz, Bsz;
-    long long kPerSplit;
-    int nsplit;
-    int conjA, conjB, accumulate;
-    double alphaRe, alphaIm;  // C (+)= alpha * A * B
-    int aKfast;  // A's unit-stride direction is a K leg (else an M leg)
-    int bKfast;
-};
-
 __device__ __forceinline__ void decomp2(const LegSet& L, long long idx, long long& o0, long long& o1) {
     o0 = 0; o1 = 0;
 #pragma unroll 1
@@ -54,4 +30,6 @@ __device__ __forceinline__ void atomic_add_c(cplx* p, double re, double im) {
 }
 
 
-int gett_try_fast(tne_ctx* ctx, const GettDesc& d, const cplx* A, const cplx* B, cplx* C, bool* handled);
+// DMMA fast paths: pick a kernel for the classified contraction (plan->kernel stays 0 if none applies)
+int gett_fast_plan(tne_ctx* ctx, ContractPlan* plan);
+int gett_fast_run(tne_ctx* ctx, const ContractPlan& plan, const cplx* A, const cplx* B, cplx* C);

@@ -47,7 +47,6 @@ struct tne_ctx {
     int64_t launches = 0;
     double stats[6] = {0, 0, 0, 0, 0, 0};
     // options
-    int64_t opt_recompute_threshold = -1;  // -1: automatic
     int64_t opt_force_generic = 0;
     int64_t opt_debug = 0;
     cplx* one_dev = nullptr;               // device constant 1+0i
@@ -91,6 +90,45 @@ struct TensorRef {                  // a tensor operand: labels in memory order 
     bool conj = false;
     int64_t nelem() const { int64_t n = 1; for (auto d : dims) n *= d; return n; }
 };
+#define MAXLEG 16
+struct LegSet {
+    int n;
+    int size[MAXLEG];
+    long long s0[MAXLEG];
+    long long s1[MAXLEG];
+    long long s2[MAXLEG];
+};
+struct GettDesc {
+    LegSet M;   // s0: A stride, s1: C stride
+    LegSet N;   // s0: B stride, s1: C stride
+    LegSet K;   // s0: A stride, s1: B stride
+    LegSet Bt;  // s0: A, s1: B, s2: C
+    long long Msz, Nsz, Ksz, Bsz;
+    long long kPerSplit;
+    int nsplit;
+    int conjA, conjB, accumulate;
+    double alphaRe, alphaIm;  // C (+)= alpha * A * B
+    int aKfast;  // A's unit-stride direction is a K leg (else an M leg)
+    int bKfast;
+};
+// A classified contraction, ready to launch any number of times with different base pointers
+// (the slice loops of tne_tree.cu re-launch the same plan with shifted operands).
+struct ContractPlan {
+    GettDesc d;
+    int kernel = 0;            // 0: generic FMA; >0: DMMA fast paths (tne_contract_dmma.cu)
+    unsigned gx = 1, gy = 1, gz = 1;
+    int threads = 256;
+    size_t smem = 0;
+    bool swapped = false;      // operands A and B exchanged (the larger free side sits on M)
+    bool zero_first = false;   // split-K with atomics into a non-accumulating output
+    int64_t c_nelem = 0;
+    bool empty = false;
+    int aux[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    double flops = 0, bytes = 0;
+};
+int contract_plan(tne_ctx* ctx, const TensorRef& A, const TensorRef& B, const TensorRef& C, bool accumulate,
+                  double alpha_re, double alpha_im, ContractPlan* plan);
+int contract_run(tne_ctx* ctx, const ContractPlan& plan, const cplx* A, const cplx* B, cplx* C);
 // C (+)= A * B over the labels; C's layout is given by its labels/strides.
 int contract_launch(tne_ctx* ctx, const TensorRef& A, const TensorRef& B, const TensorRef& C, bool accumulate,
                     double alpha_re = 1.0, double alpha_im = 0.0);

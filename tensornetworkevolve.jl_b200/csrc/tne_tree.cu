@@ -13,10 +13,13 @@
 //     contractions, src/peps.jl:470-476);
 //   * backward: source-transformed reverse mode, dA = dC * B^H and dB = A^H * dC per op, with
 //     the conjugations fused into operand loads (einsum_grad's two conj copies disappear);
-//   * memory: intermediates get static offsets in one workspace arena from exact lifetimes;
-//     if the plan exceeds the budget, the largest forward values are dropped after their last
-//     forward use and recomputed segment-wise when the backward pass needs them;
-//   * slicing: sliced labels are looped over (sharded by rank), leaves become strided views.
+//   * memory: intermediates get static offsets in one workspace arena from exact lifetimes.
+//     A tree may be cut into checkpointed segments (tne.h): values crossing a segment boundary
+//     are kept, the reverse pass walks the segments backwards and re-runs each segment's forward
+//     ops from its checkpoints, so one segment's tape is alive at a time; inside a segment its
+//     own sliced labels are looped over (every value carrying the label is 1/size as large;
+//     checkpoints are read and written through strided views or accumulated);
+//   * slicing: globally sliced labels are looped over (sharded by rank), leaves become strided views.
 #include <algorithm>
 #include <functional>
 #include <set>
@@ -37,6 +40,7 @@ struct Val {
     int64_t offset = -1;   // workspace byte offset
     int leaf = -1;         // leaf index for sliced views
     int64_t slice_base = 0;  // element offset added per slice (filled at run time)
+    bool persistent = false;  // touched by more than one segment: lives in the checkpoint arena
 };
 
 enum OpKind { OP_CONTRACT = 0, OP_AXPY = 1, OP_ZERO = 2 };
@@ -49,6 +53,8 @@ struct Op {
     double are = 1.0, aim = 0.0;
     bool recompute = false;
     bool backward = false;
+    int node = 0;          // tree node (post-order index) the op belongs to
+    int seg = 0;
 };
 
 typedef std::vector<std::pair<int32_t, int64_t>> Key;  // sorted (leaf, replacement handle)
@@ -102,117 +108,6 @@ void out_layout(const Val& a, const Val& b, const std::vector<int32_t>& keep, st
         if (find_in(keep, b.labels[i]) >= 0 && find_in(labels, b.labels[i]) < 0) { labels.push_back(b.labels[i]); dims.push_back(b.dims[i]); }
 }
 
-TensorRef ref_of(const Program& P, int id, bool conj) {
-    const Val& v = P.vals[id];
-    TensorRef t;
-    t.labels = v.labels;
-    t.dims = v.dims;
-    t.strides = v.strides;
-    t.conj = conj;
-    t.ptr = v.ext ? v.ext + v.slice_base : reinterpret_cast<cplx*>(reinterpret_cast<char*>(P.ctx->ws) + v.offset);
-    return t;
-}
-
-// ---------------------------------------------------------------------------------------
-// static memory plan: greedy-by-size offset assignment over exact lifetimes
-// ---------------------------------------------------------------------------------------
-int64_t plan_memory(Program& P) {
-    const int nv = (int)P.vals.size();
-    std::vector<int> first(nv, -1), last(nv, -1);
-    for (int i = 0; i < (int)P.all.size(); ++i) {
-        const Op& op = P.all[i];
-        int ids[3] = {op.out, op.a, op.b};
-        for (int id : ids) {
-            if (id < 0 || P.vals[id].ext) continue;
-            if (first[id] < 0) first[id] = i;
-            last[id] = i;
-        }
-    }
-    std::vector<int> order;
-    for (int v = 0; v < nv; ++v) if (first[v] >= 0) order.push_back(v);
-    auto bytes_of = [&](int v) { int64_t b = P.vals[v].nelem * (int64_t)sizeof(cplx); return (b + 511) / 512 * 512; };
-    std::sort(order.begin(), order.end(), [&](int x, int y) {
-        int64_t bx = bytes_of(x), by = bytes_of(y);
-        if (bx != by) return bx > by;
-        return first[x] < first[y];
-    });
-    std::vector<int> placed;
-    int64_t peak = 0;
-    for (int v : order) {
-        std::vector<std::pair<int64_t, int64_t>> busy;
-        for (int u : placed)
-            if (!(last[u] < first[v] || last[v] < first[u])) busy.emplace_back(P.vals[u].offset, P.vals[u].offset + bytes_of(u));
-        std::sort(busy.begin(), busy.end());
-        int64_t off = 0, need = bytes_of(v);
-        for (auto& iv : busy) {
-            if (iv.first - off >= need) break;
-            off = std::max(off, iv.second);
-        }
-        P.vals[v].offset = off;
-        placed.push_back(v);
-        peak = std::max(peak, off + need);
-    }
-    return peak;
-}
-
-// ---------------------------------------------------------------------------------------
-// final op sequence with drop/recompute of forward values larger than `threshold` bytes
-// ---------------------------------------------------------------------------------------
-void schedule(Program& P, int64_t threshold) {
-    P.all.clear();
-    const int nv0 = (int)P.vals.size();
-    std::vector<bool> used_bwd(nv0, false);
-    for (auto& op : P.bwd) { if (op.a >= 0 && op.a < nv0) used_bwd[op.a] = true; if (op.b >= 0 && op.b < nv0) used_bwd[op.b] = true; }
-    std::vector<std::vector<int>> producers(nv0);
-    for (int i = 0; i < (int)P.fwd.size(); ++i) producers[P.fwd[i].out].push_back(i);
-    std::vector<bool> dropped(nv0, false);
-    for (int v = 0; v < nv0; ++v)
-        if (!P.vals[v].ext && !producers[v].empty() && used_bwd[v] && threshold >= 0 &&
-            P.vals[v].nelem * (int64_t)sizeof(cplx) > threshold && v != P.root_val)
-            dropped[v] = true;
-    std::vector<int> cur(nv0);
-    for (int v = 0; v < nv0; ++v) cur[v] = v;
-    std::vector<bool> alive(nv0, false);
-    for (int v = 0; v < nv0; ++v) if (P.vals[v].ext) alive[v] = true;
-    std::vector<int> last_fwd(nv0, -1);
-    for (int i = 0; i < (int)P.fwd.size(); ++i) { if (P.fwd[i].a >= 0) last_fwd[P.fwd[i].a] = i; if (P.fwd[i].b >= 0) last_fwd[P.fwd[i].b] = i; }
-    auto remap = [&](Op op) {
-        if (op.out < nv0) op.out = cur[op.out];
-        if (op.a >= 0 && op.a < nv0) op.a = cur[op.a];
-        if (op.b >= 0 && op.b < nv0) op.b = cur[op.b];
-        return op;
-    };
-    for (int i = 0; i < (int)P.fwd.size(); ++i) {
-        const Op& op = P.fwd[i];
-        P.all.push_back(remap(op));
-        alive[op.out] = true;
-        int ins[2] = {op.a, op.b};
-        for (int v : ins) if (v >= 0 && dropped[v] && last_fwd[v] == i) alive[v] = false;
-    }
-    for (int v = 0; v < nv0; ++v) if (dropped[v] && last_fwd[v] < 0) alive[v] = false;  // never read forward
-    std::function<void(int)> ensure = [&](int v) {
-        if (v < 0 || v >= nv0 || alive[v] || producers[v].empty()) return;  // only forward values are recomputed
-        for (int pi : producers[v]) { ensure(P.fwd[pi].a); ensure(P.fwd[pi].b); }
-        // fresh instance so the two lifetimes get separate workspace intervals
-        Val clone = P.vals[v];
-        clone.offset = -1;
-        P.vals.push_back(clone);
-        P.written.push_back(true);
-        cur[v] = (int)P.vals.size() - 1;
-        for (int pi : producers[v]) {
-            Op op = remap(P.fwd[pi]);
-            op.recompute = true;
-            P.all.push_back(op);
-        }
-        alive[v] = true;
-    };
-    for (auto& op0 : P.bwd) {
-        ensure(op0.a);
-        ensure(op0.b);
-        P.all.push_back(remap(op0));
-    }
-}
-
 // ---------------------------------------------------------------------------------------
 // tree parsing and the term dynamic programme
 // ---------------------------------------------------------------------------------------
@@ -225,7 +120,7 @@ struct Builder {
     std::vector<int32_t> sliced;
     int n_terms = 0;
     const tne_term* terms = nullptr;
-    std::map<int64_t, int> repl_val;       // (leaf, handle) -> value id, keyed by handle*4096+leaf
+    int cur_node = 0;                      // node the ops being emitted belong to
 
     Builder(tne_ctx* c, Program& p, const tne_tree* t) : ctx(c), P(p), tree(t) {}
 
@@ -259,6 +154,7 @@ struct Builder {
         op.out = out; op.a = a; op.b = b;
         op.conj_a = P.vals[a].conj; op.conj_b = P.vals[b].conj;
         op.are = are; op.aim = aim;
+        op.node = cur_node;
         P.emit(P.fwd, op);
         return out;
     }
@@ -320,6 +216,9 @@ int build_forward(Builder& B, const tne_buf* leaves, const int32_t* leaf_conj, b
             B.nodes[lf].var[key] = v;
         }
     }
+    std::vector<int> parent_of_leaf(nl, 0);
+    for (int j = 0; j < nn; ++j)
+        for (int q = 0; q < 2; ++q) { int c = T->node_children[2 * j + q]; if (c >= 0 && c < nl) parent_of_leaf[c] = j; }
     for (int k = 0; k < B.n_terms; ++k) {
         const tne_term& t = B.terms[k];
         if (t.n_repl != 1) continue;
@@ -333,6 +232,7 @@ int build_forward(Builder& B, const tne_buf* leaves, const int32_t* leaf_conj, b
         op.a = nd.var[Key{{(int32_t)lf, t.repl[0]}}];
         op.conj_a = P.vals[op.a].conj;
         op.are = t.coef_re; op.aim = t.coef_im;
+        op.node = parent_of_leaf[lf];
         P.emit(P.fwd, op);
     }
     // internal nodes
@@ -340,6 +240,7 @@ int build_forward(Builder& B, const tne_buf* leaves, const int32_t* leaf_conj, b
     for (int j = 0; j < nn; ++j) {
         int ca = T->node_children[2 * j], cb = T->node_children[2 * j + 1];
         int self = nl + j;
+        B.cur_node = j;
         if (ca < 0 || cb < 0 || ca >= self || cb >= self || ca == cb) return tne_fail(ctx, TNE_ERR_INVALID, "node %d has invalid children (%d, %d); nodes must be in post-order", j, ca, cb);
         NodeInfo& nd = B.nodes[self];
         NodeInfo& na = B.nodes[ca];
@@ -397,6 +298,7 @@ int build_forward(Builder& B, const tne_buf* leaves, const int32_t* leaf_conj, b
             op.kind = OP_AXPY;
             op.out = root.sigma; op.a = result;
             op.are = any0 ? cre : 0.0; op.aim = any0 ? cim : 0.0;
+            op.node = nn - 1;
             P.emit(P.fwd, op);
         }
         result = root.sigma;
@@ -451,7 +353,7 @@ void build_backward(Program& P, int root, int seed_val) {
         if (op.kind == OP_AXPY) {
             if (!P.vals[op.a].needs_grad) continue;
             Op g;
-            g.kind = OP_AXPY; g.backward = true;
+            g.kind = OP_AXPY; g.backward = true; g.node = op.node; g.seg = op.seg;
             g.out = grad_of(op.a); g.a = dout;
             if (op.conj_a) { g.conj_a = true; g.are = op.are; g.aim = op.aim; }       // a' = conj(a): da = conj(conj(alpha) dout)
             else { g.conj_a = false; g.are = op.are; g.aim = -op.aim; }
@@ -461,7 +363,7 @@ void build_backward(Program& P, int root, int seed_val) {
         // c (+)= alpha * fa(a) * fb(b)
         if (P.vals[op.a].needs_grad) {
             Op g;
-            g.kind = OP_CONTRACT; g.backward = true;
+            g.kind = OP_CONTRACT; g.backward = true; g.node = op.node; g.seg = op.seg;
             g.out = grad_of(op.a); g.a = dout; g.b = op.b;
             if (op.conj_a) { g.conj_a = true; g.conj_b = op.conj_b; g.are = op.are; g.aim = op.aim; }
             else { g.conj_a = false; g.conj_b = !op.conj_b; g.are = op.are; g.aim = -op.aim; }
@@ -469,7 +371,7 @@ void build_backward(Program& P, int root, int seed_val) {
         }
         if (P.vals[op.b].needs_grad) {
             Op g;
-            g.kind = OP_CONTRACT; g.backward = true;
+            g.kind = OP_CONTRACT; g.backward = true; g.node = op.node; g.seg = op.seg;
             g.out = grad_of(op.b); g.a = op.a; g.b = dout;
             if (op.conj_b) { g.conj_b = true; g.conj_a = op.conj_a; g.are = op.are; g.aim = op.aim; }
             else { g.conj_b = false; g.conj_a = !op.conj_a; g.are = op.are; g.aim = -op.aim; }
@@ -478,29 +380,311 @@ void build_backward(Program& P, int root, int seed_val) {
     }
 }
 
-int run_ops(Program& P, bool count_stats) {
-    tne_ctx* ctx = P.ctx;
-    for (const Op& op : P.all) {
-        TensorRef C = ref_of(P, op.out, false);
-        if (op.kind == OP_AXPY) {
-            TensorRef A = ref_of(P, op.a, op.conj_a);
-            TensorRef one;
-            one.ptr = ctx->one_dev;
-            TNE_TRY(contract_launch(ctx, A, one, C, op.acc, op.are, op.aim));
-            continue;
+
+// ---------------------------------------------------------------------------------------
+// phases: the executable form of a (segmented) program
+// ---------------------------------------------------------------------------------------
+struct PView {               // how one value looks inside one phase (segment-local slicing applied)
+    std::vector<int32_t> labels;
+    std::vector<int64_t> dims, strides;
+    std::vector<int64_t> sl_stride;   // element stride per segment-sliced label (0: label absent)
+    bool temp = false;                // phase-local storage (sliced labels removed), else checkpoint / external
+    int64_t off = 0;                  // byte offset: temp arena (temp) or checkpoint arena
+    bool dep = false;                 // differs from slice to slice
+    int64_t nelem = 1;
+};
+
+struct PhaseOp {
+    Op op;
+    ContractPlan plan;
+    bool first_slice_only = false;
+};
+
+struct Phase {
+    int seg = 0;
+    bool backward = false;
+    std::vector<int32_t> sliced;
+    std::vector<int64_t> ssz;
+    int64_t nsl = 1;
+    std::vector<PhaseOp> ops;
+    std::map<int, PView> views;
+    std::vector<int> zero_at_start;   // checkpoint values this phase accumulates into
+    int64_t temp_bytes = 0;
+};
+
+struct Interval { int id; int64_t bytes; int first, last; int64_t off; };
+
+// greedy-by-size offset assignment over exact lifetimes; returns the peak
+int64_t plan_intervals(std::vector<Interval>& iv) {
+    std::vector<int> order(iv.size());
+    for (size_t i = 0; i < iv.size(); ++i) order[i] = (int)i;
+    std::sort(order.begin(), order.end(), [&](int x, int y) {
+        if (iv[x].bytes != iv[y].bytes) return iv[x].bytes > iv[y].bytes;
+        return iv[x].first < iv[y].first;
+    });
+    std::vector<int> placed;
+    int64_t peak = 0;
+    for (int v : order) {
+        std::vector<std::pair<int64_t, int64_t>> busy;
+        for (int u : placed)
+            if (!(iv[u].last < iv[v].first || iv[v].last < iv[u].first)) busy.emplace_back(iv[u].off, iv[u].off + iv[u].bytes);
+        std::sort(busy.begin(), busy.end());
+        int64_t off = 0;
+        for (auto& b : busy) {
+            if (b.first - off >= iv[v].bytes) break;
+            off = std::max(off, b.second);
         }
-        TensorRef A = ref_of(P, op.a, op.conj_a);
-        TensorRef Bt = ref_of(P, op.b, op.conj_b);
-        TNE_TRY(contract_launch(ctx, A, Bt, C, op.acc, op.are, op.aim));
-        if (count_stats) {
-            double f, b;
-            contract_cost(A, Bt, C, &f, &b);
-            if (op.recompute) P.re_flops += f; else { P.flops += f; P.bytes += b; }
-            P.n_contract++;
-        }
+        iv[v].off = off;
+        placed.push_back(v);
+        peak = std::max(peak, off + iv[v].bytes);
     }
-    return TNE_OK;
+    return peak;
 }
+
+inline int64_t round512(int64_t b) { return (b + 511) / 512 * 512; }
+
+struct Exec {
+    Program& P;
+    tne_ctx* ctx;
+    std::vector<Phase> phases;
+    int64_t persist_bytes = 0, temp_bytes = 0;
+    std::map<int32_t, int64_t> label_size;
+    std::set<int> ever_zeroed;   // checkpoints are cleared by the first phase that writes them only
+    Exec(Program& p) : P(p), ctx(p.ctx) {}
+
+    void full_strides(const Val& v, std::vector<int64_t>& st) const {
+        if (!v.strides.empty()) { st = v.strides; return; }
+        st.resize(v.dims.size());
+        int64_t acc = 1;
+        for (size_t i = 0; i < v.dims.size(); ++i) { st[i] = acc; acc *= v.dims[i]; }
+    }
+
+    // segment bookkeeping: op.seg from the node -> segment map; persistence of values
+    int assign_segments(const tne_tree* T) {
+        const int nn = T->n_nodes;
+        int S = std::max(1, (int)T->n_segments);
+        std::vector<int> seg_of_node(nn, 0);
+        if (T->n_segments > 1) {
+            if (!T->seg_first_node || T->seg_first_node[0] != 0) return tne_fail(ctx, TNE_ERR_INVALID, "seg_first_node[0] must be 0");
+            for (int s = 0; s < S; ++s) {
+                int lo = T->seg_first_node[s], hi = s + 1 < S ? T->seg_first_node[s + 1] : nn;
+                if (lo < 0 || hi > nn || lo >= hi) return tne_fail(ctx, TNE_ERR_INVALID, "segment %d covers no nodes", s);
+                for (int j = lo; j < hi; ++j) seg_of_node[j] = s;
+            }
+        }
+        for (auto& op : P.fwd) op.seg = seg_of_node[op.node];
+        std::stable_sort(P.fwd.begin(), P.fwd.end(), [](const Op& x, const Op& y) { return x.seg < y.seg; });
+        return TNE_OK;
+    }
+
+    void mark_persistent() {
+        std::vector<int> seg_seen(P.vals.size(), -1);
+        auto touch = [&](int v, int seg) {
+            if (v < 0 || P.vals[v].ext) return;
+            if (seg_seen[v] < 0) seg_seen[v] = seg;
+            else if (seg_seen[v] != seg) P.vals[v].persistent = true;
+        };
+        for (auto& op : P.fwd) { touch(op.out, op.seg); touch(op.a, op.seg); touch(op.b, op.seg); }
+        for (auto& op : P.bwd) { touch(op.out, op.seg); touch(op.a, op.seg); touch(op.b, op.seg); }
+    }
+
+    int make_view(Phase& ph, int v) {
+        if (v < 0 || ph.views.count(v)) return TNE_OK;
+        const Val& val = P.vals[v];
+        PView pv;
+        pv.temp = !val.ext && !val.persistent;
+        std::vector<int64_t> st;
+        full_strides(val, st);
+        pv.sl_stride.assign(ph.sliced.size(), 0);
+        for (size_t q = 0; q < val.labels.size(); ++q) {
+            int s = find_in(ph.sliced, val.labels[q]);
+            if (s >= 0) {
+                pv.dep = true;
+                if (!pv.temp) pv.sl_stride[s] = st[q];
+                continue;
+            }
+            pv.labels.push_back(val.labels[q]);
+            pv.dims.push_back(val.dims[q]);
+            pv.strides.push_back(st[q]);
+        }
+        for (auto d : pv.dims) pv.nelem *= d;
+        if (pv.temp) {  // contiguous in its reduced shape
+            int64_t acc = 1;
+            for (size_t q = 0; q < pv.dims.size(); ++q) { pv.strides[q] = acc; acc *= pv.dims[q]; }
+        }
+        ph.views.emplace(v, std::move(pv));
+        return TNE_OK;
+    }
+
+    TensorRef ref_of(const Phase& ph, int v, bool conj) const {
+        const PView& pv = ph.views.at(v);
+        TensorRef t;
+        t.labels = pv.labels; t.dims = pv.dims; t.strides = pv.strides; t.conj = conj;
+        return t;
+    }
+
+    int build_phase(Phase& ph, const std::vector<Op>& ops) {
+        for (auto& op : ops) { TNE_TRY(make_view(ph, op.out)); TNE_TRY(make_view(ph, op.a)); TNE_TRY(make_view(ph, op.b)); }
+        std::set<int> seen;
+        for (auto op : ops) {
+            PView& vo = ph.views.at(op.out);
+            bool in_dep = (op.a >= 0 && ph.views.at(op.a).dep) || (op.b >= 0 && ph.views.at(op.b).dep);
+            bool out_view_dep = false;
+            for (auto s : vo.sl_stride) if (s != 0) out_view_dep = true;
+            PhaseOp po;
+            po.first_slice_only = false;
+            if (vo.temp) {
+                op.acc = seen.count(op.out) > 0;
+                seen.insert(op.out);
+                if (P.vals[op.out].labels.size() != vo.labels.size()) out_view_dep = true;
+            } else {
+                op.acc = true;  // checkpoints are cleared at phase start, external outputs at program start
+                if (!P.vals[op.out].ext && !ever_zeroed.count(op.out)) { ever_zeroed.insert(op.out); ph.zero_at_start.push_back(op.out); }
+                if (!in_dep && !out_view_dep && ph.nsl > 1) po.first_slice_only = true;
+            }
+            if (in_dep || out_view_dep) vo.dep = true;
+            po.op = op;
+            TensorRef C = ref_of(ph, op.out, false);
+            TensorRef A = ref_of(ph, op.a, op.conj_a);
+            TensorRef Bt;
+            if (op.kind == OP_CONTRACT) Bt = ref_of(ph, op.b, op.conj_b);
+            TNE_TRY(contract_plan(ctx, A, Bt, C, op.acc, op.are, op.aim, &po.plan));
+            ph.ops.push_back(std::move(po));
+        }
+        // temp arena of this phase
+        std::vector<Interval> iv;
+        std::map<int, int> slot;
+        for (int i = 0; i < (int)ph.ops.size(); ++i) {
+            const Op& op = ph.ops[i].op;
+            int ids[3] = {op.out, op.a, op.b};
+            for (int v : ids) {
+                if (v < 0 || !ph.views.at(v).temp) continue;
+                auto it = slot.find(v);
+                if (it == slot.end()) { slot[v] = (int)iv.size(); iv.push_back({v, round512(ph.views.at(v).nelem * (int64_t)sizeof(cplx)), i, i, 0}); }
+                else iv[it->second].last = i;
+            }
+        }
+        ph.temp_bytes = plan_intervals(iv);
+        for (auto& x : iv) ph.views.at(x.id).off = x.off;
+        return TNE_OK;
+    }
+
+    int build(const tne_tree* T, bool has_grad) {
+        const int S = std::max(1, (int)T->n_segments);
+        // segment-local sliced labels
+        std::vector<std::vector<int32_t>> seg_sliced(S);
+        if (T->n_segments > 1 && T->seg_sliced_off)
+            for (int s = 0; s < S; ++s)
+                for (int q = T->seg_sliced_off[s]; q < T->seg_sliced_off[s + 1]; ++q) seg_sliced[s].push_back(T->seg_sliced_labels[q]);
+        for (auto& v : P.vals) for (size_t q = 0; q < v.labels.size(); ++q) label_size[v.labels[q]] = v.dims[q];
+        mark_persistent();
+        std::vector<std::vector<Op>> fseg(S), bseg(S);
+        for (auto& op : P.fwd) fseg[op.seg].push_back(op);
+        for (auto& op : P.bwd) bseg[op.seg].push_back(op);
+        auto new_phase = [&](int s, bool backward) {
+            Phase ph;
+            ph.seg = s; ph.backward = backward;
+            for (auto l : seg_sliced[s]) {
+                auto it = label_size.find(l);
+                if (it == label_size.end()) continue;  // label does not occur (e.g. sliced globally)
+                ph.sliced.push_back(l); ph.ssz.push_back(it->second); ph.nsl *= it->second;
+            }
+            return ph;
+        };
+        // forward phases; the last segment keeps its tape and runs its reverse ops in the same phase
+        for (int s = 0; s < S; ++s) {
+            std::vector<Op> ops = fseg[s];
+            bool fused_bwd = has_grad && s == S - 1;
+            if (fused_bwd) ops.insert(ops.end(), bseg[s].begin(), bseg[s].end());
+            if (ops.empty()) continue;
+            Phase ph = new_phase(s, fused_bwd);
+            TNE_TRY(build_phase(ph, ops));
+            phases.push_back(std::move(ph));
+        }
+        // reverse phases with recomputation of the segment's own forward values
+        for (int s = S - 2; s >= 0 && has_grad; --s) {
+            if (bseg[s].empty()) continue;
+            std::set<int> need;
+            for (auto& op : bseg[s]) {
+                int ins[2] = {op.a, op.b};
+                for (int v : ins) if (v >= 0 && !P.vals[v].ext && !P.vals[v].persistent) need.insert(v);
+            }
+            // only values produced by forward ops of this segment can be recomputed
+            std::set<int> fwd_outs;
+            for (auto& op : fseg[s]) fwd_outs.insert(op.out);
+            std::vector<Op> re;
+            for (int i = (int)fseg[s].size() - 1; i >= 0; --i) {
+                const Op& op = fseg[s][i];
+                if (!need.count(op.out) || P.vals[op.out].persistent || P.vals[op.out].ext) continue;
+                Op r = op;
+                r.recompute = true;
+                re.push_back(r);
+                int ins[2] = {op.a, op.b};
+                for (int v : ins) if (v >= 0 && fwd_outs.count(v)) need.insert(v);
+            }
+            std::reverse(re.begin(), re.end());
+            Phase ph = new_phase(s, true);
+            if (ph.nsl > 1)
+                for (auto& op : re) {
+                    int ins[2] = {op.a, op.b};
+                    for (int v : ins)
+                        if (v >= 0 && P.vals[v].persistent && fwd_outs.count(v))
+                            return tne_fail(ctx, TNE_ERR_UNSUPPORTED, "segment %d re-reads its own checkpoint inside a sliced segment", s);
+                }
+            re.insert(re.end(), bseg[s].begin(), bseg[s].end());
+            TNE_TRY(build_phase(ph, re));
+            phases.push_back(std::move(ph));
+        }
+        // checkpoint arena over the phase timeline
+        std::vector<Interval> iv;
+        std::map<int, int> slot;
+        for (int pi = 0; pi < (int)phases.size(); ++pi)
+            for (auto& kv : phases[pi].views) {
+                int v = kv.first;
+                if (!P.vals[v].persistent) continue;
+                auto it = slot.find(v);
+                if (it == slot.end()) { slot[v] = (int)iv.size(); iv.push_back({v, round512(P.vals[v].nelem * (int64_t)sizeof(cplx)), pi, pi, 0}); }
+                else iv[it->second].last = pi;
+            }
+        persist_bytes = plan_intervals(iv);
+        for (auto& x : iv) P.vals[x.id].offset = x.off;
+        for (auto& ph : phases) temp_bytes = std::max(temp_bytes, ph.temp_bytes);
+        return TNE_OK;
+    }
+
+    cplx* base_ptr(const Phase& ph, int v) const {
+        const Val& val = P.vals[v];
+        if (val.ext) return val.ext + val.slice_base;
+        const PView& pv = ph.views.at(v);
+        char* ws = reinterpret_cast<char*>(ctx->ws);
+        return reinterpret_cast<cplx*>(pv.temp ? ws + persist_bytes + pv.off : ws + val.offset);
+    }
+
+    int run() {
+        for (auto& ph : phases) {
+            for (int v : ph.zero_at_start) TNE_TRY(launch_fill_zero(ctx, base_ptr(ph, v), P.vals[v].nelem));
+            std::vector<int64_t> idx(ph.sliced.size(), 0);
+            for (int64_t it = 0; it < ph.nsl; ++it) {
+                int64_t rem = it;
+                for (size_t s = 0; s < idx.size(); ++s) { idx[s] = rem % ph.ssz[s]; rem /= ph.ssz[s]; }
+                auto ptr_of = [&](int v) -> cplx* {
+                    if (v < 0) return ctx->one_dev;
+                    cplx* p = base_ptr(ph, v);
+                    const PView& pv = ph.views.at(v);
+                    for (size_t s = 0; s < idx.size(); ++s) p += idx[s] * pv.sl_stride[s];
+                    return p;
+                };
+                for (auto& po : ph.ops) {
+                    if (po.first_slice_only && it > 0) continue;
+                    TNE_TRY(contract_run(ctx, po.plan, ptr_of(po.op.a), ptr_of(po.op.b), ptr_of(po.op.out)));
+                    if (po.op.recompute) P.re_flops += po.plan.flops; else { P.flops += po.plan.flops; P.bytes += po.plan.bytes; }
+                    P.n_contract++;
+                }
+            }
+        }
+        return TNE_OK;
+    }
+};
 
 }  // namespace
 
@@ -520,32 +704,46 @@ extern "C" int tne_expect_terms(tne_ctx* ctx, const tne_tree* tree, const tne_bu
     int root = -1;
     TNE_TRY(build_forward(B, leaves, leaf_conj, true, &root));
     P.root_val = root;
+    Exec E(P);
+    TNE_TRY(E.assign_segments(tree));
 
-    // output value (accumulated over slices) lives in a user-visible buffer
+    // outputs live in user-visible buffers, cleared once; every write into them accumulates
+    // (over global slices, segment slices and repeated contributions alike)
+    std::vector<tne_buf> owned;
+    auto fail_cleanup = [&](int rc) { for (auto h : owned) tne_free(ctx, h); return rc; };
     tne_buf hval;
     TNE_TRY(buf_new(ctx, P.vals[root].dims, &hval));
-    const bool sliced = tree->n_sliced > 0;
+    owned.push_back(hval);
+    {
+        Buf* vb = buf_get(ctx, hval);
+        P.vals[root].ext = vb->ptr();
+        int rc = launch_fill_zero(ctx, vb->ptr(), vb->nelem);
+        if (rc) return fail_cleanup(rc);
+    }
     std::vector<tne_buf> hgrads;
-    std::vector<int> grad_vals;
-    int seed_val = -1;
     tne_buf hseed = 0;
     if (n_grad > 0) {
-        if (P.vals[root].nelem != 1) { tne_free(ctx, hval); return tne_fail(ctx, TNE_ERR_UNSUPPORTED, "gradients need a scalar output"); }
-        TNE_TRY(buf_new(ctx, {}, &hseed));
+        if (P.vals[root].nelem != 1) return fail_cleanup(tne_fail(ctx, TNE_ERR_UNSUPPORTED, "gradients need a scalar output"));
+        int rc = buf_new(ctx, {}, &hseed);
+        if (rc) return fail_cleanup(rc);
+        owned.push_back(hseed);
         cplx s = make_double2(seed_re, seed_im);
         TNE_CUDA(ctx, cudaMemcpyAsync(buf_get(ctx, hseed)->ptr(), &s, sizeof(cplx), cudaMemcpyHostToDevice, ctx->stream));
         TNE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        seed_val = P.new_val({}, {});
+        int seed_val = P.new_val({}, {});
         P.vals[seed_val].ext = buf_get(ctx, hseed)->ptr();
         P.written[seed_val] = true;
         for (int g = 0; g < n_grad; ++g) {
             int lf = grad_leaves[g];
-            if (lf < 0 || lf >= tree->n_leaves) return tne_fail(ctx, TNE_ERR_INVALID, "gradient requested for unknown leaf %d", lf);
+            if (lf < 0 || lf >= tree->n_leaves) return fail_cleanup(tne_fail(ctx, TNE_ERR_INVALID, "gradient requested for unknown leaf %d", lf));
             Buf* lb = buf_get(ctx, leaves[lf]);
             tne_buf hg;
-            TNE_TRY(buf_new(ctx, lb->dims, &hg));
+            rc = buf_new(ctx, lb->dims, &hg);
+            if (rc) return fail_cleanup(rc);
+            owned.push_back(hg);
             Buf* gb = buf_get(ctx, hg);
-            TNE_TRY(launch_fill_zero(ctx, gb->ptr(), gb->nelem));
+            rc = launch_fill_zero(ctx, gb->ptr(), gb->nelem);
+            if (rc) return fail_cleanup(rc);
             hgrads.push_back(hg);
             int lv = B.nodes[lf].var[Key()];
             P.vals[lv].needs_grad = true;
@@ -557,60 +755,29 @@ extern "C" int tne_expect_terms(tne_ctx* ctx, const tne_tree* tree, const tne_bu
             gv.ext = gb->ptr();
             gv.leaf = lf;
             P.vals.push_back(gv);
-            P.written.push_back(true);  // pre-zeroed: every write accumulates
+            P.written.push_back(true);
             P.vals[lv].grad = (int)P.vals.size() - 1;
-            grad_vals.push_back(P.vals[lv].grad);
         }
         build_backward(P, root, seed_val);
     }
-    // root: write into the output buffer; with slices it accumulates across slices
     {
-        Buf* vb = buf_get(ctx, hval);
-        P.vals[root].ext = vb->ptr();
-        if (sliced) {
-            TNE_TRY(launch_fill_zero(ctx, vb->ptr(), vb->nelem));
-            for (auto& op : P.fwd) if (op.out == root) op.acc = true;
-        }
+        int rc = E.build(tree, n_grad > 0);
+        if (rc) return fail_cleanup(rc);
     }
-
-    // memory plan with automatic recompute threshold
-    int64_t budget = ctx->mem_limit - ctx->in_use;
-    std::vector<int64_t> cands;
-    for (auto& v : P.vals) if (!v.ext) cands.push_back(v.nelem * (int64_t)sizeof(cplx));
-    std::sort(cands.begin(), cands.end(), std::greater<int64_t>());
-    cands.erase(std::unique(cands.begin(), cands.end()), cands.end());
-    const size_t nvals0 = P.vals.size();
-    int64_t peak = 0;
-    int64_t thr = ctx->opt_recompute_threshold;
-    bool ok = false;
-    if (thr >= 0 || n_grad == 0) {
-        schedule(P, n_grad == 0 ? -1 : thr);
-        peak = plan_memory(P);
-        ok = peak <= budget;
-    } else {
-        schedule(P, -1);
-        peak = plan_memory(P);
-        ok = peak <= budget;
-        for (size_t c = 0; !ok && c < cands.size(); ++c) {
-            P.vals.resize(nvals0);
-            P.written.resize(nvals0);
-            schedule(P, cands[c] - 1);
-            peak = plan_memory(P);
-            ok = peak <= budget;
-            thr = cands[c] - 1;
-        }
-    }
-    if (!ok) {
-        tne_free(ctx, hval);
-        for (auto h : hgrads) tne_free(ctx, h);
-        if (hseed) tne_free(ctx, hseed);
-        return tne_fail(ctx, TNE_ERR_OOM, "tree program needs %lld bytes of workspace but the budget is %lld; slice more labels",
-                        (long long)peak, (long long)budget);
-    }
+    const int64_t budget = ctx->mem_limit - ctx->in_use;
+    const int64_t peak = E.persist_bytes + E.temp_bytes;
+    if (peak > budget)
+        return fail_cleanup(tne_fail(ctx, TNE_ERR_OOM,
+                                     "tree program needs %lld bytes of workspace (%lld checkpoints + %lld per-segment) but the budget is %lld; "
+                                     "use more segments / slice more labels",
+                                     (long long)peak, (long long)E.persist_bytes, (long long)E.temp_bytes, (long long)budget));
     P.ws_bytes = peak;
-    TNE_TRY(ws_reserve(ctx, peak));
+    {
+        int rc = ws_reserve(ctx, peak);
+        if (rc) return fail_cleanup(rc);
+    }
 
-    // slice loop
+    // global slice loop (SlicedEinsum), sharded by rank
     std::vector<int64_t> ssz(tree->n_sliced, 1);
     for (int s = 0; s < tree->n_sliced; ++s) {
         bool found = false;
@@ -618,13 +785,11 @@ extern "C" int tne_expect_terms(tne_ctx* ctx, const tne_tree* tree, const tne_bu
             int q = find_in(B.leaf_labels[i], tree->sliced_labels[s]);
             if (q >= 0) { ssz[s] = buf_get(ctx, leaves[i])->dims[q]; found = true; }
         }
-        if (!found) return tne_fail(ctx, TNE_ERR_INVALID, "sliced label %d is not on any leaf", (int)tree->sliced_labels[s]);
+        if (!found) return fail_cleanup(tne_fail(ctx, TNE_ERR_INVALID, "sliced label %d is not on any leaf", (int)tree->sliced_labels[s]));
     }
     int64_t nslices = 1;
     for (auto s : ssz) nslices *= s;
     const int world = std::max(1, (int)tree->shard_world), rank = tree->shard_rank;
-    bool first = true;
-    (void)first;
     for (int64_t it = 0; it < nslices; ++it) {
         if (it % world != rank) continue;
         if (tree->n_sliced > 0) {
@@ -644,14 +809,20 @@ extern "C" int tne_expect_terms(tne_ctx* ctx, const tne_tree* tree, const tne_bu
                 v.slice_base = base;
             }
         }
-        TNE_TRY(run_ops(P, true));
-        first = false;
+        int rc = E.run();
+        if (rc) return fail_cleanup(rc);
     }
     ctx->stats[0] = P.flops; ctx->stats[1] = P.bytes; ctx->stats[2] = (double)P.n_contract;
     ctx->stats[3] = (double)peak; ctx->stats[4] = P.re_flops; ctx->stats[5] = (double)P.vals.size();
-    if (ctx->opt_debug)
-        fprintf(stderr, "[tne] program: %zu fwd ops, %zu bwd ops, %zu scheduled, workspace %.3f GiB, recompute threshold %lld, flops %.3e (+%.3e recomputed)\n",
-                P.fwd.size(), P.bwd.size(), P.all.size(), peak / 1073741824.0, (long long)thr, P.flops, P.re_flops);
+    if (ctx->opt_debug) {
+        fprintf(stderr, "[tne] program: %zu fwd ops, %zu bwd ops, %zu phases, workspace %.3f GiB (checkpoints %.3f + segment %.3f), flops %.3e (+%.3e recomputed), %lld launches\n",
+                P.fwd.size(), P.bwd.size(), E.phases.size(), peak / 1073741824.0, E.persist_bytes / 1073741824.0,
+                E.temp_bytes / 1073741824.0, P.flops, P.re_flops, (long long)P.n_contract);
+        if (ctx->opt_debug > 1)
+            for (auto& ph : E.phases)
+                fprintf(stderr, "[tne]   phase seg %d %s: %zu ops x %lld slices, temp %.3f GiB\n", ph.seg, ph.backward ? "bwd" : "fwd",
+                        ph.ops.size(), (long long)ph.nsl, ph.temp_bytes / 1073741824.0);
+    }
     if (hseed) tne_free(ctx, hseed);
     *value_out = hval;
     for (int g = 0; g < n_grad; ++g) grads_out[g] = hgrads[g];

@@ -49,6 +49,8 @@ class NestedEinsum:
         self.eins = eins
         self.tensorindex = tensorindex
         self._ser = None
+        # optional checkpointed segments (root only): [(first post-order node index, [sliced labels]), ...]
+        self.segments = None
 
     def isleaf(self):
         return self.tensorindex >= 0
@@ -129,6 +131,20 @@ class SerializedTree:
         t.n_sliced = len(slicing)
         t.sliced_labels = self._keep["sliced"]
         t.shard_rank, t.shard_world = shard
+        segs = nested.segments or []
+        if len(segs) > 1:
+            off = [0]
+            for _, ls in segs:
+                off.append(off[-1] + len(ls))
+            self._keep["seg_first"] = _i32([f for f, _ in segs])
+            self._keep["seg_off"] = _i32(off)
+            self._keep["seg_labels"] = _i32([l for _, ls in segs for l in ls])
+            t.n_segments = len(segs)
+            t.seg_first_node = self._keep["seg_first"]
+            t.seg_sliced_off = self._keep["seg_off"]
+            t.seg_sliced_labels = self._keep["seg_labels"]
+        else:
+            t.n_segments = 0
         self.struct = t
         self.root_iy = list(nested.eins.iy)
 
@@ -284,15 +300,21 @@ def pick_slices(nested, iy, size_dict, nslices):
     return chosen
 
 
-def optimize_code(ixs, iy, size_dict, optimizer="greedy", nslices=0, slicing=None):
+def optimize_code(ixs, iy, size_dict, optimizer="greedy", nslices=0, slicing=None, segments=None):
     """``optimize_code(EinCode(ixs, iy), size_dict, optimizer, simplifier)`` (src/peps.jl:87,91).
 
     ``optimizer``: ``"greedy"`` or an explicit leaf order (list).  ``nslices`` / ``slicing``
-    produce a ``SlicedEinsum`` (the role of ``TreeSA(nslices=k)``, test/peps.jl:9)."""
+    produce a ``SlicedEinsum`` (the role of ``TreeSA(nslices=k)``, test/peps.jl:9).
+    ``segments`` (explicit leaf order only): ``[(position in the order, [labels]), ...]`` -- a
+    checkpointed segment starts at the node that absorbs ``order[position]`` and loops over the
+    given labels (see ``tne_tree`` in include/tne.h); the first entry must have position 0 or 1."""
     if len(ixs) == 1:
         raise ValueError("a single-tensor network needs no order")
     if isinstance(optimizer, (list, tuple)):
         nested = optimize_sequence(ixs, iy, list(optimizer))
+        if segments:
+            # left-deep chain: post-order node j absorbs order[j + 1]
+            nested.segments = [(max(0, pos - 1), list(ls)) for pos, ls in segments]
     else:
         nested = optimize_greedy(ixs, iy, size_dict)
     if slicing:

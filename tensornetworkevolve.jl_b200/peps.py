@@ -90,8 +90,10 @@ class VidalPEPS(PEPS):
     kind = "vidal"
 
 
-def _optimized_code(alllabels, physical_labels, virtual_labels, max_ind, nflavor, D, optimizer, nslices):
-    """src/peps.jl:84-93."""
+def _optimized_code(alllabels, physical_labels, virtual_labels, max_ind, nflavor, D, optimizer, nslices, segments=None):
+    """src/peps.jl:84-93.  ``segments``: ``[(site, [bond labels]), ...]`` for an explicit sweep order -- a
+    checkpointed segment of the inner-product tree starts where ``site``'s bra tensor is absorbed and loops
+    over the given bonds (bra and ket copy of each)."""
     size_dict = {l: nflavor for l in physical_labels}
     size_dict.update({l: D for l in virtual_labels})
     st_opt = "greedy" if isinstance(optimizer, (list, tuple)) else optimizer
@@ -100,12 +102,15 @@ def _optimized_code(alllabels, physical_labels, virtual_labels, max_ind, nflavor
     for l in rep.values():
         size_dict[l] = D
     ixs = [list(l) for l in alllabels] + [[rep.get(x, x) for x in l] for l in alllabels]
-    code_ip = es.optimize_code(ixs, [], size_dict, optimizer, nslices)
+    segs = None
+    if segments and isinstance(optimizer, (list, tuple)):
+        segs = [(list(optimizer).index(site - 1), [l for b in bonds for l in (b, rep[b])]) for site, bonds in segments]
+    code_ip = es.optimize_code(ixs, [], size_dict, optimizer, nslices, segments=segs)
     return code_st, code_ip
 
 
 def make_peps(kind, vertex_labels, vertex_tensors, virtual_labels, Dmax, eps, nflavor=2, bond_tensors=None,
-              optimizer="greedy", nslices=0):
+              optimizer="greedy", nslices=0, segments=None):
     """The label-deriving constructors, src/peps.jl:69-82 and :142-151."""
     physical_labels = []
     for vl in vertex_labels:
@@ -122,7 +127,7 @@ def make_peps(kind, vertex_labels, vertex_tensors, virtual_labels, Dmax, eps, nf
     alll = [list(l) for l in vertex_labels]
     if kind == "vidal":
         alll = alll + [[l] for l in virtual_labels]
-    cst, cip = _optimized_code(alll, physical_labels, virtual_labels, max_ind, nflavor, Dmax, optimizer, nslices)
+    cst, cip = _optimized_code(alll, physical_labels, virtual_labels, max_ind, nflavor, Dmax, optimizer, nslices, segments)
     cls = VidalPEPS if kind == "vidal" else SimplePEPS
     return cls(physical_labels, virtual_labels, vertex_labels, vertex_tensors, max_ind, cst, cip, Dmax, eps,
                nflavor, bond_tensors)
@@ -217,7 +222,24 @@ def load_variables(peps, variables):
 
 
 # -- factories, src/peps.jl:244-280 -----------------------------------------------------
-def _peps_zero_state(kind, g, D, nflavor=2, Dmax=None, eps=1e-12, optimizer="greedy", nslices=0):
+def sweep_plan(g, L):
+    """Boundary-sweep contraction plan for an ``L x L`` ``grid`` PEPS (vertex ``v = x + (y-1) L``): the leaf
+    order ``bra_1, ket_1, bra_2, ...`` and one checkpointed segment per lattice column ``y``.  Column
+    ``y >= 2`` loops over the bond between the last sites of columns ``y-1`` and ``y``: it is open during
+    the whole column, so slicing it costs no flops and divides the column's tape by ``D^2``."""
+    n = g.nv()
+    order = []
+    for i in range(n):
+        order += [i, n + i]
+    emap = {e: n + 1 + k for k, e in enumerate(g.edges())}
+    segments = [(1, [])]
+    for y in range(2, L + 1):
+        a, b = L + (y - 2) * L, L + (y - 1) * L
+        segments.append((1 + (y - 1) * L, [emap[(a, b)]]))
+    return order, segments
+
+
+def _peps_zero_state(kind, g, D, nflavor=2, Dmax=None, eps=1e-12, optimizer="greedy", nslices=0, segments=None):
     Dmax = D if Dmax is None else Dmax
     nv, ne = g.nv(), g.ne()
     virtual_labels = list(range(nv + 1, nv + ne + 1))
@@ -232,7 +254,7 @@ def _peps_zero_state(kind, g, D, nflavor=2, Dmax=None, eps=1e-12, optimizer="gre
     if any(0 in vl for vl in vertex_labels):
         raise ValueError("incorrect input labels1")
     bonds = [B200Array.from_numpy(np.ones(D, dtype=np.complex128)) for _ in range(ne)] if kind == "vidal" else None
-    return make_peps(kind, vertex_labels, vertex_tensors, virtual_labels, Dmax, eps, nflavor, bonds, optimizer, nslices)
+    return make_peps(kind, vertex_labels, vertex_tensors, virtual_labels, Dmax, eps, nflavor, bonds, optimizer, nslices, segments)
 
 
 def zero_simplepeps(g, D, **kw):
@@ -499,19 +521,15 @@ def _expect_fused(terms, pa, pb, shard):
     if not diff:
         val, _ = es.expect_terms_device(code, leaves, cj, tlist)
         return val
-    val, _ = es.expect_terms_device(code, leaves, cj, tlist)
-    cache = {}
+    # value and the pullbacks for a unit cotangent in ONE device program (forward + reverse sweep); the
+    # pullback is linear in the cotangent, so back(dy) only rescales the stored gradients
     gl = [i for i in range(nt) if ad.requires_grad(bra[i])]
+    val, grads = es.expect_terms_device(code, leaves, cj, tlist, gl, 1.0 + 0j)
+    gmap = dict(zip(gl, grads))
 
     def mk(i):
         def back(dy):
-            key = id(dy)
-            if key not in cache:
-                cache.clear()
-                _, grads = es.expect_terms_device(code, leaves, cj, tlist, gl, 1.0 + 0j)
-                cache[key] = (dy, dict(zip(gl, grads)))
-            g = cache[key][1][i]
             # bra leaves enter conjugated: the pullback is antilinear in the cotangent
-            return DiffTensor(g.bmul(dy.data.to_complex().conj()), requires_grad=False)
+            return DiffTensor(gmap[i].bmul(dy.data.to_complex().conj()), requires_grad=False)
         return back
     return ad.difftensor(val, "expect", *[(bra[i], mk(i)) for i in range(nt)])

@@ -60,13 +60,17 @@ def iloss2(h, peps, variables, shard=(0, 1)):  # src/timeevolve.jl:55-60
     return _real(P.expect(h, P.conj(pl), pr, shard=shard))
 
 
-def wrap_difftensor(peps):  # src/timeevolve.jl:65-67
-    return P.replace_tensors(peps, [t if isinstance(t, DiffTensor) else DiffTensor(t) for t in peps.alltensors()])
+def wrap_difftensor(peps, requires_grad=True):  # src/timeevolve.jl:65-67
+    return P.replace_tensors(peps, [t if isinstance(t, DiffTensor) else DiffTensor(t, requires_grad=requires_grad)
+                                    for t in peps.alltensors()])
 
 
 def fvec(peps, h, shard=(0, 1)):  # src/timeevolve.jl:61-64
+    """The reference wraps the constant ``peps`` with ``requires_grad = true`` and then discards those
+    gradients; here the constant side is wrapped with ``requires_grad = false`` (same result, no wasted
+    reverse pass through ``norm(peps)``)."""
     variables = P.variables(peps)
-    g = ad.gradient(lambda x: iloss2(h, wrap_difftensor(peps), x, shard=shard), DiffTensor(variables))[0]
+    g = ad.gradient(lambda x: iloss2(h, wrap_difftensor(peps, False), x, shard=shard), DiffTensor(variables))[0]
     return ad.mul(-1j, g)
 
 
@@ -77,7 +81,7 @@ def energy_and_gradient(peps, h, shard=(0, 1)):
     proportional to the rank's partial energy, so partial results add up exactly)."""
     variables = DiffTensor(P.variables(peps))
     ad.GLOBAL_TAPE.instructs.clear()
-    y = iloss2(h, wrap_difftensor(peps), variables, shard=shard)
+    y = iloss2(h, wrap_difftensor(peps, False), variables, shard=shard)
     storage = ad.init_storage_(y)
     ad.back_(ad.GLOBAL_TAPE, storage)
     g = ad.getgrad(storage, variables)

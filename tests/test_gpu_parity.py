@@ -181,3 +181,34 @@ def test_linearity_and_scaling_properties(tne):
     # L(s x) = L(x) for real s > 0  =>  Re <x, grad> = 0 with grad = i * fvec
     grad = 1j * f
     assert abs(np.real(np.vdot(v, grad))) < 1e-9 * np.linalg.norm(v) * np.linalg.norm(grad)
+
+
+# -- checkpointed segments with segment-local slicing (the 6x6 D=4 execution plan) at oracle-checkable size --
+@pytest.mark.parametrize("L,D", [(3, 2), (4, 3)])
+def test_segmented_program_matches_oracle(tne, L, D):
+    ctx = tne.context()
+    g = OG.grid([L, L])
+    gd = tne.grid([L, L])
+    order, segs = tne.sweep_plan(gd, L)
+    assert order == sweep_order(L * L) and len(segs) == L
+    op = oracle_peps(g, D, seed_for(L, D), optimizer=order)
+    dp = device_peps_like(tne, op, g, D, optimizer=order, segments=segs)
+    assert dp.code_inner_product.segments is not None
+    h = OT.rydberg_hamiltonian(g, 10.0, 0.2, 0.3)
+    hd = to_device_hamiltonian(tne, h)
+    assert rel(tne.norm(dp).to_numpy(), OP.norm(op)) < TOL
+    assert rel(tne.expect(hd, dp, dp).to_numpy(), OP.expect(h, op, op)) < TOL
+    fref = OTE.fvec(op, h).data
+    y, f = tne.energy_and_gradient(dp, hd)
+    st = ctx.program_stats()
+    assert rel(f.to_numpy(), fref) < TOL
+    assert rel(y.to_numpy(), OTE.iloss2(h, op, OP.variables(op))) < TOL
+    assert st["recompute_flops"] > 0  # the reverse pass did re-run segment forwards
+    # segments + a globally sliced label + term sharding together
+    ds = device_peps_like(tne, op, g, D, optimizer=order, segments=segs, nslices=1)
+    parts = [tne.energy_and_gradient(ds, hd, shard=(r, 3)) for r in range(3)]
+    assert rel(sum(p[1].to_numpy() for p in parts), fref) < TOL
+    # gradient of the plain norm w.r.t. every leaf through the segmented reverse pass
+    gref = OAD.gradient(lambda x: OP.norm(OP.load_variables(op, x)), OAD.DiffTensor(OP.variables(op)))[0].data
+    gdev = tne.gradient(lambda x: tne.norm(tne.load_variables(dp, x)), tne.DiffTensor(tne.variables(dp)))[0].to_numpy()
+    assert rel(gdev, gref) < TOL
