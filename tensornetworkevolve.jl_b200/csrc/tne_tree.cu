@@ -549,6 +549,18 @@ struct Exec {
             TensorRef Bt;
             if (op.kind == OP_CONTRACT) Bt = ref_of(ph, op.b, op.conj_b);
             TNE_TRY(contract_plan(ctx, A, Bt, C, op.acc, op.are, op.aim, &po.plan));
+            if (ctx->opt_debug > 2 && !po.plan.empty) {
+                const GettDesc& d = po.plan.d;
+                fprintf(stderr, "[tne-op] seg %d %s%s kind %d kernel %d acc %d swap %d M %lld N %lld K %lld B %lld conj %d%d |", ph.seg,
+                        op.backward ? "bwd" : "fwd", op.recompute ? "(re)" : "", op.kind, po.plan.kernel, (int)op.acc, (int)po.plan.swapped,
+                        d.Msz, d.Nsz, d.Ksz, d.Bsz, d.conjA, d.conjB);
+                auto dump = [&](const char* nm, const LegSet& L) {
+                    fprintf(stderr, " %s:", nm);
+                    for (int i = 0; i < L.n; ++i) fprintf(stderr, " %d(%lld,%lld,%lld)", L.size[i], L.s0[i], L.s1[i], L.s2[i]);
+                };
+                dump("M[a,c]", d.M); dump("N[b,c]", d.N); dump("K[a,b]", d.K); dump("Bt[a,b,c]", d.Bt);
+                fprintf(stderr, "\n");
+            }
             ph.ops.push_back(std::move(po));
         }
         // temp arena of this phase

@@ -27,6 +27,17 @@ def test_binary_einsum_shapes(tne, force_generic):
         ([[1, 2], [3, 4]], [(3, 4), (2, 5)], [4, 1, 3, 2]),                              # outer product + permute
         ([[1, 2, 3, 4, 5, 6], [2, 7, 5]], [(4, 4, 4, 4, 4, 4), (4, 2, 4)], [1, 3, 4, 6, 7]),  # absorb shape
         ([[1, 2, 3], [1, 2, 4]], [(64, 64, 3), (64, 64, 5)], [3, 4]),                   # reduce shape (long K)
+        # DMMA absorb kernel: big M, K legs at the fastest and a slow position, N appended (forward sweep step)
+        ([[1, 2, 3, 4, 5, 6, 7, 8], [1, 9, 7, 10]], [(4, 4, 4, 4, 4, 4, 4, 2), (4, 2, 4, 4)], [2, 3, 4, 5, 6, 8, 9, 10]),
+        # ... its reverse: K slow, N lands on the fastest output position
+        ([[2, 3, 4, 5, 6, 8, 9, 10], [1, 9, 7, 10]], [(4, 4, 4, 4, 4, 2, 2, 4), (4, 2, 4, 4)], [1, 2, 3, 4, 5, 6, 7, 8]),
+        # odd dimensions (D = 3): padded k-steps and n-tiles
+        ([[1, 2, 3, 4, 5, 6, 7, 8], [1, 9, 7, 10]], [(3, 3, 3, 3, 3, 3, 3, 2), (3, 2, 3, 3)], [2, 3, 4, 5, 6, 8, 9, 10]),
+        ([[1, 2, 3, 4], [3, 5]], [(16, 16, 3, 16), (3, 5)], [1, 2, 5, 4]),
+        # DMMA reduce kernel: leaf gradient shape (tiny output, long reduction)
+        ([[1, 2, 3, 4, 5], [1, 2, 3, 6, 7]], [(32, 32, 16, 4, 2), (32, 32, 16, 4, 4)], [4, 5, 6, 7]),
+        ([[4, 1, 2, 3, 5], [1, 6, 2, 3, 7]], [(4, 32, 32, 16, 2), (32, 3, 32, 16, 3)], [6, 7, 5, 4]),
+        ([[1, 2, 3], [1, 2, 4]], [(128, 80, 3), (128, 80, 5)], [3, 4]),
         ([[1, 2, 3]], [(3, 4, 5)], [3, 1, 2]),                                           # unary permute
         ([[1, 2, 3]], [(3, 4, 5)], [2]),                                                 # unary sum
     ]
