@@ -58,6 +58,14 @@ class Context:
         return dict(flops=s[0], bytes=s[1], contractions=int(s[2]), workspace_bytes=int(s[3]),
                     recompute_flops=s[4], values=int(s[5]))
 
+    def profile_collect(self):
+        """Per kernel class: launches, device ms, algorithmic flops and bytes since the last call."""
+        out = (C.c_double * 16)()
+        self.check(self.L.tne_profile_collect(self.h, out))
+        names = ["gett_generic", "gett_absorb", "gett_reduce", "other"]
+        return {names[c]: dict(launches=int(out[4 * c]), ms=out[4 * c + 1], flops=out[4 * c + 2], bytes=out[4 * c + 3])
+                for c in range(4)}
+
     def mem_info(self):
         a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
         self.check(self.L.tne_mem_info(self.h, C.byref(a), C.byref(b), C.byref(c)))
@@ -102,7 +110,10 @@ class B200Array:
         ctx = ctx or context()
         x = np.asarray(x)
         is_real = not np.iscomplexobj(x)
-        host = np.array(x, dtype=np.complex128, order="F")  # keeps 0-dim arrays 0-dim
+        if x.dtype == np.complex128 and x.ndim > 0 and x.flags.f_contiguous:
+            host = x  # borrowed as is (e.g. a pinned staging buffer): no extra host copy
+        else:
+            host = np.array(x, dtype=np.complex128, order="F")  # keeps 0-dim arrays 0-dim
         h = C.c_int64()
         ctx.check(ctx.L.tne_alloc(ctx.h, host.ndim, _i64(host.shape), C.byref(h)))
         if host.size:
@@ -277,3 +288,23 @@ def einsum_device(ixs, xs, iy, conj=None):
         for l, s in zip(ix, x.shape):
             sizes[l] = s
     return B200Array(h.value, tuple(sizes[l] for l in iy), all(x.is_real for x in xs), ctx)
+
+
+def init_comm(ctx, dist, rank, world):
+    """Create the library's NCCL communicator (``tne_comm_init``); the unique id travels through the
+    host program's ``torch.distributed`` group."""
+    import torch
+    idbuf = (C.c_ubyte * 128)()
+    if rank == 0:
+        ctx.check(ctx.L.tne_nccl_unique_id(idbuf))
+    t = torch.tensor(list(bytes(idbuf)), dtype=torch.uint8)
+    if dist.get_backend() == "nccl":
+        t = t.cuda()
+    dist.broadcast(t, 0)
+    raw = bytes(t.cpu().tolist())
+    ctx.check(ctx.L.tne_comm_init(ctx.h, C.create_string_buffer(raw, 128), rank, world))
+
+
+def allreduce_sum(ctx, arrays):
+    """In-place sum over the ranks (``tne_allreduce_sum``: NCCL over NVLink)."""
+    ctx.check(ctx.L.tne_allreduce_sum(ctx.h, len(arrays), _i64([a.handle for a in arrays])))

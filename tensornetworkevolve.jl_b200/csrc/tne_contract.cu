@@ -288,8 +288,26 @@ int contract_plan(tne_ctx* ctx, const TensorRef& A0, const TensorRef& B0, const 
     return TNE_OK;
 }
 
+static int contract_run_inner(tne_ctx* ctx, const ContractPlan& plan, const cplx* A, const cplx* B, cplx* C);
+
 int contract_run(tne_ctx* ctx, const ContractPlan& plan, const cplx* A, const cplx* B, cplx* C) {
     if (plan.empty) return TNE_OK;
+    if (!ctx->opt_profile) return contract_run_inner(ctx, plan, A, B, C);
+    tne_ctx::ProfRec r;
+    cudaEvent_t* ev[2] = {&r.e0, &r.e1};
+    for (auto e : ev) {
+        if (!ctx->event_pool.empty()) { *e = ctx->event_pool.back(); ctx->event_pool.pop_back(); }
+        else TNE_CUDA(ctx, cudaEventCreate(e));
+    }
+    r.cls = plan.kernel; r.flops = plan.flops; r.bytes = plan.bytes;
+    TNE_CUDA(ctx, cudaEventRecord(r.e0, ctx->stream));
+    int rc = contract_run_inner(ctx, plan, A, B, C);
+    TNE_CUDA(ctx, cudaEventRecord(r.e1, ctx->stream));
+    ctx->prof.push_back(r);
+    return rc;
+}
+
+static int contract_run_inner(tne_ctx* ctx, const ContractPlan& plan, const cplx* A, const cplx* B, cplx* C) {
     if (plan.swapped) std::swap(A, B);
     if (plan.kernel != 0) return gett_fast_run(ctx, plan, A, B, C);
     if (plan.zero_first) TNE_TRY(launch_fill_zero(ctx, C, plan.c_nelem));

@@ -222,10 +222,26 @@ extern "C" int tne_last_program_stats(tne_ctx* ctx, double* s) {
     return TNE_OK;
 }
 
+extern "C" int tne_profile_collect(tne_ctx* ctx, double* out) {
+    for (int i = 0; i < 4 * TNE_PROFILE_CLASSES; ++i) out[i] = 0.0;
+    TNE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (auto& r : ctx->prof) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, r.e0, r.e1);
+        int c = std::min(std::max(r.cls, 0), TNE_PROFILE_CLASSES - 1);
+        out[4 * c] += 1.0; out[4 * c + 1] += ms; out[4 * c + 2] += r.flops; out[4 * c + 3] += r.bytes;
+        ctx->event_pool.push_back(r.e0);
+        ctx->event_pool.push_back(r.e1);
+    }
+    ctx->prof.clear();
+    return TNE_OK;
+}
+
 extern "C" int tne_set_option(tne_ctx* ctx, const char* key, int64_t value) {
     std::string k(key ? key : "");
     if (k == "force_generic_kernel") ctx->opt_force_generic = value;
     else if (k == "debug") ctx->opt_debug = value;
+    else if (k == "profile") ctx->opt_profile = value;
     else return tne_fail(ctx, TNE_ERR_INVALID, "unknown option '%s'", k.c_str());
     return TNE_OK;
 }

@@ -49,6 +49,10 @@ struct tne_ctx {
     // options
     int64_t opt_force_generic = 0;
     int64_t opt_debug = 0;
+    int64_t opt_profile = 0;
+    struct ProfRec { cudaEvent_t e0, e1; int cls; double flops, bytes; };
+    std::vector<ProfRec> prof;              // pending event pairs
+    std::vector<cudaEvent_t> event_pool;
     cplx* one_dev = nullptr;               // device constant 1+0i
     void* nccl = nullptr;                  // ncclComm_t
     void* nccl_lib = nullptr;
