@@ -62,7 +62,7 @@ class Context:
         """Per kernel class: launches, device ms, algorithmic flops and bytes since the last call."""
         out = (C.c_double * 16)()
         self.check(self.L.tne_profile_collect(self.h, out))
-        names = ["gett_generic", "gett_absorb", "gett_reduce", "other"]
+        names = ["gett_generic", "gett_absorb", "gett_reduce", "gett_absorb_tma"]
         return {names[c]: dict(launches=int(out[4 * c]), ms=out[4 * c + 1], flops=out[4 * c + 2], bytes=out[4 * c + 3])
                 for c in range(4)}
 

@@ -157,6 +157,8 @@ static int fill_legset(tne_ctx* ctx, LegSet& L, const std::vector<HLeg>& legs, i
     auto pick = [](const HLeg& l, int w) -> long long { return w == 0 ? l.sa : (w == 1 ? l.sb : (w == 2 ? l.sc : 0)); };
     for (int i = 0; i < L.n; ++i) {
         L.size[i] = (int)legs[i].size;
+        L.shift[i] = -1;
+        if ((legs[i].size & (legs[i].size - 1)) == 0) { int sh = 0; while ((1LL << sh) < legs[i].size) ++sh; L.shift[i] = sh; }
         L.s0[i] = pick(legs[i], which0);
         L.s1[i] = pick(legs[i], which1);
         L.s2[i] = pick(legs[i], which2);
@@ -239,6 +241,11 @@ int contract_plan(tne_ctx* ctx, const TensorRef& A0, const TensorRef& B0, const 
     }
     contract_cost(A0, B0, C, &plan->flops, &plan->bytes);
     plan->c_nelem = C.nelem();
+    if (!C.strides.empty()) {  // memory extent of a strided / padded output (cleared before split-K atomics)
+        int64_t ext = 1;
+        for (size_t i = 0; i < C.dims.size(); ++i) ext += (C.dims[i] - 1) * C.strides[i];
+        plan->c_nelem = C.nelem() == 0 ? 0 : ext;
+    }
     plan->empty = (cl.Msz * cl.Nsz * cl.Bsz == 0);
     if (plan->empty) return TNE_OK;
     GettDesc& d = plan->d;

@@ -28,15 +28,121 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                  : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-enum { KERNEL_ABSORB = 1, KERNEL_REDUCE = 2 };
+enum { KERNEL_ABSORB = 1, KERNEL_REDUCE = 2, KERNEL_ABSORB_TMA = 3 };
 
 // ---------------------------------------------------------------------------------------
 // absorb
 // ---------------------------------------------------------------------------------------
 // KS: DMMA k-steps (4 reals = 2 complex k each); padded K = 2 * KS complex.
-template <int KS>
-__global__ void __launch_bounds__(256, 2) gett_absorb(const __grid_constant__ GettDesc d, const cplx* __restrict__ A,
-                                                   const cplx* __restrict__ B, cplx* __restrict__ C, int Np) {
+// MTW: 8-row m-tiles per warp iteration.  The A fragments of the NEXT tile are fetched into a second
+// register set before the current tile's DMMAs are issued, so every warp always has HBM loads in flight
+// under its math and its stores (software pipeline; there is no shared-memory stage for A because each
+// A element is consumed by exactly one warp).
+template <int KS, int MTW>
+struct AbsorbTile {
+    long long oC[MTW];
+    bool ok[MTW];
+    double a[MTW][KS];
+};
+
+// Row -> (A offset, C offset).  A warp walks consecutive tiles, so the decomposition of everything above
+// the fastest M leg is cached per lane and only redone when that outer index changes (a few hundred
+// cycles of dependent integer latency per tile otherwise -- more than the tile's DMMA issue time).
+struct RowCache {
+    long long outer = -1, baseA = 0, baseC = 0;
+};
+__device__ __forceinline__ void row_offsets(const GettDesc& d, RowCache& rc, long long row, long long& oA, long long& oC) {
+    const int sh = d.M.shift[0];
+    long long i0, outer;
+    if (d.M.n == 0) { oA = 0; oC = 0; return; }
+    if (sh >= 0) { i0 = row & (long long)(d.M.size[0] - 1); outer = row >> sh; }
+    else { outer = row / d.M.size[0]; i0 = row - outer * d.M.size[0]; }
+    if (outer != rc.outer) {
+        rc.outer = outer;
+        long long a = 0, c = 0, idx = outer;
+#pragma unroll 1
+        for (int i = 1; i < d.M.n; ++i) {
+            long long q, r;
+            const int s2 = d.M.shift[i];
+            if (s2 >= 0) { r = idx & (long long)(d.M.size[i] - 1); q = idx >> s2; }
+            else { q = idx / d.M.size[i]; r = idx - q * d.M.size[i]; }
+            a += r * d.M.s0[i]; c += r * d.M.s1[i];
+            idx = q;
+        }
+        rc.baseA = a; rc.baseC = c;
+    }
+    oA = rc.baseA + i0 * d.M.s0[0];
+    oC = rc.baseC + i0 * d.M.s1[0];
+}
+
+template <int KS, int MTW>
+__device__ __forceinline__ void absorb_load(AbsorbTile<KS, MTW>& t, const GettDesc& d, const cplx* __restrict__ A,
+                                            const long long* offAk, long long w, int lrow, int lcol, RowCache* rc) {
+    long long oA[MTW];
+#pragma unroll
+    for (int mt = 0; mt < MTW; ++mt) {
+        const long long row = w * (8 * MTW) + (mt << 3) + lrow;
+        t.ok[mt] = row < d.Msz;
+        oA[mt] = 0; t.oC[mt] = 0;
+        if (t.ok[mt]) row_offsets(d, rc[mt], row, oA[mt], t.oC[mt]);
+    }
+    // one 128-bit load per lane and k-quad: lane (lrow, lcol) fetches the complex element (row, k = 4 q + lcol).
+    // The real reduction index is ORDERED so that this is already the DMMA A fragment: k-step 2q takes the
+    // four real parts of the quad, k-step 2q+1 the four imaginary parts (B' rows are stored in the same order).
+#pragma unroll
+    for (int q = 0; q < KS / 2; ++q) {
+        const long long ofk = offAk[4 * q + lcol];
+#pragma unroll
+        for (int mt = 0; mt < MTW; ++mt) {
+            cplx v = make_double2(0.0, 0.0);
+            if (t.ok[mt] && ofk >= 0) v = __ldcs(A + oA[mt] + ofk);
+            t.a[mt][2 * q] = v.x;
+            t.a[mt][2 * q + 1] = v.y;
+        }
+    }
+}
+
+template <int KS, int MTW>
+__device__ __forceinline__ void absorb_compute(const AbsorbTile<KS, MTW>& t, const GettDesc& d, cplx* __restrict__ C,
+                                               const double* Bs, const long long* offCn, int NT, int lrow, int lcol) {
+    constexpr int STRIDE = 4 * KS + 4;
+    constexpr int NTU = 4 / MTW < 1 ? 1 : 4 / MTW;   // n-tiles in flight: >= 4 independent DMMA accumulator chains per warp
+    for (int nt0 = 0; nt0 < NT; nt0 += NTU) {   // NT is a multiple of NTU (Np is padded by the host)
+        double c[NTU][MTW][2];
+#pragma unroll
+        for (int u = 0; u < NTU; ++u)
+#pragma unroll
+            for (int mt = 0; mt < MTW; ++mt) { c[u][mt][0] = 0.0; c[u][mt][1] = 0.0; }
+        const double* brow = Bs + (8 * nt0 + lrow) * STRIDE + lcol;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+            double b[NTU];
+#pragma unroll
+            for (int u = 0; u < NTU; ++u) b[u] = brow[u * 8 * STRIDE + 4 * ks];
+#pragma unroll
+            for (int u = 0; u < NTU; ++u)
+#pragma unroll
+                for (int mt = 0; mt < MTW; ++mt) dmma884(c[u][mt][0], c[u][mt][1], t.a[mt][ks], b[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < NTU; ++u) {
+            const long long ofn = offCn[4 * (nt0 + u) + lcol];
+            if (ofn < 0) continue;
+#pragma unroll
+            for (int mt = 0; mt < MTW; ++mt) {
+                if (!t.ok[mt]) continue;
+                cplx* p = C + t.oC[mt] + ofn;
+                cplx v = make_double2(c[u][mt][0], c[u][mt][1]);
+                if (d.accumulate) { cplx o = *p; v.x += o.x; v.y += o.y; }
+                __stcs(p, v);
+            }
+        }
+    }
+}
+
+template <int KS, int MTW, int MINB, bool PREFETCH>
+__global__ void __launch_bounds__(256, MINB) gett_absorb(const __grid_constant__ GettDesc d, const cplx* __restrict__ A,
+                                                         const cplx* __restrict__ B, cplx* __restrict__ C, int Np) {
     constexpr int KP = 2 * KS;            // padded complex K
     constexpr int STRIDE = 4 * KS + 4;    // doubles per B' row (conflict-free fragment reads)
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -68,60 +174,206 @@ __global__ void __launch_bounds__(256, 2) gett_absorb(const __grid_constant__ Ge
             bi = d.alphaRe * v.y + d.alphaIm * v.x;
         }
         // (ar + i sA ai)(br + i bi): Re = ar br - sA ai bi ; Im = ar bi + sA ai br
-        double* r0 = Bs + (2 * n) * STRIDE + 2 * k;      // output column (n, re)
-        double* r1 = Bs + (2 * n + 1) * STRIDE + 2 * k;  // output column (n, im)
-        r0[0] = br; r0[1] = -sA * bi;
-        r1[0] = bi; r1[1] = sA * br;
+        const int jre = 8 * (k >> 2) + (k & 3), jim = jre + 4;   // real reduction index of (k, re) and (k, im)
+        double* r0 = Bs + (2 * n) * STRIDE;      // output column (n, re)
+        double* r1 = Bs + (2 * n + 1) * STRIDE;  // output column (n, im)
+        r0[jre] = br; r0[jim] = -sA * bi;
+        r1[jre] = bi; r1[jim] = sA * br;
     }
     __syncthreads();
 
     const int lane = tid & 31;
     const int lrow = lane >> 2, lcol = lane & 3;
     const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
-    const long long ntiles = (d.Msz + 15) >> 4;
+    const long long ntiles = (d.Msz + 8 * MTW - 1) / (8 * MTW);
     const int NT = Np >> 2;
-    for (long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (tid >> 5); w < ntiles; w += nwarps) {
-        long long oA[2], oC[2];
-        bool ok[2];
-        double a[2][KS];
-#pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
-            const long long row = (w << 4) + (mt << 3) + lrow;
-            ok[mt] = row < d.Msz;
-            oA[mt] = 0; oC[mt] = 0;
-            if (ok[mt]) decomp2(d.M, row, oA[mt], oC[mt]);
+    // blocked distribution: warp g owns the consecutive tiles [g * per, (g + 1) * per)
+    const long long g = (long long)blockIdx.x * (blockDim.x >> 5) + (tid >> 5);
+    const long long per = (ntiles + nwarps - 1) / nwarps;
+    long long w = g * per;
+    const long long wend = min(ntiles, w + per);
+    if (w >= wend) return;
+    RowCache rc[MTW];
+    AbsorbTile<KS, MTW> t0;
+    if (!PREFETCH) {
+        for (; w < wend; ++w) {
+            absorb_load(t0, d, A, offAk, w, lrow, lcol, rc);
+            absorb_compute(t0, d, C, Bs, offCn, NT, lrow, lcol);
         }
+        return;
+    }
+    AbsorbTile<KS, MTW> t1;
+    absorb_load(t0, d, A, offAk, w, lrow, lcol, rc);
+    while (true) {
+        if (w + 1 < wend) absorb_load(t1, d, A, offAk, w + 1, lrow, lcol, rc);
+        absorb_compute(t0, d, C, Bs, offCn, NT, lrow, lcol);
+        if (w + 1 >= wend) break;
+        w += 2;
+        if (w < wend) absorb_load(t0, d, A, offAk, w, lrow, lcol, rc);
+        absorb_compute(t1, d, C, Bs, offCn, NT, lrow, lcol);
+        if (w >= wend) break;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// absorb, TMA-staged: the same math, but the A tiles travel HBM -> shared memory as bulk async copies
+// (cp.async.bulk, completion on an mbarrier) issued by a producer warp into a STAGES-deep ring, so the
+// HBM latency is covered by the ring instead of by registers of DMMA-heavy warps.  Applies when a tile of
+// R consecutive rows is made of long contiguous runs in A:
+//   kf > 1 : A's fastest leg is a K leg of size kf and the fastest M leg follows it (forward sweep step):
+//            one run of R * kf elements per remaining K index ("plane");
+//   kf = 1 : A's fastest leg is the fastest M leg (reverse step dA = dC * B^H): one run of R elements per k.
+// The shared-memory image keeps the runs as they are in memory; a lane's 128-bit fragment read
+// (row, k = 4 q + lcol) is conflict-free in both cases (32-byte pad per plane when kf = 1).
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+struct TmaGeom {
+    int tpc;            // tiles (stages) per CTA: a CTA walks one contiguous chunk of rows
+    int kf;             // elements of the contiguous K run inside a row (1: rows themselves are contiguous)
+    int nplanes;        // bulk copies per stage
+    int plane_stride;   // bytes between planes in shared memory
+    int Np;
+};
+
+constexpr int TMA_STAGES = 4;
+constexpr int TMA_CONSUMERS = 4;   // consumer warps; warp TMA_CONSUMERS is the producer
+
+template <int KS, int MTW>
+__global__ void __launch_bounds__(32 * (TMA_CONSUMERS + 1), 2)
+gett_absorb_tma(const __grid_constant__ GettDesc d, const cplx* __restrict__ A, const cplx* __restrict__ B,
+                cplx* __restrict__ C, const TmaGeom g) {
+    constexpr int KP = 2 * KS;
+    constexpr int STRIDE = 4 * KS + 4;
+    constexpr int R = 8 * MTW * TMA_CONSUMERS;   // rows per stage
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int Np = g.Np;
+    const int stage_bytes = g.nplanes * g.plane_stride;
+    unsigned char* stages = smem_raw;
+    double* Bs = reinterpret_cast<double*>(smem_raw + TMA_STAGES * stage_bytes);          // [2 Np][STRIDE]
+    long long* planeoff = reinterpret_cast<long long*>(Bs + 2 * Np * STRIDE);              // [nplanes] A offset of each plane
+    long long* offCn = planeoff + 32;                                                      // [Np]
+    int* koff = reinterpret_cast<int*>(offCn + Np);                                        // [KP] smem byte offset of (row 0, k); -1: padding
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(koff + KP + (KP & 1)); // full[STAGES], empty[STAGES]
+    const int tid = threadIdx.x;
+    const int nthr = blockDim.x;
+    for (int pl = tid; pl < g.nplanes; pl += nthr) {
+        long long a, b;
+        decomp2(d.K, (long long)pl * g.kf, a, b);
+        planeoff[pl] = a;
+    }
+    for (int k = tid; k < KP; k += nthr) koff[k] = k < d.Ksz ? (k / g.kf) * g.plane_stride + (k % g.kf) * 16 : -1;
+    for (int n = tid; n < Np; n += nthr) {
+        long long b = 0, c = -1;
+        if (n < d.Nsz) decomp2(d.N, n, b, c);
+        offCn[n] = c;
+    }
+    const double sA = d.conjA ? -1.0 : 1.0;
+    for (int e = tid; e < Np * KP; e += nthr) {
+        const int k = e % KP, n = e / KP;
+        double br = 0.0, bi = 0.0;
+        if (k < d.Ksz && n < d.Nsz) {
+            long long ak, bk, bn, cn;
+            decomp2(d.K, k, ak, bk);
+            decomp2(d.N, n, bn, cn);
+            cplx v = B[bk + bn];
+            if (d.conjB) v.y = -v.y;
+            br = d.alphaRe * v.x - d.alphaIm * v.y;
+            bi = d.alphaRe * v.y + d.alphaIm * v.x;
+        }
+        const int jre = 8 * (k >> 2) + (k & 3), jim = jre + 4;
+        double* r0 = Bs + (2 * n) * STRIDE;
+        double* r1 = Bs + (2 * n + 1) * STRIDE;
+        r0[jre] = br; r0[jim] = -sA * bi;
+        r1[jre] = bi; r1[jim] = sA * br;
+    }
+    if (tid == 0) {
+        for (int s = 0; s < TMA_STAGES; ++s) {
+            mbar_init(smem_u32(&bars[s]), 1);                          // full: the producer's expect_tx arrive
+            mbar_init(smem_u32(&bars[TMA_STAGES + s]), TMA_CONSUMERS);  // empty: one arrive per consumer warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const int warp = tid >> 5, lane = tid & 31;
+    // Persistent grid; CTA b walks the tiles b, b + G, b + 2G, ... so that at any time the whole chip works on
+    // one narrow window of rows per plane (tools/mem_pattern.cu: 5.8 TB/s for this plane pattern, against
+    // 5.0 TB/s when every CTA walks its own far-away contiguous range).
+    const long long ntiles = d.Msz / R;   // the host guarantees Msz % R == 0 (M leg 0 is a multiple of R)
+    const long long tbeg = blockIdx.x, tend = ntiles, tstep = gridDim.x;
+    if (warp == TMA_CONSUMERS) {
+        // ---------------- producer warp: lane p copies plane p of every tile ----------------
+        RowCache rc;
+        int stage = 0;
+        unsigned phase = 0;
+        const unsigned chunk = (unsigned)(R * g.kf * 16);
+        for (long long t = tbeg; t < tend; t += tstep) {
+            mbar_wait(smem_u32(&bars[TMA_STAGES + stage]), phase ^ 1);
+            long long oA, oC;
+            row_offsets(d, rc, t * R, oA, oC);
+            if (lane == 0) mbar_expect_tx(smem_u32(&bars[stage]), chunk * (unsigned)g.nplanes);
+            __syncwarp();
+            for (int pl = lane; pl < g.nplanes; pl += 32)
+                bulk_g2s(smem_u32(stages + stage * stage_bytes + pl * g.plane_stride), A + oA + planeoff[pl], chunk,
+                         smem_u32(&bars[stage]));
+            if (++stage == TMA_STAGES) { stage = 0; phase ^= 1; }
+        }
+        return;
+    }
+    // ---------------- consumer warps ----------------
+    const int lrow = lane >> 2, lcol = lane & 3;
+    const int NT = Np >> 2;
+    RowCache rc[MTW];
+    int stage = 0;
+    unsigned phase = 0;
+    for (long long t = tbeg; t < tend; t += tstep) {
+        AbsorbTile<KS, MTW> tl;
+        mbar_wait(smem_u32(&bars[stage]), phase);
+        const unsigned char* sbase = stages + stage * stage_bytes;
 #pragma unroll
-        for (int ks = 0; ks < KS; ++ks) {
-            const long long ofk = offAk[2 * ks + (lcol >> 1)];
+        for (int mt = 0; mt < MTW; ++mt) {
+            const int rl = (warp * MTW + mt) * 8 + lrow;   // row inside the stage
+            long long oA;
+            tl.ok[mt] = true;
+            row_offsets(d, rc[mt], t * R + rl, oA, tl.oC[mt]);
 #pragma unroll
-            for (int mt = 0; mt < 2; ++mt) {
-                double v = 0.0;
-                if (ok[mt] && ofk >= 0) v = reinterpret_cast<const double*>(A + oA[mt] + ofk)[lcol & 1];
-                a[mt][ks] = v;
+            for (int q = 0; q < KS / 2; ++q) {
+                const int ko = koff[4 * q + lcol];
+                cplx v = make_double2(0.0, 0.0);
+                if (ko >= 0) v = *reinterpret_cast<const cplx*>(sbase + ko + rl * g.kf * 16);
+                tl.a[mt][2 * q] = v.x;
+                tl.a[mt][2 * q + 1] = v.y;
             }
         }
-        for (int nt = 0; nt < NT; ++nt) {
-            double c[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
-            const double* brow = Bs + (8 * nt + lrow) * STRIDE + lcol;
-#pragma unroll
-            for (int ks = 0; ks < KS; ++ks) {
-                const double b = brow[4 * ks];
-                dmma884(c[0][0], c[0][1], a[0][ks], b);
-                dmma884(c[1][0], c[1][1], a[1][ks], b);
-            }
-            const long long ofn = offCn[4 * nt + lcol];
-            if (ofn >= 0) {
-#pragma unroll
-                for (int mt = 0; mt < 2; ++mt) {
-                    if (!ok[mt]) continue;
-                    cplx* p = C + oC[mt] + ofn;
-                    cplx v = make_double2(c[mt][0], c[mt][1]);
-                    if (d.accumulate) { cplx o = *p; v.x += o.x; v.y += o.y; }
-                    *p = v;
-                }
-            }
-        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&bars[TMA_STAGES + stage]));   // fragments are in registers: refill the slot
+        if (++stage == TMA_STAGES) { stage = 0; phase ^= 1; }
+        absorb_compute(tl, d, C, Bs, offCn, NT, lrow, lcol);
     }
 }
 
@@ -186,7 +438,9 @@ __global__ void __launch_bounds__(256, 2) gett_reduce(const __grid_constant__ Ge
             long long idx = outer;
 #pragma unroll 1
             for (int i = 1; i < d.K.n; ++i) {
-                long long q = idx / d.K.size[i], r = idx - q * d.K.size[i];
+                long long q, r;
+                if (d.K.shift[i] >= 0) { r = idx & (long long)(d.K.size[i] - 1); q = idx >> d.K.shift[i]; }
+                else { q = idx / d.K.size[i]; r = idx - q * d.K.size[i]; }
                 baseA += r * d.K.s0[i]; baseB += r * d.K.s1[i];
                 idx = q;
             }
@@ -239,20 +493,36 @@ void sort_legs_by(LegSet& L, int which) {  // insertion sort of the legs by stri
             long long a = which == 0 ? L.s0[j - 1] : L.s1[j - 1], b = which == 0 ? L.s0[j] : L.s1[j];
             if (a <= b) break;
             std::swap(L.size[j - 1], L.size[j]);
+            std::swap(L.shift[j - 1], L.shift[j]);
             std::swap(L.s0[j - 1], L.s0[j]);
             std::swap(L.s1[j - 1], L.s1[j]);
             std::swap(L.s2[j - 1], L.s2[j]);
         }
 }
 
-template <int KS>
+template <int KS, int MTW, int MINB, bool PREFETCH>
 int launch_absorb(tne_ctx* ctx, const ContractPlan& plan, const cplx* A, const cplx* B, cplx* C) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(gett_absorb<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        cudaFuncSetAttribute(gett_absorb<KS, MTW, MINB, PREFETCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
         attr_set = true;
     }
-    gett_absorb<KS><<<plan.gx, plan.threads, plan.smem, ctx->stream>>>(plan.d, A, B, C, plan.aux[1]);
+    unsigned gx = (unsigned)std::min<long long>((long long)plan.gx / 2 * MINB, ((plan.d.Msz + 8 * MTW - 1) / (8 * MTW) + 7) / 8);
+    gett_absorb<KS, MTW, MINB, PREFETCH><<<gx, plan.threads, plan.smem, ctx->stream>>>(plan.d, A, B, C, plan.aux[1]);
+    TNE_LAUNCH_CHECK(ctx);
+    return TNE_OK;
+}
+
+template <int KS, int MTW>
+int launch_absorb_tma(tne_ctx* ctx, const ContractPlan& plan, const cplx* A, const cplx* B, cplx* C) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(gett_absorb_tma<KS, MTW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
+        attr_set = true;
+    }
+    TmaGeom g;
+    g.kf = plan.aux[4]; g.nplanes = plan.aux[5]; g.plane_stride = plan.aux[6]; g.Np = plan.aux[1]; g.tpc = plan.aux[2];
+    gett_absorb_tma<KS, MTW><<<plan.gx, 32 * (TMA_CONSUMERS + 1), plan.smem, ctx->stream>>>(plan.d, A, B, C, g);
     TNE_LAUNCH_CHECK(ctx);
     return TNE_OK;
 }
@@ -272,18 +542,48 @@ int gett_fast_plan(tne_ctx* ctx, ContractPlan* plan) {
     if (d.Bsz != 1) return TNE_OK;
     // ---- absorb: big M, small K and N ----
     if (d.Msz >= 2048 && d.Ksz <= 32 && d.Nsz <= 64 && d.Ksz * d.Nsz >= 4) {
-        int ks = 1;
+        int ks = 2;   // k-steps come in pairs (a quad of complex k per 128-bit load)
         while (2 * ks < d.Ksz) ks <<= 1;
-        const int Np = (int)((d.Nsz + 3) / 4 * 4);
+        // n-tiles are processed NTU = 4 / MTW at a time: pad N so that the tile count is a multiple of NTU
+        // (zero columns of B', never stored) unless that would more than double the math
+        const int mtw_sel = (ctx->opt_variant & 15) ? 1 : (ks >= 16 ? 1 : (ks >= 4 ? 2 : 4));
+        const int ntu = 4 / mtw_sel;
+        int Np = (int)((d.Nsz + 3) / 4 * 4);
+        Np = (Np + 4 * ntu - 1) / (4 * ntu) * (4 * ntu);
         sort_legs_by(d.N, 1);  // B is staged in shared memory: order the N legs by the OUTPUT stride
         plan->kernel = KERNEL_ABSORB;
         plan->aux[0] = ks;
         plan->aux[1] = Np;
         plan->threads = 256;
+        // TMA-staged variant when a tile of R rows is made of long contiguous runs of A (see gett_absorb_tma)
+        if ((ctx->opt_variant & 15) == 0 && d.M.n >= 1) {
+            const int mtw = ks >= 16 ? 1 : (ks >= 8 ? 2 : 4);
+            const int R = 8 * mtw * TMA_CONSUMERS;
+            LegSet Ks = d.K;
+            sort_legs_by(Ks, 0);
+            int kf = 0;
+            if (d.M.s0[0] == 1) kf = 1;                                                  // rows contiguous
+            else if (Ks.n >= 1 && Ks.s0[0] == 1 && d.M.s0[0] == Ks.size[0]) kf = Ks.size[0];  // K run, then rows
+            if (kf > 0 && d.M.size[0] % R == 0 && d.Msz >= 4LL * R * ctx->sm_count) {
+                d.K = Ks;  // plane p <-> K index p * kf needs the contiguous leg first
+                const int nplanes = (int)(d.Ksz / kf);
+                const int plane_stride = R * kf * 16 + (kf == 1 ? 32 : 0);
+                const int Np2 = (Np + 15) / 16 * 16 >= Np ? ((mtw == 1) ? (Np + 15) / 16 * 16 : (mtw == 2 ? (Np + 7) / 8 * 8 : Np)) : Np;
+                size_t smem = (size_t)TMA_STAGES * nplanes * plane_stride + (size_t)(2 * Np2) * (4 * ks + 4) * sizeof(double) +
+                              (32 + Np2) * sizeof(long long) + (2 * ks + 2) * sizeof(int) + 2 * TMA_STAGES * sizeof(long long) + 128;
+                if (nplanes <= 32 && smem <= 100 * 1024) {
+                    plan->kernel = KERNEL_ABSORB_TMA;
+                    plan->aux[1] = Np2;
+                    plan->aux[4] = kf; plan->aux[5] = nplanes; plan->aux[6] = plane_stride; plan->aux[7] = mtw;
+                    plan->smem = smem;
+                    plan->aux[2] = 1;
+                    plan->gx = (unsigned)std::min<long long>((long long)ctx->sm_count * 2, d.Msz / R);
+                    return TNE_OK;
+                }
+            }
+        }
         plan->smem = (size_t)(2 * Np) * (4 * ks + 4) * sizeof(double) + (size_t)(2 * ks + Np) * sizeof(long long);
-        const long long ntiles = (d.Msz + 15) / 16;
-        const long long ctas = (ntiles + 7) / 8;
-        plan->gx = (unsigned)std::min<long long>(ctas, (long long)ctx->sm_count * 2);
+        plan->gx = (unsigned)ctx->sm_count * 2;   // resident CTAs at 2 per SM; the launcher scales with the variant's occupancy
         return TNE_OK;
     }
     // ---- reduce: small M x N, long K ----
@@ -314,13 +614,36 @@ int gett_fast_plan(tne_ctx* ctx, ContractPlan* plan) {
 }
 
 int gett_fast_run(tne_ctx* ctx, const ContractPlan& plan, const cplx* A, const cplx* B, cplx* C) {
-    if (plan.kernel == KERNEL_ABSORB) {
+    if (plan.kernel == KERNEL_ABSORB_TMA) {
         switch (plan.aux[0]) {
-            case 1: return launch_absorb<1>(ctx, plan, A, B, C);
-            case 2: return launch_absorb<2>(ctx, plan, A, B, C);
-            case 4: return launch_absorb<4>(ctx, plan, A, B, C);
-            case 8: return launch_absorb<8>(ctx, plan, A, B, C);
-            case 16: return launch_absorb<16>(ctx, plan, A, B, C);
+            case 2: return launch_absorb_tma<2, 4>(ctx, plan, A, B, C);
+            case 4: return launch_absorb_tma<4, 4>(ctx, plan, A, B, C);
+            case 8: return launch_absorb_tma<8, 2>(ctx, plan, A, B, C);
+            case 16: return launch_absorb_tma<16, 1>(ctx, plan, A, B, C);
+        }
+        return tne_fail(ctx, TNE_ERR_UNSUPPORTED, "absorb (TMA) kernel: bad k-step count %d", plan.aux[0]);
+    }
+    if (plan.kernel == KERNEL_ABSORB) {
+        if ((ctx->opt_variant & 15) == 1) {
+            switch (plan.aux[0]) {
+                case 2: return launch_absorb<2, 1, 4, false>(ctx, plan, A, B, C);
+                case 4: return launch_absorb<4, 1, 4, false>(ctx, plan, A, B, C);
+                case 8: return launch_absorb<8, 1, 4, false>(ctx, plan, A, B, C);
+                case 16: return launch_absorb<16, 1, 4, false>(ctx, plan, A, B, C);
+            }
+        } else if ((ctx->opt_variant & 15) == 2) {
+            switch (plan.aux[0]) {
+                case 2: return launch_absorb<2, 1, 3, false>(ctx, plan, A, B, C);
+                case 4: return launch_absorb<4, 1, 3, false>(ctx, plan, A, B, C);
+                case 8: return launch_absorb<8, 1, 3, false>(ctx, plan, A, B, C);
+                case 16: return launch_absorb<16, 1, 3, false>(ctx, plan, A, B, C);
+            }
+        }
+        switch (plan.aux[0]) {
+            case 2: return launch_absorb<2, 4, 2, true>(ctx, plan, A, B, C);
+            case 4: return launch_absorb<4, 2, 2, true>(ctx, plan, A, B, C);
+            case 8: return launch_absorb<8, 2, 2, true>(ctx, plan, A, B, C);
+            case 16: return launch_absorb<16, 1, 2, true>(ctx, plan, A, B, C);
         }
         return tne_fail(ctx, TNE_ERR_UNSUPPORTED, "absorb kernel: bad k-step count %d", plan.aux[0]);
     }

@@ -7,7 +7,9 @@ __device__ __forceinline__ void decomp2(const LegSet& L, long long idx, long lon
 #pragma unroll 1
     for (int i = 0; i < L.n; ++i) {
         long long q, r;
-        if (idx < 0x7fffffffLL) { unsigned u = (unsigned)idx, s = (unsigned)L.size[i]; unsigned uq = u / s; q = uq; r = u - uq * s; }
+        const int sh = L.shift[i];
+        if (sh >= 0) { r = idx & (long long)(L.size[i] - 1); q = idx >> sh; }
+        else if (idx < 0x7fffffffLL) { unsigned u = (unsigned)idx, s = (unsigned)L.size[i]; unsigned uq = u / s; q = uq; r = u - uq * s; }
         else { q = idx / L.size[i]; r = idx - q * L.size[i]; }
         o0 += r * L.s0[i];
         o1 += r * L.s1[i];
@@ -18,7 +20,10 @@ __device__ __forceinline__ void decomp3(const LegSet& L, long long idx, long lon
     o0 = 0; o1 = 0; o2 = 0;
 #pragma unroll 1
     for (int i = 0; i < L.n; ++i) {
-        long long q = idx / L.size[i], r = idx - q * L.size[i];
+        long long q, r;
+        const int sh = L.shift[i];
+        if (sh >= 0) { r = idx & (long long)(L.size[i] - 1); q = idx >> sh; }
+        else { q = idx / L.size[i]; r = idx - q * L.size[i]; }
         o0 += r * L.s0[i]; o1 += r * L.s1[i]; o2 += r * L.s2[i];
         idx = q;
     }

@@ -50,6 +50,8 @@ struct tne_ctx {
     int64_t opt_force_generic = 0;
     int64_t opt_debug = 0;
     int64_t opt_profile = 0;
+    int64_t opt_pad = 0;                   // stride padding (elements) of workspace tensors, see tne_tree.cu
+    int64_t opt_variant = 0;               // kernel-variant switch for tuning experiments
     struct ProfRec { cudaEvent_t e0, e1; int cls; double flops, bytes; };
     std::vector<ProfRec> prof;              // pending event pairs
     std::vector<cudaEvent_t> event_pool;
@@ -98,6 +100,7 @@ struct TensorRef {                  // a tensor operand: labels in memory order 
 struct LegSet {
     int n;
     int size[MAXLEG];
+    int shift[MAXLEG];   // log2(size) for power-of-two legs (index arithmetic by shift/mask), else -1
     long long s0[MAXLEG];
     long long s1[MAXLEG];
     long long s2[MAXLEG];

@@ -452,11 +452,34 @@ struct Exec {
     std::set<int> ever_zeroed;   // checkpoints are cleared by the first phase that writes them only
     Exec(Program& p) : P(p), ctx(p.ctx) {}
 
+    // Layout of workspace tensors: column-major; with option "pad" > 0 a leg whose stride would reach
+    // 64 KiB gets that many extra elements of stride (an experiment against HBM channel aliasing of the
+    // huge power-of-two strides the sweep produces; measured to bring nothing on B200, so off by default).
+    // Returns the extent in elements.
+    int64_t padded_strides(const std::vector<int64_t>& dims, std::vector<int64_t>& st) const {
+        st.resize(dims.size());
+        const int64_t pad = ctx->opt_pad;
+        int64_t acc = 1;
+        for (size_t i = 0; i < dims.size(); ++i) {
+            if (pad > 0 && i > 0 && dims[i] > 1 && acc * (int64_t)sizeof(cplx) >= (64 << 10)) acc += pad;
+            st[i] = acc;
+            acc *= dims[i];
+        }
+        return acc;
+    }
+    int64_t extent_of(const Val& v) const {
+        std::vector<int64_t> st;
+        return padded_strides(v.dims, st);
+    }
     void full_strides(const Val& v, std::vector<int64_t>& st) const {
         if (!v.strides.empty()) { st = v.strides; return; }
-        st.resize(v.dims.size());
-        int64_t acc = 1;
-        for (size_t i = 0; i < v.dims.size(); ++i) { st[i] = acc; acc *= v.dims[i]; }
+        if (v.ext) {
+            st.resize(v.dims.size());
+            int64_t acc = 1;
+            for (size_t i = 0; i < v.dims.size(); ++i) { st[i] = acc; acc *= v.dims[i]; }
+            return;
+        }
+        padded_strides(v.dims, st);
     }
 
     // segment bookkeeping: op.seg from the node -> segment map; persistence of values
@@ -508,10 +531,7 @@ struct Exec {
             pv.strides.push_back(st[q]);
         }
         for (auto d : pv.dims) pv.nelem *= d;
-        if (pv.temp) {  // contiguous in its reduced shape
-            int64_t acc = 1;
-            for (size_t q = 0; q < pv.dims.size(); ++q) { pv.strides[q] = acc; acc *= pv.dims[q]; }
-        }
+        if (pv.temp) pv.nelem = padded_strides(pv.dims, pv.strides);  // dense (padded) in its reduced shape; nelem = extent
         ph.views.emplace(v, std::move(pv));
         return TNE_OK;
     }
@@ -655,7 +675,7 @@ struct Exec {
                 int v = kv.first;
                 if (!P.vals[v].persistent) continue;
                 auto it = slot.find(v);
-                if (it == slot.end()) { slot[v] = (int)iv.size(); iv.push_back({v, round512(P.vals[v].nelem * (int64_t)sizeof(cplx)), pi, pi, 0}); }
+                if (it == slot.end()) { slot[v] = (int)iv.size(); iv.push_back({v, round512(extent_of(P.vals[v]) * (int64_t)sizeof(cplx)), pi, pi, 0}); }
                 else iv[it->second].last = pi;
             }
         persist_bytes = plan_intervals(iv);
@@ -674,7 +694,7 @@ struct Exec {
 
     int run() {
         for (auto& ph : phases) {
-            for (int v : ph.zero_at_start) TNE_TRY(launch_fill_zero(ctx, base_ptr(ph, v), P.vals[v].nelem));
+            for (int v : ph.zero_at_start) TNE_TRY(launch_fill_zero(ctx, base_ptr(ph, v), extent_of(P.vals[v])));
             std::vector<int64_t> idx(ph.sliced.size(), 0);
             for (int64_t it = 0; it < ph.nsl; ++it) {
                 int64_t rem = it;

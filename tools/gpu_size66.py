@@ -8,6 +8,8 @@ from helpers import seed_for
 
 L = int(sys.argv[1]); D = int(sys.argv[2]); what = sys.argv[3:] or ["norm", "expect", "grad"]
 ctx = T.context(); ctx.set_option("debug", int(os.environ.get("TNE_DEBUG", "2")))
+if os.environ.get("TNE_VARIANT"): ctx.set_option("variant", int(os.environ["TNE_VARIANT"]))
+if os.environ.get("TNE_PAD"): ctx.set_option("pad", int(os.environ["TNE_PAD"]))
 g = T.grid([L, L])
 rng = np.random.default_rng(seed_for(L, D))
 t0 = time.time()
@@ -16,6 +18,11 @@ p = T.rand_simplepeps(g, D, rng, optimizer=order, segments=segs)
 h = T.rydberg_hamiltonian(g, 10.0, 0.2, 0.3)
 print("build", time.time() - t0, flush=True)
 def timed(name, f):
+    if os.environ.get("TNE_PROFILE") and "again" in name:
+        ctx.set_option("profile", 1); ctx.profile_collect(); f()
+        for k, v in ctx.profile_collect().items():
+            if v["launches"]: print("   ", k, v["launches"], "launches %.1f ms  %.2f TFLOP/s  %.2f TB/s" % (v["ms"], v["flops"] / v["ms"] / 1e9, v["bytes"] / v["ms"] / 1e9))
+        ctx.set_option("profile", 0)
     ctx.sync(); t0 = time.time(); r = f(); t1 = time.time(); ctx.sync(); t2 = time.time()
     st = ctx.program_stats()
     print(name, "%.3f s (host enqueue %.3f s)" % (t2 - t0, t1 - t0), "TFLOP/s %.2f" % ((st["flops"] + st["recompute_flops"]) / (t2 - t0) / 1e12), st, ctx.mem_info(), flush=True)
@@ -23,6 +30,11 @@ def timed(name, f):
 if "norm" in what:
     n = timed("norm", lambda: T.norm(p)); print(n.to_numpy())
     n = timed("norm again", lambda: T.norm(p))
+if "normgrad" in what:
+    TA = T.tensorad
+    gfun = lambda: TA.gradient(lambda x: T.norm(T.load_variables(p, x)), T.DiffTensor(T.variables(p)))[0]
+    gn = timed("norm gradient", gfun); print(np.abs(gn.to_numpy()).max())
+    gn = timed("norm gradient again", gfun)
 if "expect" in what:
     e = timed("expect", lambda: T.expect(h, p, p)); print(e.to_numpy())
 if "grad" in what:
