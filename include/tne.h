@@ -59,9 +59,9 @@ int tne_last_program_stats(tne_ctx* ctx, double* stats6);
 /* option knobs: "force_generic_kernel", "debug", "profile" (1: bracket every contraction launch with a
  * CUDA-event pair on the context's stream; read the totals with tne_profile_collect) */
 int tne_set_option(tne_ctx* ctx, const char* key, int64_t value);
-/* Per kernel class c (0 generic FMA, 1 DMMA absorb, 2 DMMA reduce, 3 DMMA absorb with TMA-staged operand): out[4c .. 4c+3] = launches, summed
+/* Per kernel class c (0 generic FMA, 1 DMMA absorb, 2 DMMA reduce, 3 DMMA absorb with TMA-staged operand, 4 DMMA reduce with TMA-staged operands): out[4c .. 4c+3] = launches, summed
  * device milliseconds, algorithmic real flops, algorithmic bytes since the last collect.  Synchronises. */
-#define TNE_PROFILE_CLASSES 4
+#define TNE_PROFILE_CLASSES 5
 int tne_profile_collect(tne_ctx* ctx, double* out);
 
 /* ---- device tensors: Array{ComplexF64,N} as used at src/peps.jl:41,132 ---------------- */

@@ -60,11 +60,11 @@ class Context:
 
     def profile_collect(self):
         """Per kernel class: launches, device ms, algorithmic flops and bytes since the last call."""
-        out = (C.c_double * 16)()
+        names = ["gett_generic", "gett_absorb", "gett_reduce", "gett_absorb_tma", "gett_reduce_tma"]
+        out = (C.c_double * (4 * len(names)))()
         self.check(self.L.tne_profile_collect(self.h, out))
-        names = ["gett_generic", "gett_absorb", "gett_reduce", "gett_absorb_tma"]
         return {names[c]: dict(launches=int(out[4 * c]), ms=out[4 * c + 1], flops=out[4 * c + 2], bytes=out[4 * c + 3])
-                for c in range(4)}
+                for c in range(len(names))}
 
     def mem_info(self):
         a, b, c = C.c_int64(), C.c_int64(), C.c_int64()

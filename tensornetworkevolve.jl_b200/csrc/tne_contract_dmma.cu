@@ -28,7 +28,7 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                  : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-enum { KERNEL_ABSORB = 1, KERNEL_REDUCE = 2, KERNEL_ABSORB_TMA = 3 };
+enum { KERNEL_ABSORB = 1, KERNEL_REDUCE = 2, KERNEL_ABSORB_TMA = 3, KERNEL_REDUCE_TMA = 4 };
 
 // ---------------------------------------------------------------------------------------
 // absorb
@@ -487,6 +487,152 @@ __global__ void __launch_bounds__(256, 2) gett_reduce(const __grid_constant__ Ge
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// reduce, TMA-staged: chunks of KC reduction indices of BOTH big operands are bulk-copied into a shared-memory
+// ring by a producer warp; four consumer warps split every chunk's k-steps and keep the whole M x N
+// accumulator tile in registers.  For each operand a chunk is a handful of long contiguous runs
+// ("planes"): either the reduction leg is the operand's fastest leg (one run of KC elements per free
+// index), or a free leg of size f is fastest and the reduction leg follows it (one run of KC * f elements
+// per remaining free index).
+// ---------------------------------------------------------------------------------------
+struct RedGeom {
+    int fA, fB;               // contiguous free-leg run (1: the reduction leg itself is fastest)
+    int npA, npB;             // planes per operand
+    int strideA, strideB;     // bytes between planes in shared memory
+    int offB;                 // byte offset of B's planes inside a stage
+    int stage_bytes;
+    long long nchunks;        // total chunks = (Ksz / size0) * (size0 / KC)
+    int chunks_per_row;       // size0 / KC
+};
+constexpr int RED_KC = 32;
+constexpr int RED_STAGES = 4;
+constexpr int RED_CONSUMERS = 4;
+
+template <int MT, int NT>
+__global__ void __launch_bounds__(32 * (RED_CONSUMERS + 1), 2)
+gett_reduce_tma(const __grid_constant__ GettDesc d, const cplx* __restrict__ A, const cplx* __restrict__ B,
+                cplx* __restrict__ C, const RedGeom g) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned char* stages = smem_raw;
+    long long* poffA = reinterpret_cast<long long*>(smem_raw + RED_STAGES * g.stage_bytes);   // [npA] global offset of plane
+    long long* poffB = poffA + 32;                                                            // [npB]
+    double* red = reinterpret_cast<double*>(poffB + 32);                                      // [MT*NT*2*32]
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(red + MT * NT * 2 * 32);
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    for (int p = tid; p < g.npA; p += nthr) { long long a, c; decomp2(d.M, (long long)p * g.fA, a, c); poffA[p] = a; }
+    for (int p = tid; p < g.npB; p += nthr) { long long b, c; decomp2(d.N, (long long)p * g.fB, b, c); poffB[p] = b; }
+    for (int e = tid; e < MT * NT * 2 * 32; e += nthr) red[e] = 0.0;
+    if (tid == 0) {
+        for (int s = 0; s < RED_STAGES; ++s) {
+            mbar_init(smem_u32(&bars[s]), 1);
+            mbar_init(smem_u32(&bars[RED_STAGES + s]), RED_CONSUMERS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int warp = tid >> 5, lane = tid & 31;
+    const long long sa0 = d.K.s0[0], sb0 = d.K.s1[0];
+    if (warp == RED_CONSUMERS) {
+        int stage = 0;
+        unsigned phase = 0;
+        const unsigned bytesA = (unsigned)(RED_KC * g.fA * 16), bytesB = (unsigned)(RED_KC * g.fB * 16);
+        for (long long u = blockIdx.x; u < g.nchunks; u += gridDim.x) {
+            const long long outer = u / g.chunks_per_row;
+            const long long k0 = (u - outer * g.chunks_per_row) * RED_KC;
+            long long baseA = k0 * sa0, baseB = k0 * sb0, idx = outer;
+#pragma unroll 1
+            for (int i = 1; i < d.K.n; ++i) {
+                long long q, r;
+                if (d.K.shift[i] >= 0) { r = idx & (long long)(d.K.size[i] - 1); q = idx >> d.K.shift[i]; }
+                else { q = idx / d.K.size[i]; r = idx - q * d.K.size[i]; }
+                baseA += r * d.K.s0[i]; baseB += r * d.K.s1[i];
+                idx = q;
+            }
+            mbar_wait(smem_u32(&bars[RED_STAGES + stage]), phase ^ 1);
+            if (lane == 0) mbar_expect_tx(smem_u32(&bars[stage]), bytesA * (unsigned)g.npA + bytesB * (unsigned)g.npB);
+            __syncwarp();
+            unsigned char* sb = stages + stage * g.stage_bytes;
+            for (int p = lane; p < g.npA; p += 32)
+                bulk_g2s(smem_u32(sb + p * g.strideA), A + baseA + poffA[p], bytesA, smem_u32(&bars[stage]));
+            for (int p = lane; p < g.npB; p += 32)
+                bulk_g2s(smem_u32(sb + g.offB + p * g.strideB), B + baseB + poffB[p], bytesB, smem_u32(&bars[stage]));
+            if (++stage == RED_STAGES) { stage = 0; phase ^= 1; }
+        }
+        return;
+    }
+    const int lrow = lane >> 2, lcol = lane & 3;
+    const int part = lcol & 1, kin = lcol >> 1;
+    const int t = lrow & 1;
+    const double sx = d.conjA ? -1.0 : 1.0, sy = d.conjB ? -1.0 : 1.0;
+    const int ysel = (t == 0) ? part : 1 - part;
+    const double ysgn = (t == 0) ? (part == 0 ? 1.0 : -sx * sy) : (part == 0 ? sy : sx);
+    // byte offsets of this lane's fragment elements inside a stage, for k_local = 0
+    int aoff[MT], boff[NT];
+    bool okm[MT], okn[NT];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+        const int m = 8 * mt + lrow;
+        okm[mt] = m < d.Msz;
+        aoff[mt] = (m / g.fA) * g.strideA + (m % g.fA) * 16 + part * 8;
+    }
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+        const int n = 4 * nt + (lrow >> 1);
+        okn[nt] = n < d.Nsz;
+        boff[nt] = g.offB + (n / g.fB) * g.strideB + (n % g.fB) * 16 + ysel * 8;
+    }
+    double acc[MT][NT][2];
+#pragma unroll
+    for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < NT; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+    int stage = 0;
+    unsigned phase = 0;
+    for (long long u = blockIdx.x; u < g.nchunks; u += gridDim.x) {
+        mbar_wait(smem_u32(&bars[stage]), phase);
+        const unsigned char* sb = stages + stage * g.stage_bytes;
+        constexpr int KSTEPS = RED_KC / 2 / RED_CONSUMERS;   // k-steps (2 complex k) per warp and chunk
+        double af[KSTEPS][MT], bf[KSTEPS][NT];
+#pragma unroll
+        for (int j = 0; j < KSTEPS; ++j) {
+            const int kl = 2 * (warp + RED_CONSUMERS * j) + kin;
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) af[j][mt] = okm[mt] ? *reinterpret_cast<const double*>(sb + aoff[mt] + kl * g.fA * 16) : 0.0;
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) bf[j][nt] = okn[nt] ? ysgn * *reinterpret_cast<const double*>(sb + boff[nt] + kl * g.fB * 16) : 0.0;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&bars[RED_STAGES + stage]));
+        if (++stage == RED_STAGES) { stage = 0; phase ^= 1; }
+#pragma unroll
+        for (int j = 0; j < KSTEPS; ++j)
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], af[j][mt], bf[j][nt]);
+    }
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            atomicAdd(&red[((mt * NT + nt) * 2 + 0) * 32 + lane], acc[mt][nt][0]);
+            atomicAdd(&red[((mt * NT + nt) * 2 + 1) * 32 + lane], acc[mt][nt][1]);
+        }
+    asm volatile("bar.sync 1, %0;" ::"r"(32 * RED_CONSUMERS));   // consumers only (the producer warp has left)
+    for (int e = tid; e < MT * NT * 32; e += 32 * RED_CONSUMERS) {
+        const int tile = e >> 5, l = e & 31;
+        const double re = red[(tile * 2 + 0) * 32 + l], im = red[(tile * 2 + 1) * 32 + l];
+        const int mt = tile / NT, nt = tile - mt * NT;
+        const int m = 8 * mt + (l >> 2), n = 4 * nt + (l & 3);
+        if (m < d.Msz && n < d.Nsz) {
+            long long am, cm, bn, cn;
+            decomp2(d.M, m, am, cm);
+            decomp2(d.N, n, bn, cn);
+            atomic_add_c(C + cm + cn, d.alphaRe * re - d.alphaIm * im, d.alphaRe * im + d.alphaIm * re);
+        }
+    }
+}
+
 void sort_legs_by(LegSet& L, int which) {  // insertion sort of the legs by stride s0 / s1
     for (int i = 1; i < L.n; ++i)
         for (int j = i; j > 0; --j) {
@@ -523,6 +669,18 @@ int launch_absorb_tma(tne_ctx* ctx, const ContractPlan& plan, const cplx* A, con
     TmaGeom g;
     g.kf = plan.aux[4]; g.nplanes = plan.aux[5]; g.plane_stride = plan.aux[6]; g.Np = plan.aux[1]; g.tpc = plan.aux[2];
     gett_absorb_tma<KS, MTW><<<plan.gx, 32 * (TMA_CONSUMERS + 1), plan.smem, ctx->stream>>>(plan.d, A, B, C, g);
+    TNE_LAUNCH_CHECK(ctx);
+    return TNE_OK;
+}
+
+template <int MT, int NT>
+int launch_reduce_tma(tne_ctx* ctx, const ContractPlan& plan, const RedGeom& g, const cplx* A, const cplx* B, cplx* C) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(gett_reduce_tma<MT, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
+        attr_set = true;
+    }
+    gett_reduce_tma<MT, NT><<<plan.gx, 32 * (RED_CONSUMERS + 1), plan.smem, ctx->stream>>>(plan.d, A, B, C, g);
     TNE_LAUNCH_CHECK(ctx);
     return TNE_OK;
 }
@@ -592,6 +750,37 @@ int gett_fast_plan(tne_ctx* ctx, ContractPlan* plan) {
         int NT = d.Nsz <= 4 ? 1 : (d.Nsz <= 8 ? 2 : 4);
         sort_legs_by(d.K, 0);  // iterate along A's fastest reduction leg
         const int size0 = d.K.size[0];
+        if ((ctx->opt_variant & 15) == 0 && d.M.n >= 1 && d.N.n >= 1) {
+            // TMA-staged variant: both operands must be made of long contiguous runs along K leg 0
+            LegSet Ms = d.M, Ns = d.N;
+            sort_legs_by(Ms, 0);
+            sort_legs_by(Ns, 0);
+            int fA = 0, fB = 0;
+            if (d.K.s0[0] == 1) fA = 1; else if (Ms.s0[0] == 1 && d.K.s0[0] == Ms.size[0]) fA = Ms.size[0];
+            if (d.K.s1[0] == 1) fB = 1; else if (Ns.s0[0] == 1 && d.K.s1[0] == Ns.size[0]) fB = Ns.size[0];
+            if (fA > 0 && fB > 0 && size0 % RED_KC == 0 && d.Msz % fA == 0 && d.Nsz % fB == 0 && d.Msz / fA <= 32 && d.Nsz / fB <= 32) {
+                d.M = Ms; d.N = Ns;   // free index m = m0 + fA * plane needs the contiguous leg first
+                RedGeom g;
+                g.fA = fA; g.fB = fB; g.npA = (int)(d.Msz / fA); g.npB = (int)(d.Nsz / fB);
+                g.strideA = RED_KC * fA * 16 + 32; g.strideB = RED_KC * fB * 16 + 32;
+                g.offB = g.npA * g.strideA;
+                g.stage_bytes = (g.offB + g.npB * g.strideB + 127) / 128 * 128;
+                g.chunks_per_row = size0 / RED_KC;
+                g.nchunks = (d.Ksz / size0) * g.chunks_per_row;
+                size_t smem = (size_t)RED_STAGES * g.stage_bytes + 64 * sizeof(long long) + (size_t)MT * NT * 64 * sizeof(double) + 2 * RED_STAGES * sizeof(long long) + 128;
+                if (smem <= 110 * 1024) {
+                    plan->kernel = KERNEL_REDUCE_TMA;
+                    plan->aux[0] = MT * 16 + NT;
+                    static_assert(sizeof(RedGeom) <= sizeof(plan->blob), "RedGeom must fit the plan blob");
+                    memcpy(plan->blob, &g, sizeof(g));
+                    plan->smem = smem;
+                    plan->threads = 32 * (RED_CONSUMERS + 1);
+                    plan->gx = (unsigned)std::max<long long>(1, std::min<long long>(g.nchunks, (long long)ctx->sm_count * 2));
+                    plan->zero_first = !d.accumulate;
+                    return TNE_OK;
+                }
+            }
+        }
         const long long outer = d.Ksz / size0;
         const long long warps = (long long)ctx->sm_count * 2 * 8;
         // chunk of the fastest leg per work unit: ~3 units per warp, at least 64 k's, even
@@ -646,6 +835,23 @@ int gett_fast_run(tne_ctx* ctx, const ContractPlan& plan, const cplx* A, const c
             case 16: return launch_absorb<16, 1, 2, true>(ctx, plan, A, B, C);
         }
         return tne_fail(ctx, TNE_ERR_UNSUPPORTED, "absorb kernel: bad k-step count %d", plan.aux[0]);
+    }
+    if (plan.kernel == KERNEL_REDUCE_TMA) {
+        if (plan.zero_first) TNE_TRY(launch_fill_zero(ctx, C, plan.c_nelem));
+        RedGeom g;
+        memcpy(&g, plan.blob, sizeof(g));
+        switch (plan.aux[0]) {
+            case 1 * 16 + 1: return launch_reduce_tma<1, 1>(ctx, plan, g, A, B, C);
+            case 1 * 16 + 2: return launch_reduce_tma<1, 2>(ctx, plan, g, A, B, C);
+            case 1 * 16 + 4: return launch_reduce_tma<1, 4>(ctx, plan, g, A, B, C);
+            case 2 * 16 + 1: return launch_reduce_tma<2, 1>(ctx, plan, g, A, B, C);
+            case 2 * 16 + 2: return launch_reduce_tma<2, 2>(ctx, plan, g, A, B, C);
+            case 2 * 16 + 4: return launch_reduce_tma<2, 4>(ctx, plan, g, A, B, C);
+            case 4 * 16 + 1: return launch_reduce_tma<4, 1>(ctx, plan, g, A, B, C);
+            case 4 * 16 + 2: return launch_reduce_tma<4, 2>(ctx, plan, g, A, B, C);
+            case 4 * 16 + 4: return launch_reduce_tma<4, 4>(ctx, plan, g, A, B, C);
+        }
+        return tne_fail(ctx, TNE_ERR_UNSUPPORTED, "reduce (TMA) kernel: bad tile shape %d", plan.aux[0]);
     }
     if (plan.kernel == KERNEL_REDUCE) {
         if (plan.zero_first) TNE_TRY(launch_fill_zero(ctx, C, plan.c_nelem));

@@ -131,6 +131,7 @@ struct ContractPlan {
     int64_t c_nelem = 0;
     bool empty = false;
     int aux[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    unsigned char blob[64] = {0};   // kernel-specific geometry (tne_contract_dmma.cu)
     double flops = 0, bytes = 0;
 };
 int contract_plan(tne_ctx* ctx, const TensorRef& A, const TensorRef& B, const TensorRef& C, bool accumulate,
