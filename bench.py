@@ -188,6 +188,8 @@ def run_gpu(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ctx = T.context()
+    if os.environ.get("TNE_VARIANT"):
+        ctx.set_option("absorb_tma", int(os.environ["TNE_VARIANT"]))
     if world > 1:
         T.array.init_comm(ctx, dist, rank, world)
     L, D = args.L, args.D

@@ -57,7 +57,8 @@ int64_t tne_launch_count(tne_ctx* ctx);
  * top of [0]), [5] number of values */
 int tne_last_program_stats(tne_ctx* ctx, double* stats6);
 /* option knobs: "force_generic_kernel", "debug", "profile" (1: bracket every contraction launch with a
- * CUDA-event pair on the context's stream; read the totals with tne_profile_collect) */
+ * CUDA-event pair on the context's stream; read the totals with tne_profile_collect), "absorb_tma" (1: use the
+ * TMA-staged absorb kernel where it applies), "no_reduce_tma" (1: register-fed reduce kernel), "pad" */
 int tne_set_option(tne_ctx* ctx, const char* key, int64_t value);
 /* Per kernel class c (0 generic FMA, 1 DMMA absorb, 2 DMMA reduce, 3 DMMA absorb with TMA-staged operand, 4 DMMA reduce with TMA-staged operands): out[4c .. 4c+3] = launches, summed
  * device milliseconds, algorithmic real flops, algorithmic bytes since the last collect.  Synchronises. */

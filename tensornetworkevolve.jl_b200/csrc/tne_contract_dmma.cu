@@ -140,12 +140,12 @@ __device__ __forceinline__ void absorb_compute(const AbsorbTile<KS, MTW>& t, con
     }
 }
 
-template <int KS, int MTW, int MINB, bool PREFETCH>
+template <int KS, int MTW, int MINB>
 __global__ void __launch_bounds__(256, MINB) gett_absorb(const __grid_constant__ GettDesc d, const cplx* __restrict__ A,
                                                          const cplx* __restrict__ B, cplx* __restrict__ C, int Np) {
     constexpr int KP = 2 * KS;            // padded complex K
     constexpr int STRIDE = 4 * KS + 4;    // doubles per B' row (conflict-free fragment reads)
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     double* Bs = reinterpret_cast<double*>(smem_raw);                       // [2 Np][STRIDE]
     long long* offAk = reinterpret_cast<long long*>(Bs + 2 * Np * STRIDE);   // [KP]
     long long* offCn = offAk + KP;                                          // [Np]
@@ -187,31 +187,22 @@ __global__ void __launch_bounds__(256, MINB) gett_absorb(const __grid_constant__
     const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
     const long long ntiles = (d.Msz + 8 * MTW - 1) / (8 * MTW);
     const int NT = Np >> 2;
-    // blocked distribution: warp g owns the consecutive tiles [g * per, (g + 1) * per)
     const long long g = (long long)blockIdx.x * (blockDim.x >> 5) + (tid >> 5);
-    const long long per = (ntiles + nwarps - 1) / nwarps;
-    long long w = g * per;
-    const long long wend = min(ntiles, w + per);
-    if (w >= wend) return;
     RowCache rc[MTW];
     AbsorbTile<KS, MTW> t0;
-    if (!PREFETCH) {
-        for (; w < wend; ++w) {
-            absorb_load(t0, d, A, offAk, w, lrow, lcol, rc);
-            absorb_compute(t0, d, C, Bs, offCn, NT, lrow, lcol);
+    {
+        // chunk-interleaved distribution: warp g takes the chunks g, g + nwarps, ... of CH consecutive tiles, so the
+        // whole chip sweeps one narrow window of rows (HBM locality, tools/mem_pattern.cu) while the cached row
+        // decomposition still holds inside a chunk
+        constexpr int CH = 4;
+        const long long nchunks = (ntiles + CH - 1) / CH;
+        for (long long c = g; c < nchunks; c += nwarps) {
+            const long long wlast = min(ntiles, (c + 1) * CH);
+            for (long long w = c * CH; w < wlast; ++w) {
+                absorb_load(t0, d, A, offAk, w, lrow, lcol, rc);
+                absorb_compute(t0, d, C, Bs, offCn, NT, lrow, lcol);
+            }
         }
-        return;
-    }
-    AbsorbTile<KS, MTW> t1;
-    absorb_load(t0, d, A, offAk, w, lrow, lcol, rc);
-    while (true) {
-        if (w + 1 < wend) absorb_load(t1, d, A, offAk, w + 1, lrow, lcol, rc);
-        absorb_compute(t0, d, C, Bs, offCn, NT, lrow, lcol);
-        if (w + 1 >= wend) break;
-        w += 2;
-        if (w < wend) absorb_load(t0, d, A, offAk, w, lrow, lcol, rc);
-        absorb_compute(t1, d, C, Bs, offCn, NT, lrow, lcol);
-        if (w >= wend) break;
     }
 }
 
@@ -646,15 +637,15 @@ void sort_legs_by(LegSet& L, int which) {  // insertion sort of the legs by stri
         }
 }
 
-template <int KS, int MTW, int MINB, bool PREFETCH>
+template <int KS, int MTW, int MINB>
 int launch_absorb(tne_ctx* ctx, const ContractPlan& plan, const cplx* A, const cplx* B, cplx* C) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(gett_absorb<KS, MTW, MINB, PREFETCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        cudaFuncSetAttribute(gett_absorb<KS, MTW, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
         attr_set = true;
     }
     unsigned gx = (unsigned)std::min<long long>((long long)plan.gx / 2 * MINB, ((plan.d.Msz + 8 * MTW - 1) / (8 * MTW) + 7) / 8);
-    gett_absorb<KS, MTW, MINB, PREFETCH><<<gx, plan.threads, plan.smem, ctx->stream>>>(plan.d, A, B, C, plan.aux[1]);
+    gett_absorb<KS, MTW, MINB><<<gx, plan.threads, plan.smem, ctx->stream>>>(plan.d, A, B, C, plan.aux[1]);
     TNE_LAUNCH_CHECK(ctx);
     return TNE_OK;
 }
@@ -704,8 +695,7 @@ int gett_fast_plan(tne_ctx* ctx, ContractPlan* plan) {
         while (2 * ks < d.Ksz) ks <<= 1;
         // n-tiles are processed NTU = 4 / MTW at a time: pad N so that the tile count is a multiple of NTU
         // (zero columns of B', never stored) unless that would more than double the math
-        const int mtw_sel = (ctx->opt_variant & 15) ? 1 : (ks >= 16 ? 1 : (ks >= 4 ? 2 : 4));
-        const int ntu = 4 / mtw_sel;
+        const int ntu = 4;   // MTW = 1
         int Np = (int)((d.Nsz + 3) / 4 * 4);
         Np = (Np + 4 * ntu - 1) / (4 * ntu) * (4 * ntu);
         sort_legs_by(d.N, 1);  // B is staged in shared memory: order the N legs by the OUTPUT stride
@@ -714,7 +704,7 @@ int gett_fast_plan(tne_ctx* ctx, ContractPlan* plan) {
         plan->aux[1] = Np;
         plan->threads = 256;
         // TMA-staged variant when a tile of R rows is made of long contiguous runs of A (see gett_absorb_tma)
-        if ((ctx->opt_variant & 15) == 0 && d.M.n >= 1) {
+        if (ctx->opt_absorb_tma && d.M.n >= 1) {
             const int mtw = ks >= 16 ? 1 : (ks >= 8 ? 2 : 4);
             const int R = 8 * mtw * TMA_CONSUMERS;
             LegSet Ks = d.K;
@@ -726,7 +716,7 @@ int gett_fast_plan(tne_ctx* ctx, ContractPlan* plan) {
                 d.K = Ks;  // plane p <-> K index p * kf needs the contiguous leg first
                 const int nplanes = (int)(d.Ksz / kf);
                 const int plane_stride = R * kf * 16 + (kf == 1 ? 32 : 0);
-                const int Np2 = (Np + 15) / 16 * 16 >= Np ? ((mtw == 1) ? (Np + 15) / 16 * 16 : (mtw == 2 ? (Np + 7) / 8 * 8 : Np)) : Np;
+                const int Np2 = Np;   // already a multiple of 16 columns (4 n-tiles)
                 size_t smem = (size_t)TMA_STAGES * nplanes * plane_stride + (size_t)(2 * Np2) * (4 * ks + 4) * sizeof(double) +
                               (32 + Np2) * sizeof(long long) + (2 * ks + 2) * sizeof(int) + 2 * TMA_STAGES * sizeof(long long) + 128;
                 if (nplanes <= 32 && smem <= 100 * 1024) {
@@ -750,7 +740,7 @@ int gett_fast_plan(tne_ctx* ctx, ContractPlan* plan) {
         int NT = d.Nsz <= 4 ? 1 : (d.Nsz <= 8 ? 2 : 4);
         sort_legs_by(d.K, 0);  // iterate along A's fastest reduction leg
         const int size0 = d.K.size[0];
-        if ((ctx->opt_variant & 15) == 0 && d.M.n >= 1 && d.N.n >= 1) {
+        if (!ctx->opt_no_reduce_tma && d.M.n >= 1 && d.N.n >= 1) {
             // TMA-staged variant: both operands must be made of long contiguous runs along K leg 0
             LegSet Ms = d.M, Ns = d.N;
             sort_legs_by(Ms, 0);
@@ -813,26 +803,11 @@ int gett_fast_run(tne_ctx* ctx, const ContractPlan& plan, const cplx* A, const c
         return tne_fail(ctx, TNE_ERR_UNSUPPORTED, "absorb (TMA) kernel: bad k-step count %d", plan.aux[0]);
     }
     if (plan.kernel == KERNEL_ABSORB) {
-        if ((ctx->opt_variant & 15) == 1) {
-            switch (plan.aux[0]) {
-                case 2: return launch_absorb<2, 1, 4, false>(ctx, plan, A, B, C);
-                case 4: return launch_absorb<4, 1, 4, false>(ctx, plan, A, B, C);
-                case 8: return launch_absorb<8, 1, 4, false>(ctx, plan, A, B, C);
-                case 16: return launch_absorb<16, 1, 4, false>(ctx, plan, A, B, C);
-            }
-        } else if ((ctx->opt_variant & 15) == 2) {
-            switch (plan.aux[0]) {
-                case 2: return launch_absorb<2, 1, 3, false>(ctx, plan, A, B, C);
-                case 4: return launch_absorb<4, 1, 3, false>(ctx, plan, A, B, C);
-                case 8: return launch_absorb<8, 1, 3, false>(ctx, plan, A, B, C);
-                case 16: return launch_absorb<16, 1, 3, false>(ctx, plan, A, B, C);
-            }
-        }
-        switch (plan.aux[0]) {
-            case 2: return launch_absorb<2, 4, 2, true>(ctx, plan, A, B, C);
-            case 4: return launch_absorb<4, 2, 2, true>(ctx, plan, A, B, C);
-            case 8: return launch_absorb<8, 2, 2, true>(ctx, plan, A, B, C);
-            case 16: return launch_absorb<16, 1, 2, true>(ctx, plan, A, B, C);
+        switch (plan.aux[0]) {   // 3 CTAs of 8 warps per SM, one 8-row m-tile per warp iteration
+            case 2: return launch_absorb<2, 1, 3>(ctx, plan, A, B, C);
+            case 4: return launch_absorb<4, 1, 3>(ctx, plan, A, B, C);
+            case 8: return launch_absorb<8, 1, 3>(ctx, plan, A, B, C);
+            case 16: return launch_absorb<16, 1, 3>(ctx, plan, A, B, C);
         }
         return tne_fail(ctx, TNE_ERR_UNSUPPORTED, "absorb kernel: bad k-step count %d", plan.aux[0]);
     }

@@ -51,7 +51,8 @@ struct tne_ctx {
     int64_t opt_debug = 0;
     int64_t opt_profile = 0;
     int64_t opt_pad = 0;                   // stride padding (elements) of workspace tensors, see tne_tree.cu
-    int64_t opt_variant = 0;               // kernel-variant switch for tuning experiments
+    int64_t opt_absorb_tma = 0;            // 1: TMA-staged absorb kernel where applicable (default: register-fed)
+    int64_t opt_no_reduce_tma = 0;         // 1: register-fed reduce kernel instead of the TMA-staged one
     struct ProfRec { cudaEvent_t e0, e1; int cls; double flops, bytes; };
     std::vector<ProfRec> prof;              // pending event pairs
     std::vector<cudaEvent_t> event_pool;
