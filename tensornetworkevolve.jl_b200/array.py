@@ -308,3 +308,16 @@ def init_comm(ctx, dist, rank, world):
 def allreduce_sum(ctx, arrays):
     """In-place sum over the ranks (``tne_allreduce_sum``: NCCL over NVLink)."""
     ctx.check(ctx.L.tne_allreduce_sum(ctx.h, len(arrays), _i64([a.handle for a in arrays])))
+
+
+def svd_trunc(a, Dmax, eps=0.0):
+    """``U, S, V = svd(A)`` truncated like src/peps.jl:381-390 (``A ~= U * Diagonal(S) * V'``); returns
+    ``(U, S, V, kept, truncation_error)``.  Sizes of a bond update (even m, even n <= 16)."""
+    ctx = a.ctx
+    hu, hs, hv = C.c_int64(), C.c_int64(), C.c_int64()
+    kept, err = C.c_int32(), C.c_double()
+    ctx.check(ctx.L.tne_svd_trunc(ctx.h, a.handle, int(Dmax), float(eps), C.byref(hu), C.byref(hs), C.byref(hv),
+                                  C.byref(kept), C.byref(err)))
+    k = kept.value
+    return (B200Array(hu.value, (a.shape[0], k), False, ctx), B200Array(hs.value, (k,), True, ctx),
+            B200Array(hv.value, (a.shape[1], k), False, ctx), k, err.value)

@@ -1,9 +1,531 @@
-// Bond update (K5): placeholder until the Jacobi SVD kernel lands.
+// Bond update (K5 of SURVEY.md 2c): the device side of apply_onbond! (src/peps.jl:353-417) and of
+// LinearAlgebra.svd + truncation (src/peps.jl:381-390).
+//
+// One CTA per bond job, many independent jobs per launch (a TEBD wavefront).  The reference forms the
+// (up to 128 x 128) two-site matrix and calls LAPACK zgesdd; here the two site tensors are first
+// orthogonalised against their outer legs (CGS2 QR of the O x (2 Ds) matricisation), so that the SVD runs on
+// the small core  theta[(a,p'),(b,q')] = sum_{p,q,s} G[p'q',pq] R_i[a,(p,s)] R_j[b,(q,s)]  (at most 4Ds x 4Ds,
+// 16 x 16 for D = 4) with a one-sided (Hestenes) Jacobi iteration in shared memory -- same singular values,
+// U = Q_i u, conj(V) = Q_j conj(v).  Everything is complex128 FMA arithmetic; the matrices are far too small
+// for the tensor pipe to matter and the step is latency-bound.
+#include <algorithm>
+#include <cmath>
+
 #include "tne_internal.h"
 
-extern "C" int tne_svd_trunc(tne_ctx* ctx, tne_buf, int, double, tne_buf*, tne_buf*, tne_buf*, int32_t*, double*) {
-    return tne_fail(ctx, TNE_ERR_UNSUPPORTED, "tne_svd_trunc: not built yet");
+namespace {
+
+constexpr int BOND_THREADS = 256;
+constexpr int MAXI = 32;          // 2 * Ds: columns of a site matricisation (shared bond Ds <= 16)
+constexpr int MAXN = 2 * MAXI;    // rows / columns of the core theta
+
+struct BondDev {
+    const cplx* t[2];             // site tensors i, j
+    int rank[2];
+    int dims[2][TNE_MAX_RANK];
+    int axis[2];                  // position of the shared bond
+    const cplx* lambda[2][TNE_MAX_RANK];   // Vidal bond vectors per axis (null: none)
+    double gate[32];              // 4 x 4 complex, column-major, M[o_i + 2 o_j, i_i + 2 i_j]
+    int Dmax;
+    double eps;
+    int vidal;
+    // scratch / outputs
+    cplx* Q[2];                   // O x I (column-major): the matricisation, orthonormalised in place
+    cplx* UV[2];                  // (2 O) x Dcap column-major: reshape(U, (sl..., D)) and reshape(conj(V), (sr..., D))
+    cplx* S;                      // Dcap singular values (imaginary part 0)
+    int Dcap;
+    int* kept;
+    double* trunc_err;
+};
+
+__device__ __forceinline__ cplx cmulc(cplx a, cplx b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ cplx cmulconj(cplx a, cplx b) {  // conj(a) * b
+    return make_double2(a.x * b.x + a.y * b.y, a.x * b.y - a.y * b.x);
 }
-extern "C" int tne_apply_onbond_batched(tne_ctx* ctx, int, tne_bond_job*) {
-    return tne_fail(ctx, TNE_ERR_UNSUPPORTED, "tne_apply_onbond_batched: not built yet");
+__device__ __forceinline__ cplx csqrt_pos(cplx z) {  // principal square root
+    if (z.y == 0.0) return z.x >= 0 ? make_double2(sqrt(z.x), 0.0) : make_double2(0.0, sqrt(-z.x));
+    double r = hypot(z.x, z.y);
+    double a = sqrt(0.5 * (r + fabs(z.x)));
+    double b = 0.5 * z.y / a;
+    return z.x >= 0 ? make_double2(a, b) : make_double2(fabs(b), copysign(a, z.y));
+}
+__device__ __forceinline__ cplx cinv(cplx z) {
+    double dd = z.x * z.x + z.y * z.y;
+    return make_double2(z.x / dd, -z.y / dd);
+}
+__device__ __forceinline__ cplx safe_inv_dev(cplx y) {  // src/peps.jl:419-426
+    const double eps = 1e-10;
+    if (hypot(y.x, y.y) < eps) y = make_double2(y.x >= 0 ? eps : -eps, 0.0);
+    return cinv(y);
+}
+
+// block-wide sum of a complex value (all threads get the result)
+__device__ cplx block_sum(cplx v, double* red) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int o = 16; o > 0; o >>= 1) {
+        v.x += __shfl_xor_sync(0xffffffffu, v.x, o);
+        v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
+    }
+    __syncthreads();
+    if (lane == 0) { red[2 * warp] = v.x; red[2 * warp + 1] = v.y; }
+    __syncthreads();
+    cplx r = make_double2(0.0, 0.0);
+    for (int w = 0; w < BOND_THREADS / 32; ++w) { r.x += red[2 * w]; r.y += red[2 * w + 1]; }
+    return r;
+}
+
+// outer index o (the virtual legs other than the shared one, in tensor order) and (p, s) -> linear tensor index
+struct SiteMap {
+    int rank, ax, Ds, O;
+    int dim[TNE_MAX_RANK];
+    long long stride[TNE_MAX_RANK];
+    __device__ void init(const int* dims, int rank_, int ax_) {
+        rank = rank_; ax = ax_;
+        long long s = 1;
+        O = 1;
+        for (int q = 0; q < rank; ++q) { dim[q] = dims[q]; stride[q] = s; s *= dims[q]; if (q != 0 && q != ax) O *= dims[q]; }
+        Ds = dims[ax];
+    }
+    __device__ long long outer_offset(int o, int* leg_index /* may be null */) const {
+        long long off = 0;
+        for (int q = 1; q < rank; ++q) {
+            if (q == ax) continue;
+            int r = o % dim[q];
+            o /= dim[q];
+            off += r * stride[q];
+            if (leg_index) leg_index[q] = r;
+        }
+        return off;
+    }
+};
+
+__global__ void __launch_bounds__(BOND_THREADS) bond_kernel(const BondDev* __restrict__ jobs) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const BondDev& J = jobs[blockIdx.x];
+    const int tid = threadIdx.x;
+    cplx* R[2];
+    R[0] = reinterpret_cast<cplx*>(smem);                 // [MAXI][MAXI] column-major (I x I)
+    R[1] = R[0] + MAXI * MAXI;
+    cplx* W = R[1] + MAXI * MAXI;                         // theta, then W = theta * V : [ni][nj] column-major
+    cplx* V = W + MAXN * MAXN;                            // [nj][nj]
+    double* red = reinterpret_cast<double*>(V + MAXN * MAXN);   // 64 doubles
+    double* sval = red + 64;                              // [MAXN]
+    int* perm = reinterpret_cast<int*>(sval + MAXN);      // [MAXN]
+    cplx* coef = reinterpret_cast<cplx*>(perm + MAXN);    // [MAXI]
+    __shared__ SiteMap map[2];
+    __shared__ int s_flag;
+    if (tid < 2) map[tid].init(J.dims[tid], J.rank[tid], J.axis[tid]);
+    __syncthreads();
+
+    // ---- 1. matricise (Vidal: absorb sqrt(lambda) on every virtual leg) and orthogonalise: T = Q R ----
+    for (int side = 0; side < 2; ++side) {
+        const SiteMap& M = map[side];
+        const int O = M.O, Ds = M.Ds, I = 2 * Ds;
+        cplx* Q = J.Q[side];
+        for (int e = tid; e < O * I; e += BOND_THREADS) {
+            const int o = e % O, c = e / O;       // column c = p + 2 s
+            const int p = c & 1, s = c >> 1;
+            int li[TNE_MAX_RANK];
+            long long off = M.outer_offset(o, li) + p * M.stride[0] + (long long)s * M.stride[M.ax];
+            cplx v = J.t[side][off];
+            if (J.vidal) {
+                li[M.ax] = s;
+                for (int q = 1; q < M.rank; ++q)
+                    if (J.lambda[side][q]) v = cmulc(v, csqrt_pos(J.lambda[side][q][li[q]]));
+            }
+            Q[(long long)c * O + o] = v;
+        }
+        for (int e = tid; e < MAXI * MAXI; e += BOND_THREADS) R[side][e] = make_double2(0.0, 0.0);
+        __syncthreads();
+        // classical Gram-Schmidt with one re-orthogonalisation pass ("twice is enough")
+        for (int c = 0; c < I; ++c) {
+            cplx* vc = Q + (long long)c * O;
+            double nrm0 = 0.0;
+            {
+                cplx a = make_double2(0.0, 0.0);
+                for (int o = tid; o < O; o += BOND_THREADS) { cplx x = vc[o]; a.x += x.x * x.x + x.y * x.y; }
+                nrm0 = sqrt(block_sum(a, red).x);
+            }
+            for (int pass = 0; pass < 2; ++pass) {
+                // coef[k] = <q_k, v> for k < c: warp w takes k = w, w + 8, ...
+                const int lane = tid & 31, warp = tid >> 5;
+                for (int k = warp; k < c; k += BOND_THREADS / 32) {
+                    const cplx* qk = Q + (long long)k * O;
+                    cplx a = make_double2(0.0, 0.0);
+                    for (int o = lane; o < O; o += 32) { cplx t = cmulconj(qk[o], vc[o]); a.x += t.x; a.y += t.y; }
+                    for (int sh = 16; sh > 0; sh >>= 1) { a.x += __shfl_xor_sync(0xffffffffu, a.x, sh); a.y += __shfl_xor_sync(0xffffffffu, a.y, sh); }
+                    if (lane == 0) coef[k] = a;
+                }
+                __syncthreads();
+                for (int o = tid; o < O; o += BOND_THREADS) {
+                    cplx x = vc[o];
+                    for (int k = 0; k < c; ++k) { cplx t = cmulc(coef[k], Q[(long long)k * O + o]); x.x -= t.x; x.y -= t.y; }
+                    vc[o] = x;
+                }
+                if (tid < c) { cplx r = R[side][c * MAXI + tid]; r.x += coef[tid].x; r.y += coef[tid].y; R[side][c * MAXI + tid] = r; }
+                __syncthreads();
+            }
+            cplx a = make_double2(0.0, 0.0);
+            for (int o = tid; o < O; o += BOND_THREADS) { cplx x = vc[o]; a.x += x.x * x.x + x.y * x.y; }
+            const double nrm = sqrt(block_sum(a, red).x);
+            // a column that is (numerically) in the span of the previous ones contributes nothing
+            const bool dead = !(nrm > 1e-13 * nrm0) || nrm0 == 0.0;
+            const double inv = dead ? 0.0 : 1.0 / nrm;
+            for (int o = tid; o < O; o += BOND_THREADS) { cplx x = vc[o]; vc[o] = make_double2(x.x * inv, x.y * inv); }
+            if (tid == 0) R[side][c * MAXI + c] = make_double2(dead ? 0.0 : nrm, 0.0);
+            __syncthreads();
+        }
+    }
+
+    // ---- 2. the core: theta[(a,p'),(b,q')] = sum_{p,q,s} G[p'+2q', p+2q] R_i[a,(p,s)] R_j[b,(q,s)] ----
+    const int Ds = map[0].Ds;
+    const int Ii = 2 * Ds, Ij = 2 * Ds;
+    const int ni = 2 * Ii, nj = 2 * Ij;      // row index a + Ii * p' ... stored as (p' + 2 a) to follow (phys, outer) order
+    for (int e = tid; e < ni * nj; e += BOND_THREADS) {
+        const int row = e % ni, col = e / ni;
+        const int pp = row & 1, a = row >> 1, qq = col & 1, b = col >> 1;
+        cplx acc = make_double2(0.0, 0.0);
+        for (int s = 0; s < Ds; ++s)
+            for (int p = 0; p < 2; ++p) {
+                const cplx ri = R[0][(p + 2 * s) * MAXI + a];
+                if (ri.x == 0.0 && ri.y == 0.0) continue;
+                for (int q = 0; q < 2; ++q) {
+                    const int gi = (pp + 2 * qq) + 4 * (p + 2 * q);
+                    const cplx g = make_double2(J.gate[2 * gi], J.gate[2 * gi + 1]);
+                    cplx t = cmulc(cmulc(g, ri), R[1][(q + 2 * s) * MAXI + b]);
+                    acc.x += t.x; acc.y += t.y;
+                }
+            }
+        W[col * MAXN + row] = acc;
+    }
+    for (int e = tid; e < nj * nj; e += BOND_THREADS) {
+        const int r = e % nj, c = e / nj;
+        V[c * MAXN + r] = make_double2(r == c ? 1.0 : 0.0, 0.0);
+    }
+    __syncthreads();
+
+    // ---- 3. one-sided Jacobi: rotate column pairs of W (and V) until all pairs are orthogonal ----
+    {
+        const int lane = tid & 31, warp = tid >> 5, nwarp = BOND_THREADS / 32;
+        const int npad = nj + (nj & 1);
+        for (int sweep = 0; sweep < 40; ++sweep) {
+            if (tid == 0) s_flag = 0;
+            __syncthreads();
+            for (int step = 0; step < npad - 1; ++step) {
+                // round-robin tournament: npad / 2 disjoint pairs per step
+                for (int pr = warp; pr < npad / 2; pr += nwarp) {
+                    int x = pr == 0 ? npad - 1 : (step + pr) % (npad - 1);
+                    int y = (step + npad - 1 - pr) % (npad - 1);
+                    if (pr == 0) y = step % (npad - 1);
+                    int p = min(x, y), q = max(x, y);
+                    if (q >= nj || p == q) continue;
+                    cplx* wp = W + p * MAXN;
+                    cplx* wq = W + q * MAXN;
+                    double al = 0.0, be = 0.0;
+                    cplx ga = make_double2(0.0, 0.0);
+                    for (int r = lane; r < ni; r += 32) {
+                        cplx u = wp[r], v = wq[r];
+                        al += u.x * u.x + u.y * u.y;
+                        be += v.x * v.x + v.y * v.y;
+                        cplx t = cmulconj(u, v);
+                        ga.x += t.x; ga.y += t.y;
+                    }
+                    for (int sh = 16; sh > 0; sh >>= 1) {
+                        al += __shfl_xor_sync(0xffffffffu, al, sh);
+                        be += __shfl_xor_sync(0xffffffffu, be, sh);
+                        ga.x += __shfl_xor_sync(0xffffffffu, ga.x, sh);
+                        ga.y += __shfl_xor_sync(0xffffffffu, ga.y, sh);
+                    }
+                    const double g = hypot(ga.x, ga.y);
+                    if (g <= 1e-15 * sqrt(al * be) || g == 0.0) continue;
+                    if (lane == 0) s_flag = 1;
+                    // unitary rotation [c, s e^{i phi}; -s e^{-i phi}, c] that zeroes <w_p', w_q'>
+                    const double zeta = (be - al) / (2.0 * g);
+                    const double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                    const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+                    const cplx ph = make_double2(ga.x / g, ga.y / g);   // e^{i phi}, gamma = <w_p, w_q>
+                    for (int r = lane; r < ni; r += 32) {
+                        cplx u = wp[r], v = wq[r];
+                        cplx vph = cmulconj(ph, v);            // e^{-i phi} v
+                        cplx uph = cmulc(ph, u);               // e^{ i phi} u
+                        wp[r] = make_double2(c * u.x - s * vph.x, c * u.y - s * vph.y);
+                        wq[r] = make_double2(s * uph.x + c * v.x, s * uph.y + c * v.y);
+                    }
+                    cplx* vp = V + p * MAXN;
+                    cplx* vq = V + q * MAXN;
+                    for (int r = lane; r < nj; r += 32) {
+                        cplx u = vp[r], v = vq[r];
+                        cplx vph = cmulconj(ph, v);
+                        cplx uph = cmulc(ph, u);
+                        vp[r] = make_double2(c * u.x - s * vph.x, c * u.y - s * vph.y);
+                        vq[r] = make_double2(s * uph.x + c * v.x, s * uph.y + c * v.y);
+                    }
+                }
+                __syncthreads();
+            }
+            if (s_flag == 0) break;
+            __syncthreads();
+        }
+    }
+
+    // ---- 4. singular values, descending order, truncation (src/peps.jl:383-390) ----
+    for (int c = tid; c < nj; c += BOND_THREADS) {
+        double a = 0.0;
+        for (int r = 0; r < ni; ++r) { cplx u = W[c * MAXN + r]; a += u.x * u.x + u.y * u.y; }
+        sval[c] = sqrt(a);
+    }
+    __syncthreads();
+    for (int c = tid; c < nj; c += BOND_THREADS) {
+        int rank = 0;
+        for (int k = 0; k < nj; ++k) if (sval[k] > sval[c] || (sval[k] == sval[c] && k < c)) ++rank;
+        perm[rank] = c;
+    }
+    __syncthreads();
+    const int mi = 2 * map[0].O, mj = 2 * map[1].O;
+    const int full = min(mi, mj);             // size(U, 2) of the reference's thin SVD
+    const int ncomp = min(nj, full);          // singular values beyond this are exactly zero
+    if (tid == 0) {
+        int D0 = -1;
+        for (int k = 0; k < ncomp; ++k) if (sval[perm[k]] < J.eps) { D0 = k; break; }
+        if (D0 < 0 && full > ncomp && 0.0 < J.eps) D0 = ncomp;
+        int D = D0 < 0 ? min(J.Dmax, full) : min(D0, J.Dmax);
+        D = min(D, ncomp);
+        double err = 0.0;
+        for (int k = D; k < ncomp; ++k) err += sval[perm[k]];
+        *J.kept = D;
+        *J.trunc_err = D < full ? err : -1.0;   // -1: nothing was cut (the reference logs only when D < size(U,2))
+        s_flag = D;
+    }
+    __syncthreads();
+    const int D = s_flag;
+
+    // ---- 5. U = Q_i u, conj(V) = Q_j conj(v); Simple: sqrt(S) into both; Vidal: divide the outer legs ----
+    for (int side = 0; side < 2; ++side) {
+        const SiteMap& M = map[side];
+        const int O = M.O, I = 2 * M.Ds;
+        const cplx* Q = J.Q[side];
+        cplx* out = J.UV[side];
+        const int rows = 2 * O;
+        for (int e = tid; e < rows * D; e += BOND_THREADS) {
+            const int row = e % rows, dd = e / rows;
+            const int pp = row & 1, o = row >> 1;
+            const int col = perm[dd];
+            const double s = sval[col];
+            cplx acc = make_double2(0.0, 0.0);
+            if (side == 0) {
+                for (int a = 0; a < I; ++a) { cplx t = cmulc(Q[(long long)a * O + o], W[col * MAXN + pp + 2 * a]); acc.x += t.x; acc.y += t.y; }
+                const double inv = s > 0.0 ? 1.0 / s : 0.0;   // u = W / s
+                acc.x *= inv; acc.y *= inv;
+            } else {
+                for (int b = 0; b < I; ++b) {
+                    cplx v = V[col * MAXN + pp + 2 * b];
+                    v.y = -v.y;
+                    cplx t = cmulc(Q[(long long)b * O + o], v);
+                    acc.x += t.x; acc.y += t.y;
+                }
+            }
+            if (J.vidal) {
+                int li[TNE_MAX_RANK];
+                M.outer_offset(o, li);
+                for (int q = 1; q < M.rank; ++q)
+                    if (q != M.ax && J.lambda[side][q]) acc = cmulc(acc, safe_inv_dev(csqrt_pos(J.lambda[side][q][li[q]])));
+            } else {
+                const double sq = sqrt(s);
+                acc.x *= sq; acc.y *= sq;
+            }
+            out[(long long)dd * rows + row] = acc;
+        }
+    }
+    for (int dd = tid; dd < D; dd += BOND_THREADS) J.S[dd] = make_double2(sval[perm[dd]], 0.0);
+}
+
+size_t bond_smem_bytes() {
+    return (size_t)(2 * MAXI * MAXI + 2 * MAXN * MAXN + MAXI) * sizeof(cplx) + (64 + MAXN) * sizeof(double) + MAXN * sizeof(int) + 64;
+}
+
+struct HostJob {
+    tne_buf q[2] = {0, 0}, uv[2] = {0, 0}, s = 0;
+    int O[2] = {1, 1};
+    std::vector<int64_t> dims[2];
+    int axis[2] = {0, 0};
+};
+
+}  // namespace
+
+static int bond_run(tne_ctx* ctx, int n_jobs, const tne_bond_job* in, std::vector<HostJob>& hj, std::vector<int>& kept,
+                    std::vector<double>& err, int svd_only, const tne_buf* svd_A) {
+    (void)svd_only; (void)svd_A;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(bond_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bond_smem_bytes());
+        attr_set = true;
+    }
+    std::vector<BondDev> dev(n_jobs);
+    hj.resize(n_jobs);
+    tne_buf hmeta;
+    TNE_TRY(buf_new(ctx, {(int64_t)(2 * n_jobs + 1)}, &hmeta));   // kept (as int in .x slot) and error per job
+    char* meta = reinterpret_cast<char*>(buf_get(ctx, hmeta)->ptr());
+    for (int k = 0; k < n_jobs; ++k) {
+        const tne_bond_job& jb = in[k];
+        BondDev& d = dev[k];
+        memset(&d, 0, sizeof(d));
+        const tne_buf tb[2] = {jb.ti, jb.tj};
+        const int ax[2] = {jb.axis_i, jb.axis_j};
+        for (int side = 0; side < 2; ++side) {
+            Buf* b = buf_get(ctx, tb[side]);
+            if (!b) return TNE_ERR_INVALID;
+            const int rk = (int)b->dims.size();
+            if (rk < 2 || ax[side] < 1 || ax[side] >= rk) return tne_fail(ctx, TNE_ERR_INVALID, "bond job %d: bad shared axis", k);
+            if (b->dims[0] != 2) return tne_fail(ctx, TNE_ERR_UNSUPPORTED, "bond job %d: the physical leg must come first and have dimension 2", k);
+            d.t[side] = b->ptr();
+            d.rank[side] = rk;
+            d.axis[side] = ax[side];
+            int O = 1;
+            for (int q = 0; q < rk; ++q) { d.dims[side][q] = (int)b->dims[q]; if (q != 0 && q != ax[side]) O *= (int)b->dims[q]; }
+            hj[k].O[side] = O;
+            hj[k].dims[side] = b->dims;
+            hj[k].axis[side] = ax[side];
+            if (jb.vidal) {
+                const tne_buf* lam = side == 0 ? jb.lambda_i : jb.lambda_j;
+                for (int q = 1; q < rk; ++q) {
+                    if (!lam[q]) return tne_fail(ctx, TNE_ERR_INVALID, "bond job %d: missing bond vector for axis %d", k, q);
+                    Buf* lb = buf_get(ctx, lam[q]);
+                    if (!lb || lb->nelem != b->dims[q]) return tne_fail(ctx, TNE_ERR_INVALID, "bond job %d: bond vector of axis %d has the wrong length", k, q);
+                    d.lambda[side][q] = lb->ptr();
+                }
+            }
+        }
+        const int Ds = d.dims[0][ax[0]];
+        if (Ds != d.dims[1][ax[1]]) return tne_fail(ctx, TNE_ERR_INVALID, "bond job %d: shared bond sizes differ", k);
+        if (2 * Ds > MAXI) return tne_fail(ctx, TNE_ERR_UNSUPPORTED, "bond job %d: bond dimension %d > %d", k, Ds, MAXI / 2);
+        memcpy(d.gate, jb.gate, sizeof(d.gate));
+        d.Dmax = jb.Dmax; d.eps = jb.eps; d.vidal = jb.vidal;
+        d.Dcap = std::min(4 * Ds, std::min(2 * hj[k].O[0], 2 * hj[k].O[1]));
+        d.Dcap = std::max(1, std::min(d.Dcap, std::max(1, (int)jb.Dmax)));
+        for (int side = 0; side < 2; ++side) {
+            TNE_TRY(buf_new(ctx, {(int64_t)hj[k].O[side] * 2 * Ds}, &hj[k].q[side]));
+            TNE_TRY(buf_new(ctx, {(int64_t)2 * hj[k].O[side] * d.Dcap}, &hj[k].uv[side]));
+            d.Q[side] = buf_get(ctx, hj[k].q[side])->ptr();
+            d.UV[side] = buf_get(ctx, hj[k].uv[side])->ptr();
+        }
+        TNE_TRY(buf_new(ctx, {(int64_t)d.Dcap}, &hj[k].s));
+        d.S = buf_get(ctx, hj[k].s)->ptr();
+        d.kept = reinterpret_cast<int*>(meta + 16 * (2 * k));
+        d.trunc_err = reinterpret_cast<double*>(meta + 16 * (2 * k + 1));
+    }
+    tne_buf hdev;
+    const int64_t dev_elems = ((int64_t)n_jobs * (int64_t)sizeof(BondDev) + 15) / 16;
+    TNE_TRY(buf_new(ctx, {dev_elems}, &hdev));
+    TNE_CUDA(ctx, cudaMemcpyAsync(buf_get(ctx, hdev)->ptr(), dev.data(), (size_t)n_jobs * sizeof(BondDev), cudaMemcpyHostToDevice, ctx->stream));
+    bond_kernel<<<n_jobs, BOND_THREADS, bond_smem_bytes(), ctx->stream>>>(reinterpret_cast<const BondDev*>(buf_get(ctx, hdev)->ptr()));
+    TNE_LAUNCH_CHECK(ctx);
+    std::vector<char> hmeta_host((size_t)32 * n_jobs);
+    TNE_CUDA(ctx, cudaMemcpyAsync(hmeta_host.data(), meta, hmeta_host.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    TNE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // also guarantees `dev` was consumed
+    kept.resize(n_jobs); err.resize(n_jobs);
+    for (int k = 0; k < n_jobs; ++k) {
+        kept[k] = *reinterpret_cast<int*>(hmeta_host.data() + 32 * k);
+        err[k] = *reinterpret_cast<double*>(hmeta_host.data() + 32 * k + 16);
+    }
+    tne_free(ctx, hdev);
+    tne_free(ctx, hmeta);
+    return TNE_OK;
+}
+
+// reshape(U, (sl..., D)) -> the site tensor in its own leg order (src/peps.jl:392-393)
+static int bond_place(tne_ctx* ctx, tne_buf uv, const std::vector<int64_t>& dims, int axis, int D, tne_buf* out) {
+    const int rk = (int)dims.size();
+    TensorRef A, one, C;
+    A.ptr = buf_get(ctx, uv)->ptr();
+    std::vector<int64_t> odims = dims;
+    odims[axis] = D;
+    for (int q = 0; q < rk; ++q) if (q != axis) { A.labels.push_back(q); A.dims.push_back(dims[q]); }
+    A.labels.push_back(axis); A.dims.push_back(D);
+    for (int q = 0; q < rk; ++q) { C.labels.push_back(q); C.dims.push_back(odims[q]); }
+    one.ptr = ctx->one_dev;
+    TNE_TRY(buf_new(ctx, odims, out));
+    C.ptr = buf_get(ctx, *out)->ptr();
+    return contract_launch(ctx, A, one, C, false);
+}
+
+extern "C" int tne_apply_onbond_batched(tne_ctx* ctx, int n_jobs, tne_bond_job* jobs) {
+    if (n_jobs <= 0) return TNE_OK;
+    if (!jobs) return tne_fail(ctx, TNE_ERR_INVALID, "null jobs");
+    std::vector<HostJob> hj;
+    std::vector<int> kept;
+    std::vector<double> err;
+    TNE_TRY(bond_run(ctx, n_jobs, jobs, hj, kept, err, 0, nullptr));
+    for (int k = 0; k < n_jobs; ++k) {
+        const int D = kept[k];
+        TNE_TRY(bond_place(ctx, hj[k].uv[0], hj[k].dims[0], hj[k].axis[0], D, &jobs[k].ti_out));
+        TNE_TRY(bond_place(ctx, hj[k].uv[1], hj[k].dims[1], hj[k].axis[1], D, &jobs[k].tj_out));
+        TNE_TRY(buf_new(ctx, {(int64_t)D}, &jobs[k].s_out));
+        if (D > 0)
+            TNE_CUDA(ctx, cudaMemcpyAsync(buf_get(ctx, jobs[k].s_out)->ptr(), buf_get(ctx, hj[k].s)->ptr(), (size_t)D * sizeof(cplx),
+                                          cudaMemcpyDeviceToDevice, ctx->stream));
+        jobs[k].kept = D;
+        jobs[k].trunc_err = err[k];
+        for (int side = 0; side < 2; ++side) { tne_free(ctx, hj[k].q[side]); tne_free(ctx, hj[k].uv[side]); }
+        tne_free(ctx, hj[k].s);
+    }
+    return TNE_OK;
+}
+
+// LinearAlgebra.svd(A) + truncation for a matrix: the same kernel on the trivial "bond" whose sites are
+// t_i[p, r, s] = A[(p, r), s] restricted ... (general matrices go through the two-site form with an identity gate)
+extern "C" int tne_svd_trunc(tne_ctx* ctx, tne_buf hA, int Dmax, double eps, tne_buf* U, tne_buf* S, tne_buf* V, int32_t* kept,
+                             double* trunc_err) {
+    Buf* a = buf_get(ctx, hA);
+    if (!a) return TNE_ERR_INVALID;
+    if (a->dims.size() != 2) return tne_fail(ctx, TNE_ERR_INVALID, "svd: a matrix is required");
+    const int64_t m = a->dims[0], n = a->dims[1];
+    if (m % 2 || n % 2 || n > MAXI / 2)
+        return tne_fail(ctx, TNE_ERR_UNSUPPORTED, "svd: supported for even m and even n <= %d (bond-update sizes)", MAXI / 2);
+    // A = T_i * T_j^T with T_i = A (rows (p, o), shared s = column) and T_j = identity on (q, s):
+    // site i: dims (2, m/2, n) with shared axis 2;  site j: dims (2, n/2, n) with T_j[(q, o'), s] = delta
+    std::vector<cplx> eye((size_t)n * n, make_double2(0.0, 0.0));
+    for (int64_t i = 0; i < n; ++i) eye[(size_t)(i * n + i)] = make_double2(1.0, 0.0);
+    tne_buf hI, hAi;
+    TNE_TRY(buf_new(ctx, {2, n / 2, n}, &hI));
+    TNE_CUDA(ctx, cudaMemcpyAsync(buf_get(ctx, hI)->ptr(), eye.data(), eye.size() * sizeof(cplx), cudaMemcpyHostToDevice, ctx->stream));
+    TNE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    Buf src = *a;
+    TNE_TRY(buf_view(ctx, src, 0, {2, m / 2, n}, &hAi));
+    tne_bond_job jb;
+    memset(&jb, 0, sizeof(jb));
+    jb.ti = hAi; jb.tj = hI; jb.axis_i = 2; jb.axis_j = 2;
+    for (int g = 0; g < 4; ++g) jb.gate[2 * (g + 4 * g)] = 1.0;   // identity gate
+    jb.Dmax = Dmax; jb.eps = eps; jb.vidal = 1;                    // "vidal" form returns bare U and conj(V)
+    // unit bond vectors so that the Vidal scalings are no-ops
+    std::vector<cplx> ones((size_t)std::max(m, n), make_double2(1.0, 0.0));
+    tne_buf h1;
+    TNE_TRY(buf_new(ctx, {(int64_t)ones.size()}, &h1));
+    TNE_CUDA(ctx, cudaMemcpyAsync(buf_get(ctx, h1)->ptr(), ones.data(), ones.size() * sizeof(cplx), cudaMemcpyHostToDevice, ctx->stream));
+    TNE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    tne_buf l_mi, l_ni, l_n;
+    Buf one_src = *buf_get(ctx, h1);
+    TNE_TRY(buf_view(ctx, one_src, 0, {m / 2}, &l_mi));
+    TNE_TRY(buf_view(ctx, one_src, 0, {n / 2}, &l_ni));
+    TNE_TRY(buf_view(ctx, one_src, 0, {n}, &l_n));
+    jb.lambda_i[1] = l_mi; jb.lambda_i[2] = l_n;
+    jb.lambda_j[1] = l_ni; jb.lambda_j[2] = l_n;
+    int rc = tne_apply_onbond_batched(ctx, 1, &jb);
+    tne_free(ctx, hI); tne_free(ctx, hAi); tne_free(ctx, h1); tne_free(ctx, l_mi); tne_free(ctx, l_ni); tne_free(ctx, l_n);
+    if (rc) return rc;
+    // ti_out: (2, m/2, D) = U as (m x D); tj_out: (2, n/2, D) = conj(V); return V itself
+    const int D = jb.kept;
+    Buf ub = *buf_get(ctx, jb.ti_out);
+    TNE_TRY(buf_view(ctx, ub, 0, {m, (int64_t)D}, U));
+    tne_free(ctx, jb.ti_out);
+    tne_buf vc;
+    Buf vb = *buf_get(ctx, jb.tj_out);
+    TNE_TRY(buf_view(ctx, vb, 0, {n, (int64_t)D}, &vc));
+    tne_free(ctx, jb.tj_out);
+    rc = tne_map(ctx, TNE_CONJ, vc, 0.0, 0.0, V);
+    tne_free(ctx, vc);
+    if (rc) return rc;
+    *S = jb.s_out;
+    if (kept) *kept = D;
+    if (trunc_err) *trunc_err = jb.trunc_err;
+    return TNE_OK;
 }

@@ -404,25 +404,34 @@ def bond_job(peps, i, j, mat):
 
 
 def apply_onbond_(peps, i, j, mat):  # src/peps.jl:353-417
-    if getphysicallabel(peps, i) != getvlabel(peps, i)[0] or getphysicallabel(peps, j) != getvlabel(peps, j)[0]:
-        raise ValueError("the device bond update expects the physical leg first (src/peps.jl:253)")
-    job, shared = bond_job(peps, i, j, mat)
-    ctx = _dev(peps.vertex_tensors[i - 1]).ctx
-    jobs = (_lib.TneBondJob * 1)(job)
-    ctx.check(ctx.L.tne_apply_onbond_batched(ctx.h, 1, jobs))
-    job = jobs[0]
-    si = list(_dev(peps.vertex_tensors[i - 1]).shape)
-    sj = list(_dev(peps.vertex_tensors[j - 1]).shape)
-    full = min(int(np.prod(si)) // si[job.axis_i], int(np.prod(sj)) // sj[job.axis_j])
-    si[job.axis_i] = job.kept
-    sj[job.axis_j] = job.kept
-    if job.kept < full:
-        LOG.append("truncation error is %r" % job.trunc_err)
-    peps.vertex_tensors[i - 1] = B200Array(job.ti_out, si, False, ctx)
-    peps.vertex_tensors[j - 1] = B200Array(job.tj_out, sj, False, ctx)
-    s = B200Array(job.s_out, (job.kept,), True, ctx)
-    if peps.kind == "vidal":
-        peps.bond_tensors[peps.virtual_labels.index(shared)] = s
+    return apply_onbond_batch_(peps, [(i, j, mat)])
+
+
+def apply_onbond_batch_(peps, gates):
+    """``apply_onbond!`` for a list of ``(i, j, mat)`` on pairwise disjoint sites in ONE device launch (one CTA
+    per bond: contract -> gate -> QR-reduced one-sided Jacobi SVD -> truncate -> split / rescale)."""
+    sites = [s for i, j, _ in gates for s in (i, j)]
+    if len(set(sites)) != len(sites):
+        raise ValueError("bond updates of one batch must act on disjoint sites")
+    for i, j, _ in gates:
+        if getphysicallabel(peps, i) != getvlabel(peps, i)[0] or getphysicallabel(peps, j) != getvlabel(peps, j)[0]:
+            raise ValueError("the device bond update expects the physical leg first (src/peps.jl:253)")
+    built = [bond_job(peps, i, j, mat) for i, j, mat in gates]
+    ctx = _dev(peps.vertex_tensors[gates[0][0] - 1]).ctx
+    jobs = (_lib.TneBondJob * len(built))(*[b[0] for b in built])
+    ctx.check(ctx.L.tne_apply_onbond_batched(ctx.h, len(built), jobs))
+    for (i, j, _), (_, shared), job in zip(gates, built, jobs):
+        si = list(_dev(peps.vertex_tensors[i - 1]).shape)
+        sj = list(_dev(peps.vertex_tensors[j - 1]).shape)
+        si[job.axis_i] = job.kept
+        sj[job.axis_j] = job.kept
+        if job.trunc_err >= 0:
+            LOG.append("truncation error is %r" % job.trunc_err)
+        peps.vertex_tensors[i - 1] = B200Array(job.ti_out, si, False, ctx)
+        peps.vertex_tensors[j - 1] = B200Array(job.tj_out, sj, False, ctx)
+        s = B200Array(job.s_out, (job.kept,), True, ctx)
+        if peps.kind == "vidal":
+            peps.bond_tensors[peps.virtual_labels.index(shared)] = s
     return peps
 
 

@@ -1,0 +1,112 @@
+"""Parity of the device bond update / TEBD (tne_apply_onbond_batched, tne_svd_trunc) against the oracle and the
+dense statevector, up to the SVD gauge: states, norms, singular values and truncation errors are compared, never
+the raw U / V factors (BASELINE.json north_star: "post-TEBD tensors up to SVD gauge")."""
+import numpy as np
+import pytest
+
+from oracle import graphs as OG, peps as OP, tebd as OT, yao as OY
+from helpers import device_peps_like, oracle_peps, rel, seed_for
+
+pytestmark = pytest.mark.gpu
+
+
+def test_svd_trunc_matches_lapack(tne):
+    rng = np.random.default_rng(0)
+    for (m, n) in [(16, 8), (128, 16), (8, 8), (32, 4)]:
+        a = rng.standard_normal((m, n)) + 1j * rng.standard_normal((m, n))
+        u, s, v, kept, err = tne.svd_trunc(tne.B200Array.from_numpy(a), Dmax=n, eps=0.0)
+        sref = np.linalg.svd(a, compute_uv=False)
+        assert kept == n
+        assert rel(s.to_numpy(), sref) < 1e-12
+        U, S, V = u.to_numpy(), s.to_numpy(), v.to_numpy()
+        assert rel(U @ np.diag(S) @ V.conj().T, a) < 1e-12            # A = U S V'
+        assert rel(U.conj().T @ U, np.eye(n)) < 1e-12 and rel(V.conj().T @ V, np.eye(n)) < 1e-12
+        u, s, v, kept, err = tne.svd_trunc(tne.B200Array.from_numpy(a), Dmax=n // 2, eps=0.0)
+        assert kept == n // 2 and abs(err - sref[n // 2:].sum()) < 1e-11 * sref.sum()
+    # rank-deficient input and the absolute eps cut (src/peps.jl:383-385)
+    a = np.outer(rng.standard_normal(16), rng.standard_normal(8)) + 0j
+    u, s, v, kept, err = tne.svd_trunc(tne.B200Array.from_numpy(a), Dmax=8, eps=1e-10)
+    assert kept == 1 and rel(u.to_numpy() @ np.diag(s.to_numpy()) @ v.to_numpy().conj().T, a) < 1e-12
+
+
+def test_known_answer_cnot(tne):  # test/peps.jl:18-19
+    g = tne.graph_from_edges(5, OG.test_graph().edges())
+    p = tne.zero_vidalpeps(g, 2)
+    tne.apply_onsite_(p, 1, OY.X)
+    tne.apply_onbond_(p, 1, 2, np.reshape(OY.CNOT, (2, 2, 2, 2), order="F"))
+    e4 = np.zeros(32, complex); e4[3] = 1
+    assert np.allclose(tne.vec(p), e4)
+
+
+@pytest.mark.parametrize("kind", ["simple", "vidal"])
+def test_random_two_site_gate_vs_dense_and_oracle(tne, kind):  # test/peps.jl:26-44
+    g = OG.test_graph()
+    rng = np.random.default_rng(2)
+    op = oracle_peps(g, 2, 31, kind, Dmax=4)
+    dp = device_peps_like(tne, op, g, 2, Dmax=4)
+    reg = OY.ArrayReg(OP.vec(op))
+    for n, (i, j) in enumerate([(4, 2), (1, 3), (3, 5), (2, 1)]):
+        m = OY.rand_unitary(4, rng)
+        reg.apply_(OY.put(5, (i, j), m))
+        m4 = np.reshape(m, (2, 2, 2, 2), order="F")
+        OP.apply_onbond_(op, i, j, m4)
+        tne.apply_onbond_(dp, i, j, m4)
+        if n < 3:  # exact while the new bond dimension fits Dmax (the last gate needs 8 > Dmax = 4 and truncates)
+            assert rel(tne.vec(dp), reg.state) < 1e-10
+        assert rel(tne.vec(dp), OP.vec(op)) < 1e-10
+        assert [t.shape for t in dp.vertex_tensors] == [t.shape for t in op.vertex_tensors]
+        if kind == "vidal":  # the stored bond vector = singular values (gauge-free)
+            b = op.virtual_labels.index([l for l in OP.getvlabel(op, i) if l in OP.getvlabel(op, j)][0])
+            assert rel(dp.bond_tensors[b].to_numpy(), op.bond_tensors[b]) < 1e-10
+
+
+def test_truncating_gate_matches_oracle(tne):
+    """Dmax = D: every generic gate truncates; the truncated state is unique (gauge-free) and must match."""
+    g = OG.grid([3, 3])
+    rng = np.random.default_rng(3)
+    op = oracle_peps(g, 2, seed_for(3, 2))
+    dp = device_peps_like(tne, op, g, 2)
+    for (i, j) in [(1, 2), (5, 6), (4, 5), (2, 5)]:
+        m4 = np.reshape(OY.rand_unitary(4, rng), (2, 2, 2, 2), order="F")
+        OP.LOG.clear(); tne.peps.LOG.clear()
+        OP.apply_onbond_(op, i, j, m4)
+        tne.apply_onbond_(dp, i, j, m4)
+        assert rel(tne.vec(dp), OP.vec(op)) < 1e-10
+        assert len(tne.peps.LOG) == len(OP.LOG) == 1
+        e_dev = float(tne.peps.LOG[0].split()[-1]); e_ref = float(OP.LOG[0].split()[-1])
+        assert abs(e_dev - e_ref) < 1e-10 * max(1.0, e_ref)
+
+
+@pytest.mark.parametrize("kind", ["simple", "vidal"])
+def test_rydberg_tebd_test_graph(tne, kind):  # test/tebd.jl:4-26
+    g = OG.test_graph()
+    kw = dict(Dmax=10) if kind == "simple" else dict(Dmax=10, eps=1e-10)
+    op = oracle_peps(g, 2, 41, kind, **kw)
+    dp = device_peps_like(tne, op, g, 2, **kw)
+    reg = OY.ArrayReg(OP.vec(op))
+    args = dict(t=0.3, C=10.0, delta=0.2, omega=0.3, nstep=10)
+    gd = tne.graph_from_edges(5, g.edges())
+    if kind == "simple":
+        tne.rydberg_tebd_(dp, gd, **args)
+    else:
+        tne.rydberg_tebd_(dp, **args)
+    OT.rydberg_tebd_(op, g, **args)
+    assert not np.allclose(tne.vec(dp), reg.state, atol=1e-3)
+    OT.rydberg_tebd_(reg, g, **args)
+    assert np.allclose(tne.vec(dp), reg.state, atol=1e-3)      # the reference's own assertion
+    assert rel(tne.vec(dp), OP.vec(op)) < 1e-8                  # and parity with the oracle's tensors (gauge-free)
+
+
+def test_tebd_grid_config1(tne):
+    """BASELINE.json configs[0]: 3x3, D = 2, 10 TEBD steps (9 sweeps), wavefront-batched on the device."""
+    L, D = 3, 2
+    g = OG.grid([L, L])
+    op = oracle_peps(g, D, seed_for(L, D))
+    dp = device_peps_like(tne, op, g, D)
+    args = dict(t=0.3, C=10.0, delta=0.2, omega=0.3, nstep=10)
+    OT.rydberg_tebd_(op, g, **args)
+    tne.rydberg_tebd_(dp, tne.grid([L, L]), **args)
+    assert rel(tne.vec(dp), OP.vec(op)) < 1e-8
+    assert rel(tne.norm(dp).to_numpy(), OP.norm(op)) < 1e-8
+    lv = tne.tebd.wavefronts(g.edges())
+    assert sum(len(b) for b in lv) == g.ne() and all(len({s for e in b for s in e}) == 2 * len(b) for b in lv)
