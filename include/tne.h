@@ -122,6 +122,11 @@ typedef struct {
      * are looped over: every value of the segment that carries such a label is handled one index at a time
      * (1/size of the memory); checkpoints keep their full shape and are read / written through strided
      * views or accumulated.  A label that is open for the whole segment costs no extra flops this way. */
+    /* seg_shard != 0: the segment-local slices are dealt round-robin to the ranks of the context's communicator
+     * (tne_comm_init); after every sliced segment the checkpoints it produced are summed over the ranks with an
+     * NCCL all-reduce on the context's stream, and so are the outputs, which are complete on every rank on
+     * return.  Unsliced segments are replicated. */
+    int32_t seg_shard;
     int32_t n_segments;
     const int32_t* seg_first_node;   /* [n_segments] */
     const int32_t* seg_sliced_off;   /* [n_segments + 1] */

@@ -28,6 +28,7 @@ class TneTree(C.Structure):
         ("sliced_labels", C.POINTER(C.c_int32)),
         ("shard_rank", C.c_int32),
         ("shard_world", C.c_int32),
+        ("seg_shard", C.c_int32),
         ("n_segments", C.c_int32),
         ("seg_first_node", C.POINTER(C.c_int32)),
         ("seg_sliced_off", C.POINTER(C.c_int32)),

@@ -59,6 +59,15 @@ extern "C" int tne_comm_init(tne_ctx* ctx, const void* id128, int rank, int worl
     return TNE_OK;
 }
 
+int comm_allreduce_ptr(tne_ctx* ctx, cplx* p, int64_t n) {
+    if (ctx->world <= 1 || n <= 0) return TNE_OK;
+    if (!ctx->nccl) return tne_fail(ctx, TNE_ERR_NCCL, "tne_comm_init has not been called");
+    const int NCCL_DOUBLE = 8, NCCL_SUM = 0;
+    int rc = g_nccl.allreduce(p, p, (size_t)(2 * n), NCCL_DOUBLE, NCCL_SUM, ctx->nccl, ctx->stream);
+    if (rc != 0) return tne_fail(ctx, TNE_ERR_NCCL, "ncclAllReduce failed: %s", g_nccl.errstr ? g_nccl.errstr(rc) : "?");
+    return TNE_OK;
+}
+
 extern "C" int tne_allreduce_sum(tne_ctx* ctx, int n, const tne_buf* bufs) {
     if (ctx->world <= 1) return TNE_OK;
     if (!ctx->nccl) return tne_fail(ctx, TNE_ERR_NCCL, "tne_comm_init has not been called");

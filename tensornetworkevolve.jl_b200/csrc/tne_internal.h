@@ -144,6 +144,9 @@ int contract_launch(tne_ctx* ctx, const TensorRef& A, const TensorRef& B, const 
 // algorithmic cost of one contraction (SURVEY.md 8(d) accounting)
 void contract_cost(const TensorRef& A, const TensorRef& B, const TensorRef& C, double* flops, double* bytes);
 
+// ---- multi-GPU (tne_comm.cu): in-place sum over the ranks of `n` complex elements at a device pointer
+int comm_allreduce_ptr(tne_ctx* ctx, cplx* p, int64_t n);
+
 // ---- elementwise helpers used across units ---------------------------------------------
 int launch_fill_zero(tne_ctx* ctx, cplx* p, int64_t n);
 int launch_scale_inplace(tne_ctx* ctx, cplx* p, int64_t n, double re, double im);

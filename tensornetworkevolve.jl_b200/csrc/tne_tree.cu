@@ -692,11 +692,16 @@ struct Exec {
         return reinterpret_cast<cplx*>(pv.temp ? ws + persist_bytes + pv.off : ws + val.offset);
     }
 
+    bool seg_shard = false;   // deal segment-local slices to the ranks; all-reduce the checkpoints of sliced segments
+
     int run() {
+        const int world = seg_shard ? std::max(1, ctx->world) : 1, rank = seg_shard ? ctx->rank : 0;
         for (auto& ph : phases) {
+            const bool sharded = world > 1 && ph.nsl > 1;
             for (int v : ph.zero_at_start) TNE_TRY(launch_fill_zero(ctx, base_ptr(ph, v), extent_of(P.vals[v])));
             std::vector<int64_t> idx(ph.sliced.size(), 0);
             for (int64_t it = 0; it < ph.nsl; ++it) {
+                if (sharded && it % world != rank) continue;
                 int64_t rem = it;
                 for (size_t s = 0; s < idx.size(); ++s) { idx[s] = rem % ph.ssz[s]; rem /= ph.ssz[s]; }
                 auto ptr_of = [&](int v) -> cplx* {
@@ -708,11 +713,15 @@ struct Exec {
                 };
                 for (auto& po : ph.ops) {
                     if (po.first_slice_only && it > 0) continue;
+                    // replicated segment: every rank computes the same thing; only rank 0 may add to the outputs
+                    if (world > 1 && !sharded && rank != 0 && P.vals[po.op.out].ext) continue;
                     TNE_TRY(contract_run(ctx, po.plan, ptr_of(po.op.a), ptr_of(po.op.b), ptr_of(po.op.out)));
                     if (po.op.recompute) P.re_flops += po.plan.flops; else { P.flops += po.plan.flops; P.bytes += po.plan.bytes; }
                     P.n_contract++;
                 }
             }
+            if (sharded)
+                for (int v : ph.zero_at_start) TNE_TRY(comm_allreduce_ptr(ctx, base_ptr(ph, v), extent_of(P.vals[v])));
         }
         return TNE_OK;
     }
@@ -737,6 +746,9 @@ extern "C" int tne_expect_terms(tne_ctx* ctx, const tne_tree* tree, const tne_bu
     TNE_TRY(build_forward(B, leaves, leaf_conj, true, &root));
     P.root_val = root;
     Exec E(P);
+    E.seg_shard = tree->seg_shard != 0 && ctx->world > 1;
+    if (E.seg_shard && tree->n_sliced > 0)
+        return tne_fail(ctx, TNE_ERR_UNSUPPORTED, "seg_shard cannot be combined with globally sliced labels");
     TNE_TRY(E.assign_segments(tree));
 
     // outputs live in user-visible buffers, cleared once; every write into them accumulates
@@ -842,6 +854,11 @@ extern "C" int tne_expect_terms(tne_ctx* ctx, const tne_tree* tree, const tne_bu
             }
         }
         int rc = E.run();
+        if (rc) return fail_cleanup(rc);
+    }
+    if (E.seg_shard) {   // outputs are complete on every rank on return
+        int rc = comm_allreduce_ptr(ctx, buf_get(ctx, hval)->ptr(), buf_get(ctx, hval)->nelem);
+        for (size_t g = 0; g < hgrads.size() && !rc; ++g) rc = comm_allreduce_ptr(ctx, buf_get(ctx, hgrads[g])->ptr(), buf_get(ctx, hgrads[g])->nelem);
         if (rc) return fail_cleanup(rc);
     }
     ctx->stats[0] = P.flops; ctx->stats[1] = P.bytes; ctx->stats[2] = (double)P.n_contract;

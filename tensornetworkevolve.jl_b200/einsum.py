@@ -51,6 +51,7 @@ class NestedEinsum:
         self._ser = None
         # optional checkpointed segments (root only): [(first post-order node index, [sliced labels]), ...]
         self.segments = None
+        self.seg_shard = False   # deal the segment-local slices to the ranks of the context's communicator
 
     def isleaf(self):
         return self.tensorindex >= 0
@@ -131,6 +132,7 @@ class SerializedTree:
         t.n_sliced = len(slicing)
         t.sliced_labels = self._keep["sliced"]
         t.shard_rank, t.shard_world = shard
+        t.seg_shard = 1 if nested.seg_shard else 0
         segs = nested.segments or []
         if len(segs) > 1:
             off = [0]
@@ -151,7 +153,7 @@ class SerializedTree:
 
 def serialize(code, shard=(0, 1)):
     nested, slicing = _unwrap(code)
-    key = (tuple(slicing), shard)
+    key = (tuple(slicing), shard, bool(nested.seg_shard))
     if nested._ser is None or nested._ser[0] != key:
         nested._ser = (key, SerializedTree(nested, slicing, shard))
     return nested._ser[1]
