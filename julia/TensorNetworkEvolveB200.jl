@@ -1,0 +1,169 @@
+# TensorNetworkEvolveB200.jl -- the reference-side binding of libtne_b200.so (include/tne.h).
+#
+# NOT EXECUTED in the build environment (no Julia runtime in the image or on the GPU boxes); it mirrors, call for
+# call, the ctypes binding `tensornetworkevolve.jl_b200/_lib.py` + `array.py` that the tests drive.  A maintainer of
+# TensorNetworkEvolve.jl adds this file, `include`s it after `src/TensorAD/TensorAD.jl`, and converts a PEPS with
+# `to_b200(peps)`; every method below hooks the SAME dispatch point the in-tree plug-ins use
+# (`OMEinsum.einsum(code, xs, size_dict)`: src/TensorAD/rules.jl:1-8, src/cracker.jl:4-8).
+module TensorNetworkEvolveB200
+
+using OMEinsum, LinearAlgebra
+using OMEinsum: DynamicEinCode, StaticEinCode, NestedEinsum, SlicedEinsum, getixsv, getiyv
+
+const LIB = Ref{String}("libtne_b200.so")
+const CTX = Ref{Ptr{Cvoid}}(C_NULL)
+
+struct TneError <: Exception
+    msg::String
+end
+
+function check(rc::Cint)
+    rc == 0 && return
+    throw(ErrorException(unsafe_string(ccall((:tne_last_error, LIB[]), Cstring, (Ptr{Cvoid},), CTX[]))))
+end
+
+function __init__()
+    ctx = Ref{Ptr{Cvoid}}(C_NULL)
+    rc = ccall((:tne_ctx_create, LIB[]), Cint, (Cint, Ptr{Ptr{Cvoid}}), parse(Int, get(ENV, "LOCAL_RANK", "0")), ctx)
+    rc == 0 || error("tne_ctx_create failed: there is no CPU fallback, a B200 is required")
+    CTX[] = ctx[]
+end
+
+# ---- device array: slots into `vertex_tensors::Vector{<:AbstractArray{T}}` (src/peps.jl:41) and DiffTensor ------
+mutable struct B200Array{T,N} <: AbstractArray{T,N}
+    handle::Int64
+    dims::NTuple{N,Int}
+    function B200Array{T,N}(h::Int64, dims::NTuple{N,Int}) where {T,N}
+        x = new{T,N}(h, dims)
+        finalizer(a -> ccall((:tne_free, LIB[]), Cint, (Ptr{Cvoid}, Int64), CTX[], a.handle), x)
+        return x
+    end
+end
+Base.size(x::B200Array) = x.dims
+
+function B200Array(a::AbstractArray{T,N}) where {T,N}
+    host = Array{ComplexF64,N}(a)                     # interleaved ComplexF64, column-major
+    h = Ref{Int64}(0)
+    check(ccall((:tne_alloc, LIB[]), Cint, (Ptr{Cvoid}, Cint, Ptr{Int64}, Ptr{Int64}), CTX[], N, collect(Int64, size(a)), h))
+    GC.@preserve host check(ccall((:tne_upload, LIB[]), Cint, (Ptr{Cvoid}, Int64, Ptr{Cvoid}), CTX[], h[], pointer(host)))
+    return B200Array{T,N}(h[], size(a))
+end
+
+function Base.Array(x::B200Array{T,N}) where {T,N}
+    host = Array{ComplexF64,N}(undef, size(x))
+    GC.@preserve host check(ccall((:tne_download, LIB[]), Cint, (Ptr{Cvoid}, Int64, Ptr{Cvoid}), CTX[], x.handle, pointer(host)))
+    return T <: Real ? real.(host) : host
+end
+Base.getindex(x::B200Array{T,0}) where T = Array(x)[]
+
+# ---- OMEinsum.einsum: unary and binary (peps.jl:334,344,373,376,392-393,429; rules.jl:2-5; timeevolve.jl:38) -----
+function OMEinsum.einsum(code::Union{DynamicEinCode,StaticEinCode}, xs::NTuple{N,B200Array}, size_dict::Dict) where N
+    ixs, iy = getixsv(code), getiyv(code)
+    flat = Int32[l for ix in ixs for l in ix]
+    ranks = Int32[length(ix) for ix in ixs]
+    h = Ref{Int64}(0)
+    check(ccall((:tne_einsum, LIB[]), Cint,
+                (Ptr{Cvoid}, Cint, Ptr{Int32}, Ptr{Int32}, Ptr{Int64}, Ptr{Int32}, Ptr{Int32}, Cint, Ptr{Int64}),
+                CTX[], N, flat, ranks, Int64[x.handle for x in xs], zeros(Int32, N), Int32.(iy), length(iy), h))
+    T = promote_type(map(eltype, xs)...)
+    return B200Array{T,length(iy)}(h[], ntuple(k -> size_dict[iy[k]], length(iy)))
+end
+
+# ---- (::NestedEinsum)(xs...) / (::SlicedEinsum)(xs...) fast path (peps.jl:109,321): one tne_contract_tree call ----
+struct TneTree          # layout of `tne_tree` in include/tne.h
+    n_leaves::Int32; n_nodes::Int32
+    leaf_rank::Ptr{Int32}; leaf_labels::Ptr{Int32}; node_children::Ptr{Int32}
+    node_out_rank::Ptr{Int32}; node_out_labels::Ptr{Int32}
+    n_sliced::Int32; sliced_labels::Ptr{Int32}
+    shard_rank::Int32; shard_world::Int32
+    seg_shard::Int32; n_segments::Int32
+    seg_first_node::Ptr{Int32}; seg_sliced_off::Ptr{Int32}; seg_sliced_labels::Ptr{Int32}
+end
+
+function serialize(ne::NestedEinsum, leaf_ixs)
+    children, out_rank, out_labels = Int32[], Int32[], Int32[]
+    counter = Ref(length(leaf_ixs))
+    function walk(nd)
+        OMEinsum.isleaf(nd) && return Int32(nd.tensorindex - 1)
+        ids = [walk(a) for a in nd.args]
+        append!(children, ids); push!(out_rank, length(getiyv(nd.eins))); append!(out_labels, Int32.(getiyv(nd.eins)))
+        me = counter[]; counter[] += 1
+        return Int32(me)
+    end
+    walk(ne)
+    return children, out_rank, out_labels
+end
+
+function (ne::NestedEinsum)(xs::B200Array...; slicing = Int32[], conj_flags = zeros(Int32, length(xs)))
+    leaf_ixs = OMEinsum.getixsv(ne)
+    children, out_rank, out_labels = serialize(ne, leaf_ixs)
+    lr = Int32[length(ix) for ix in leaf_ixs]; ll = Int32[l for ix in leaf_ixs for l in ix]
+    h = Ref{Int64}(0)
+    GC.@preserve lr ll children out_rank out_labels slicing begin
+        t = Ref(TneTree(length(xs), length(out_rank), pointer(lr), pointer(ll), pointer(children), pointer(out_rank),
+                        pointer(out_labels), length(slicing), pointer(slicing), 0, 1, 0, 0, C_NULL, C_NULL, C_NULL))
+        check(ccall((:tne_contract_tree, LIB[]), Cint, (Ptr{Cvoid}, Ptr{TneTree}, Ptr{Int64}, Ptr{Int32}, Ptr{Int64}),
+                    CTX[], t, Int64[x.handle for x in xs], conj_flags, h))
+    end
+    iy = getiyv(ne.eins)
+    sd = OMEinsum.get_size_dict(leaf_ixs, xs)
+    return B200Array{ComplexF64,length(iy)}(h[], ntuple(k -> sd[iy[k]], length(iy)))
+end
+(se::SlicedEinsum)(xs::B200Array...) = se.eins(xs...; slicing = Int32.(se.slicing))
+
+# ---- Base / broadcast methods TensorAD's rules and src/peps.jl:283-295 call on tensors -----------------------------
+const MAP = Dict(:copy => 0, :conj => 1, :real => 2, :imag => 3, :abs => 4, :sqrt => 5, :inv => 6, :neg => 7, :scale => 8, :pow => 9)
+function tne_map(op::Symbol, x::B200Array{T,N}, s::Number = 0.0; RT = T) where {T,N}
+    h = Ref{Int64}(0)
+    check(ccall((:tne_map, LIB[]), Cint, (Ptr{Cvoid}, Cint, Int64, Cdouble, Cdouble, Ptr{Int64}), CTX[], MAP[op], x.handle, real(s), imag(s), h))
+    return B200Array{RT,N}(h[], size(x))
+end
+Base.conj(x::B200Array) = tne_map(:conj, x)
+Base.copy(x::B200Array) = tne_map(:copy, x)
+Base.real(x::B200Array{T}) where T = tne_map(:real, x; RT = real(T))
+Base.:*(x::B200Array, c::Number) = tne_map(:scale, x, c)
+Base.:*(c::Number, x::B200Array) = tne_map(:scale, x, c)
+Base.:-(x::B200Array) = tne_map(:neg, x)
+Base.Broadcast.broadcasted(::typeof(abs), x::B200Array{T}) where T = tne_map(:abs, x; RT = real(T))
+Base.Broadcast.broadcasted(::typeof(sqrt), x::B200Array) = tne_map(:sqrt, x)
+Base.Broadcast.broadcasted(::typeof(inv), x::B200Array) = tne_map(:inv, x)
+Base.Broadcast.broadcasted(::typeof(^), x::B200Array, p::Real) = tne_map(:pow, x, p)
+function tne_map2(op::Int, a::B200Array, b::B200Array)
+    h = Ref{Int64}(0)
+    check(ccall((:tne_map2, LIB[]), Cint, (Ptr{Cvoid}, Cint, Int64, Int64, Ptr{Int64}), CTX[], op, a.handle, b.handle, h))
+    big = length(a) >= length(b) ? a : b
+    return B200Array{promote_type(eltype(a), eltype(b)),ndims(big)}(h[], size(big))
+end
+Base.:+(a::B200Array, b::B200Array) = tne_map2(0, a, b)
+Base.:-(a::B200Array, b::B200Array) = tne_map2(1, a, b)
+Base.:*(a::B200Array{T,0}, b::B200Array) where T = tne_map2(2, a, b)      # rules.jl:79-88
+Base.:*(a::B200Array, b::B200Array{T,0}) where T = tne_map2(2, a, b)
+function Base.reshape(x::B200Array{T}, dims::Dims{N}) where {T,N}
+    h = Ref{Int64}(0)
+    check(ccall((:tne_reshape, LIB[]), Cint, (Ptr{Cvoid}, Int64, Cint, Ptr{Int64}, Ptr{Int64}), CTX[], x.handle, N, collect(Int64, dims), h))
+    return B200Array{T,N}(h[], dims)
+end
+function Base.getindex(x::B200Array{T,1}, r::UnitRange{Int}) where T     # variables[a:b], src/peps.jl:217
+    h = Ref{Int64}(0)
+    check(ccall((:tne_slice, LIB[]), Cint, (Ptr{Cvoid}, Int64, Int64, Int64, Ptr{Int64}), CTX[], x.handle, first(r) - 1, length(r), h))
+    return B200Array{T,1}(h[], (length(r),))
+end
+function Base.vcat(xs::B200Array...)                                       # variables(peps), src/peps.jl:202
+    h = Ref{Int64}(0)
+    check(ccall((:tne_concat, LIB[]), Cint, (Ptr{Cvoid}, Cint, Ptr{Int64}, Ptr{Int64}), CTX[], length(xs), Int64[x.handle for x in xs], h))
+    return B200Array{promote_type(map(eltype, xs)...),1}(h[], (sum(length, xs),))
+end
+OMEinsum.asarray(x::Number, ::B200Array) = B200Array(fill(x))
+
+# ---- LinearAlgebra.svd on the bond matrix (src/peps.jl:381) and the fused apply_onbond! -------------------------------
+function LinearAlgebra.svd(a::B200Array{T,2}; Dmax = minimum(size(a)), ϵ = 0.0) where T
+    u, s, v = Ref{Int64}(0), Ref{Int64}(0), Ref{Int64}(0); kept = Ref{Int32}(0); err = Ref{Cdouble}(0)
+    check(ccall((:tne_svd_trunc, LIB[]), Cint, (Ptr{Cvoid}, Int64, Cint, Cdouble, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Int32}, Ptr{Cdouble}),
+                CTX[], a.handle, Dmax, ϵ, u, s, v, kept, err))
+    k = Int(kept[])
+    return (U = B200Array{T,2}(u[], (size(a, 1), k)), S = B200Array{real(T),1}(s[], (k,)), V = B200Array{T,2}(v[], (size(a, 2), k)))
+end
+
+to_b200(peps) = TensorNetworkEvolve.replace_tensors(peps, B200Array.(TensorNetworkEvolve.alltensors(peps)))
+
+end # module
