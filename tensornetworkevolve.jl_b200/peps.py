@@ -471,9 +471,13 @@ def apply_block(peps, block):
     raise TypeError("no apply method for %s" % type(block).__name__)
 
 
-def _term_replacements(pb, block):
+def _term_replacements(pb, block, cache=None):
     """(coef, {site: replacement tensor}) of one Hamiltonian term applied to the ket, or None if the
-    term is not a product of one-site operators (then the generic path is used)."""
+    term is not a product of one-site operators (then the generic path is used).  Scalar factors of the
+    one-site matrices are moved into ``coef`` and equal (site, matrix) pairs share ONE device tensor
+    (``cache``), so that terms which agree on a site share their partial contractions in the device
+    programme (C P1_i P1_j and C P1_i P1_k open the same pattern at site i)."""
+    cache = {} if cache is None else cache
     coef = 1.0 + 0j
     while isinstance(block, yao.Scale):
         coef *= block.factor
@@ -484,13 +488,26 @@ def _term_replacements(pb, block):
         pairs = list(zip(block.locs, block.subblocks))
     else:
         return None
+    merged = {}
+    for loc, m in pairs:   # several factors on one site multiply (later factors act last)
+        m = np.asarray(m, dtype=np.complex128)
+        merged[loc] = m @ merged[loc] if loc in merged else m
     repl = {}
-    for loc, m in pairs:
-        base = repl.get(loc, _dev(pb.vertex_tensors[loc - 1]))
-        old = getvlabel(pb, loc)
-        mlabel = [newlabel(pb, 1), getphysicallabel(pb, loc)]
-        repl[loc] = es.einsum([old, mlabel], [base, B200Array.from_numpy(np.asarray(m, dtype=np.complex128))],
-                              [mlabel[0] if l == mlabel[1] else l for l in old])
+    for loc, m in merged.items():
+        flat = m.reshape(-1, order="F")
+        nz = np.flatnonzero(np.abs(flat) > 0)
+        if nz.size == 0:
+            return 0.0 + 0j, {}
+        nu = flat[nz[0]]
+        coef *= nu
+        m = m / nu
+        key = (loc, m.tobytes())
+        if key not in cache:
+            old = getvlabel(pb, loc)
+            mlabel = [newlabel(pb, 1), getphysicallabel(pb, loc)]
+            cache[key] = es.einsum([old, mlabel], [_dev(pb.vertex_tensors[loc - 1]), B200Array.from_numpy(m)],
+                                   [mlabel[0] if l == mlabel[1] else l for l in old])
+        repl[loc] = cache[key]
     return coef, repl
 
 
@@ -500,7 +517,8 @@ def expect(op, pa, pb, shard=(0, 1)):  # src/peps.jl:469-477
     (rank, world)`` keeps only this rank's terms (the caller sums the partial values)."""
     if isinstance(op, yao.Add):
         fused = es.FUSED_TREES and len(pa.alltensors()) == len(pb.alltensors())
-        terms = [_term_replacements(pb, t) for t in op.blocks] if fused else None
+        cache = {}
+        terms = [_term_replacements(pb, t, cache) for t in op.blocks] if fused else None
         if fused and all(t is not None for t in terms) and all(_isdiff(t) for t in pa.alltensors()) == any(_isdiff(t) for t in pa.alltensors()):
             return _expect_fused(terms, pa, pb, shard)
         out = None
