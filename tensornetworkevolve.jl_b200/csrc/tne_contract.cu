@@ -324,6 +324,48 @@ static int contract_run_inner(tne_ctx* ctx, const ContractPlan& plan, const cplx
     return TNE_OK;
 }
 
+static bool legs_equal(const LegSet& x, const LegSet& y) {
+    if (x.n != y.n) return false;
+    for (int i = 0; i < x.n; ++i)
+        if (x.size[i] != y.size[i] || x.s0[i] != y.s0[i] || x.s1[i] != y.s1[i] || x.s2[i] != y.s2[i]) return false;
+    return true;
+}
+
+bool contract_multi_compatible(const ContractPlan& x, const ContractPlan& y) {
+    if (x.empty || y.empty || !gett_multi_capable(x) || !gett_multi_capable(y)) return false;
+    if (x.swapped != y.swapped || x.aux[0] != y.aux[0] || x.aux[1] != y.aux[1]) return false;
+    const GettDesc &a = x.d, &b = y.d;
+    return a.Msz == b.Msz && a.Nsz == b.Nsz && a.Ksz == b.Ksz && a.Bsz == b.Bsz && legs_equal(a.M, b.M) && legs_equal(a.N, b.N) &&
+           legs_equal(a.K, b.K) && legs_equal(a.Bt, b.Bt);
+}
+
+int contract_run_multi(tne_ctx* ctx, int T, const ContractPlan* const* plans, const cplx* const* As, const cplx* const* Bs, cplx* C) {
+    if (T == 1) return contract_run(ctx, *plans[0], As[0], Bs[0], C);
+    AbsorbMulti ops;
+    ops.T = T;
+    for (int t = 0; t < T; ++t) {
+        const ContractPlan& p = *plans[t];
+        ops.A[t] = p.swapped ? Bs[t] : As[t];
+        ops.B[t] = p.swapped ? As[t] : Bs[t];
+        ops.conjA[t] = p.d.conjA; ops.conjB[t] = p.d.conjB;
+        ops.are[t] = p.d.alphaRe; ops.aim[t] = p.d.alphaIm;
+    }
+    if (!ctx->opt_profile) return gett_fast_run_multi(ctx, *plans[0], ops, C);
+    tne_ctx::ProfRec r;
+    cudaEvent_t* ev[2] = {&r.e0, &r.e1};
+    for (auto e : ev) {
+        if (!ctx->event_pool.empty()) { *e = ctx->event_pool.back(); ctx->event_pool.pop_back(); }
+        else TNE_CUDA(ctx, cudaEventCreate(e));
+    }
+    r.cls = 1; r.flops = 0; r.bytes = 0;
+    for (int t = 0; t < T; ++t) { r.flops += plans[t]->flops; r.bytes += plans[t]->bytes - (t ? 16.0 * (double)plans[t]->c_nelem : 0.0); }
+    TNE_CUDA(ctx, cudaEventRecord(r.e0, ctx->stream));
+    int rc = gett_fast_run_multi(ctx, *plans[0], ops, C);
+    TNE_CUDA(ctx, cudaEventRecord(r.e1, ctx->stream));
+    ctx->prof.push_back(r);
+    return rc;
+}
+
 int contract_launch(tne_ctx* ctx, const TensorRef& A, const TensorRef& B, const TensorRef& C, bool accumulate,
                     double alpha_re, double alpha_im) {
     ContractPlan plan;
@@ -332,6 +374,8 @@ int contract_launch(tne_ctx* ctx, const TensorRef& A, const TensorRef& B, const 
 }
 
 #ifndef TNE_HAVE_DMMA
+bool gett_multi_capable(const ContractPlan&) { return false; }
+int gett_fast_run_multi(tne_ctx* ctx, const ContractPlan&, const AbsorbMulti&, cplx*) { return tne_fail(ctx, TNE_ERR_UNSUPPORTED, "no fast path built"); }
 int gett_fast_plan(tne_ctx*, ContractPlan*) { return TNE_OK; }
 int gett_fast_run(tne_ctx* ctx, const ContractPlan&, const cplx*, const cplx*, cplx*) { return tne_fail(ctx, TNE_ERR_UNSUPPORTED, "no fast path built"); }
 #endif

@@ -207,6 +207,108 @@ __global__ void __launch_bounds__(256, MINB) gett_absorb(const __grid_constant__
 }
 
 // ---------------------------------------------------------------------------------------
+// absorb with several contributions into one output:  C (+)= sum_t alpha_t op(A_t) op(B_t)  where all A_t have
+// the same layout (the variants of the term dynamic programme at one tree node, or the cotangents of all
+// consumers of one value).  The accumulators stay in registers across the contributions, so C is written once
+// instead of being read and re-written by every further contribution.
+// ---------------------------------------------------------------------------------------
+template <int KS>
+__global__ void __launch_bounds__(256, 2) gett_absorb_multi(const __grid_constant__ GettDesc d, const __grid_constant__ AbsorbMulti ops,
+                                                            cplx* __restrict__ C, int Np) {
+    constexpr int KP = 2 * KS;
+    constexpr int STRIDE = 4 * KS + 4;
+    constexpr int NTMAX = 8;              // Np <= 32
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* Bs = reinterpret_cast<double*>(smem_raw);                                   // [T][2 Np][STRIDE]
+    long long* offAk = reinterpret_cast<long long*>(Bs + ops.T * 2 * Np * STRIDE);       // [KP]
+    long long* offCn = offAk + KP;                                                      // [Np]
+    const int tid = threadIdx.x;
+    for (int k = tid; k < KP; k += blockDim.x) {
+        long long a = -1, b = 0;
+        if (k < d.Ksz) decomp2(d.K, k, a, b);
+        offAk[k] = a;
+    }
+    for (int n = tid; n < Np; n += blockDim.x) {
+        long long b = 0, c = -1;
+        if (n < d.Nsz) decomp2(d.N, n, b, c);
+        offCn[n] = c;
+    }
+    for (int e = tid; e < ops.T * Np * KP; e += blockDim.x) {
+        const int t = e / (Np * KP), r = e - t * (Np * KP);
+        const int k = r % KP, n = r / KP;
+        const double sA = ops.conjA[t] ? -1.0 : 1.0;
+        double br = 0.0, bi = 0.0;
+        if (k < d.Ksz && n < d.Nsz) {
+            long long ak, bk, bn, cn;
+            decomp2(d.K, k, ak, bk);
+            decomp2(d.N, n, bn, cn);
+            cplx v = ops.B[t][bk + bn];
+            if (ops.conjB[t]) v.y = -v.y;
+            br = ops.are[t] * v.x - ops.aim[t] * v.y;
+            bi = ops.are[t] * v.y + ops.aim[t] * v.x;
+        }
+        const int jre = 8 * (k >> 2) + (k & 3), jim = jre + 4;
+        double* r0 = Bs + (t * 2 * Np + 2 * n) * STRIDE;
+        double* r1 = r0 + STRIDE;
+        r0[jre] = br; r0[jim] = -sA * bi;
+        r1[jre] = bi; r1[jim] = sA * br;
+    }
+    __syncthreads();
+
+    const int lane = tid & 31;
+    const int lrow = lane >> 2, lcol = lane & 3;
+    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+    const long long ntiles = (d.Msz + 7) >> 3;
+    const int NT = Np >> 2;
+    const long long g = (long long)blockIdx.x * (blockDim.x >> 5) + (tid >> 5);
+    RowCache rc;
+    constexpr int CH = 4;
+    const long long nchunks = (ntiles + CH - 1) / CH;
+    for (long long ch = g; ch < nchunks; ch += nwarps) {
+        const long long wlast = min(ntiles, (ch + 1) * CH);
+        for (long long w = ch * CH; w < wlast; ++w) {
+            const long long row = (w << 3) + lrow;
+            const bool ok = row < d.Msz;
+            long long oA = 0, oC = 0;
+            if (ok) row_offsets(d, rc, row, oA, oC);
+            double c[NTMAX][2];
+#pragma unroll
+            for (int nt = 0; nt < NTMAX; ++nt) { c[nt][0] = 0.0; c[nt][1] = 0.0; }
+            for (int t = 0; t < ops.T; ++t) {
+                double a[KS];
+                const cplx* At = ops.A[t];
+#pragma unroll
+                for (int q = 0; q < KS / 2; ++q) {
+                    const long long ofk = offAk[4 * q + lcol];
+                    cplx v = make_double2(0.0, 0.0);
+                    if (ok && ofk >= 0) v = __ldcs(At + oA + ofk);
+                    a[2 * q] = v.x; a[2 * q + 1] = v.y;
+                }
+                const double* brow = Bs + (t * 2 * Np + lrow) * STRIDE + lcol;
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks) {
+#pragma unroll
+                    for (int nt = 0; nt < NTMAX; ++nt)
+                        if (nt < NT) dmma884(c[nt][0], c[nt][1], a[ks], brow[nt * 8 * STRIDE + 4 * ks]);
+                }
+            }
+            if (ok) {
+#pragma unroll
+                for (int nt = 0; nt < NTMAX; ++nt) {
+                    if (nt >= NT) continue;
+                    const long long ofn = offCn[4 * nt + lcol];
+                    if (ofn < 0) continue;
+                    cplx* p = C + oC + ofn;
+                    cplx v = make_double2(c[nt][0], c[nt][1]);
+                    if (d.accumulate) { cplx o = *p; v.x += o.x; v.y += o.y; }
+                    __stcs(p, v);
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // absorb, TMA-staged: the same math, but the A tiles travel HBM -> shared memory as bulk async copies
 // (cp.async.bulk, completion on an mbarrier) issued by a producer warp into a STAGES-deep ring, so the
 // HBM latency is covered by the ring instead of by registers of DMMA-heavy warps.  Applies when a tile of
@@ -650,6 +752,21 @@ int launch_absorb(tne_ctx* ctx, const ContractPlan& plan, const cplx* A, const c
     return TNE_OK;
 }
 
+template <int KS>
+int launch_absorb_multi(tne_ctx* ctx, const ContractPlan& plan, const AbsorbMulti& ops, cplx* C) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(gett_absorb_multi<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
+        attr_set = true;
+    }
+    const int Np = plan.aux[1];
+    const size_t smem = (size_t)ops.T * (2 * Np) * (4 * KS + 4) * sizeof(double) + (size_t)(2 * KS + Np) * sizeof(long long);
+    unsigned gx = (unsigned)std::min<long long>((long long)plan.gx, ((plan.d.Msz + 7) / 8 + 7) / 8);
+    gett_absorb_multi<KS><<<gx, 256, smem, ctx->stream>>>(plan.d, ops, C, Np);
+    TNE_LAUNCH_CHECK(ctx);
+    return TNE_OK;
+}
+
 template <int KS, int MTW>
 int launch_absorb_tma(tne_ctx* ctx, const ContractPlan& plan, const cplx* A, const cplx* B, cplx* C) {
     static bool attr_set = false;
@@ -790,6 +907,20 @@ int gett_fast_plan(tne_ctx* ctx, ContractPlan* plan) {
         return TNE_OK;
     }
     return TNE_OK;
+}
+
+bool gett_multi_capable(const ContractPlan& plan) {
+    return plan.kernel == KERNEL_ABSORB && plan.aux[1] <= 32;
+}
+
+int gett_fast_run_multi(tne_ctx* ctx, const ContractPlan& plan, const AbsorbMulti& ops, cplx* C) {
+    switch (plan.aux[0]) {
+        case 2: return launch_absorb_multi<2>(ctx, plan, ops, C);
+        case 4: return launch_absorb_multi<4>(ctx, plan, ops, C);
+        case 8: return launch_absorb_multi<8>(ctx, plan, ops, C);
+        case 16: return launch_absorb_multi<16>(ctx, plan, ops, C);
+    }
+    return tne_fail(ctx, TNE_ERR_UNSUPPORTED, "absorb (multi) kernel: bad k-step count %d", plan.aux[0]);
 }
 
 int gett_fast_run(tne_ctx* ctx, const ContractPlan& plan, const cplx* A, const cplx* B, cplx* C) {

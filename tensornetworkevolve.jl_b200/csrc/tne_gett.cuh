@@ -38,3 +38,5 @@ __device__ __forceinline__ void atomic_add_c(cplx* p, double re, double im) {
 // DMMA fast paths: pick a kernel for the classified contraction (plan->kernel stays 0 if none applies)
 int gett_fast_plan(tne_ctx* ctx, ContractPlan* plan);
 int gett_fast_run(tne_ctx* ctx, const ContractPlan& plan, const cplx* A, const cplx* B, cplx* C);
+bool gett_multi_capable(const ContractPlan& plan);
+int gett_fast_run_multi(tne_ctx* ctx, const ContractPlan& plan, const AbsorbMulti& ops, cplx* C);

@@ -51,6 +51,7 @@ struct tne_ctx {
     int64_t opt_debug = 0;
     int64_t opt_profile = 0;
     int64_t opt_pad = 0;                   // stride padding (elements) of workspace tensors, see tne_tree.cu
+    int64_t opt_no_fuse = 0;               // 1: one launch per contribution (no gett_absorb_multi)
     int64_t opt_absorb_tma = 0;            // 1: TMA-staged absorb kernel where applicable (default: register-fed)
     int64_t opt_no_reduce_tma = 0;         // 1: register-fed reduce kernel instead of the TMA-staged one
     struct ProfRec { cudaEvent_t e0, e1; int cls; double flops, bytes; };
@@ -135,6 +136,18 @@ struct ContractPlan {
     unsigned char blob[64] = {0};   // kernel-specific geometry (tne_contract_dmma.cu)
     double flops = 0, bytes = 0;
 };
+// several contributions into one output through the DMMA absorb kernel (see gett_absorb_multi)
+#define TNE_MULTI_MAX 3
+struct AbsorbMulti {
+    int T;
+    const cplx* A[TNE_MULTI_MAX];
+    const cplx* B[TNE_MULTI_MAX];
+    int conjA[TNE_MULTI_MAX], conjB[TNE_MULTI_MAX];
+    double are[TNE_MULTI_MAX], aim[TNE_MULTI_MAX];
+};
+bool contract_multi_compatible(const ContractPlan& x, const ContractPlan& y);
+// C (+)= sum_t: plans[t] are compatible plans; As/Bs are the operands in the ORIGINAL (a, b) order of each op
+int contract_run_multi(tne_ctx* ctx, int T, const ContractPlan* const* plans, const cplx* const* As, const cplx* const* Bs, cplx* C);
 int contract_plan(tne_ctx* ctx, const TensorRef& A, const TensorRef& B, const TensorRef& C, bool accumulate,
                   double alpha_re, double alpha_im, ContractPlan* plan);
 int contract_run(tne_ctx* ctx, const ContractPlan& plan, const cplx* A, const cplx* B, cplx* C);

@@ -398,6 +398,10 @@ struct PhaseOp {
     Op op;
     ContractPlan plan;
     bool first_slice_only = false;
+    bool dead = false;                 // merged into a later op
+    // further contributions into the same output, fused into one launch (gett_absorb_multi)
+    struct Extra { int a, b; ContractPlan plan; };
+    std::vector<Extra> extra;
 };
 
 struct Phase {
@@ -583,12 +587,43 @@ struct Exec {
             }
             ph.ops.push_back(std::move(po));
         }
+        // fuse consecutive writers of one output that run the absorb kernel with identical geometry: the group
+        // moves to the position of its last member (all inputs are ready there), C is written once
+        if (!ctx->opt_no_fuse) {
+            std::vector<PhaseOp> merged;
+            std::map<int, int> open;   // output value -> index in `merged` of a group that may still grow
+            for (auto& po : ph.ops) {
+                const int out = po.op.out;
+                int ins[2] = {po.op.a, po.op.b};
+                for (int v : ins) if (v >= 0) open.erase(v);   // a reader closes the group of the value it reads
+                auto it = open.find(out);
+                if (it != open.end() && po.op.kind == OP_CONTRACT && !po.plan.empty) {
+                    PhaseOp& g = merged[it->second];
+                    if ((int)g.extra.size() + 1 < TNE_MULTI_MAX && g.first_slice_only == po.first_slice_only &&
+                        contract_multi_compatible(g.plan, po.plan)) {
+                        PhaseOp moved = g;
+                        g.dead = true;
+                        moved.extra.push_back({po.op.a, po.op.b, po.plan});
+                        merged.push_back(std::move(moved));
+                        open[out] = (int)merged.size() - 1;
+                        continue;
+                    }
+                }
+                merged.push_back(po);
+                if (po.op.kind == OP_CONTRACT && !po.plan.empty && contract_multi_compatible(po.plan, po.plan)) open[out] = (int)merged.size() - 1;
+                else open.erase(out);
+            }
+            std::vector<PhaseOp> kept;
+            for (auto& po : merged) if (!po.dead) kept.push_back(std::move(po));
+            ph.ops.swap(kept);
+        }
         // temp arena of this phase
         std::vector<Interval> iv;
         std::map<int, int> slot;
         for (int i = 0; i < (int)ph.ops.size(); ++i) {
             const Op& op = ph.ops[i].op;
-            int ids[3] = {op.out, op.a, op.b};
+            std::vector<int> ids = {op.out, op.a, op.b};
+            for (auto& ex : ph.ops[i].extra) { ids.push_back(ex.a); ids.push_back(ex.b); }
             for (int v : ids) {
                 if (v < 0 || !ph.views.at(v).temp) continue;
                 auto it = slot.find(v);
@@ -715,7 +750,20 @@ struct Exec {
                     if (po.first_slice_only && it > 0) continue;
                     // replicated segment: every rank computes the same thing; only rank 0 may add to the outputs
                     if (world > 1 && !sharded && rank != 0 && P.vals[po.op.out].ext) continue;
-                    TNE_TRY(contract_run(ctx, po.plan, ptr_of(po.op.a), ptr_of(po.op.b), ptr_of(po.op.out)));
+                    if (po.extra.empty()) {
+                        TNE_TRY(contract_run(ctx, po.plan, ptr_of(po.op.a), ptr_of(po.op.b), ptr_of(po.op.out)));
+                    } else {
+                        const ContractPlan* plans[TNE_MULTI_MAX];
+                        const cplx *As[TNE_MULTI_MAX], *Bs[TNE_MULTI_MAX];
+                        int T = 0;
+                        plans[T] = &po.plan; As[T] = ptr_of(po.op.a); Bs[T] = ptr_of(po.op.b); ++T;
+                        for (auto& ex : po.extra) { plans[T] = &ex.plan; As[T] = ptr_of(ex.a); Bs[T] = ptr_of(ex.b); ++T; }
+                        TNE_TRY(contract_run_multi(ctx, T, plans, As, Bs, ptr_of(po.op.out)));
+                        for (auto& ex : po.extra) {
+                            if (po.op.recompute) P.re_flops += ex.plan.flops;
+                            else { P.flops += ex.plan.flops; P.bytes += ex.plan.bytes - 16.0 * (double)ex.plan.c_nelem; }
+                        }
+                    }
                     if (po.op.recompute) P.re_flops += po.plan.flops; else { P.flops += po.plan.flops; P.bytes += po.plan.bytes; }
                     P.n_contract++;
                 }
