@@ -58,13 +58,24 @@ class Context:
         return dict(flops=s[0], bytes=s[1], contractions=int(s[2]), workspace_bytes=int(s[3]),
                     recompute_flops=s[4], values=int(s[5]))
 
-    def profile_collect(self):
-        """Per kernel class: launches, device ms, algorithmic flops and bytes since the last call."""
+    def profile_collect(self, fine=False):
+        """Per kernel: launches, device ms, algorithmic flops and bytes since the last call.  ``fine``: keyed by
+        (kernel, bucket) where the bucket of an absorb kernel is log2(padded K / 2) (5, 6: fused launches)."""
         names = ["gett_generic", "gett_absorb", "gett_reduce", "gett_absorb_tma", "gett_reduce_tma"]
-        out = (C.c_double * (4 * len(names)))()
+        ncls = 40
+        out = (C.c_double * (4 * ncls))()
         self.check(self.L.tne_profile_collect(self.h, out))
-        return {names[c]: dict(launches=int(out[4 * c]), ms=out[4 * c + 1], flops=out[4 * c + 2], bytes=out[4 * c + 3])
-                for c in range(len(names))}
+        res = {}
+        for c in range(ncls):
+            if out[4 * c] == 0:
+                continue
+            key = (names[c // 8], c % 8) if fine else names[c // 8]
+            d = res.setdefault(key, dict(launches=0, ms=0.0, flops=0.0, bytes=0.0))
+            d["launches"] += int(out[4 * c]); d["ms"] += out[4 * c + 1]; d["flops"] += out[4 * c + 2]; d["bytes"] += out[4 * c + 3]
+        if not fine:
+            for n in names:
+                res.setdefault(n, dict(launches=0, ms=0.0, flops=0.0, bytes=0.0))
+        return res
 
     def mem_info(self):
         a, b, c = C.c_int64(), C.c_int64(), C.c_int64()

@@ -306,7 +306,8 @@ int contract_run(tne_ctx* ctx, const ContractPlan& plan, const cplx* A, const cp
         if (!ctx->event_pool.empty()) { *e = ctx->event_pool.back(); ctx->event_pool.pop_back(); }
         else TNE_CUDA(ctx, cudaEventCreate(e));
     }
-    r.cls = plan.kernel; r.flops = plan.flops; r.bytes = plan.bytes;
+    r.cls = 8 * plan.kernel + ((plan.kernel == 1 || plan.kernel == 3) ? (plan.aux[0] >= 16 ? 4 : plan.aux[0] >= 8 ? 3 : plan.aux[0] >= 4 ? 2 : 1) : 0);
+    r.flops = plan.flops; r.bytes = plan.bytes;
     TNE_CUDA(ctx, cudaEventRecord(r.e0, ctx->stream));
     int rc = contract_run_inner(ctx, plan, A, B, C);
     TNE_CUDA(ctx, cudaEventRecord(r.e1, ctx->stream));
@@ -357,7 +358,7 @@ int contract_run_multi(tne_ctx* ctx, int T, const ContractPlan* const* plans, co
         if (!ctx->event_pool.empty()) { *e = ctx->event_pool.back(); ctx->event_pool.pop_back(); }
         else TNE_CUDA(ctx, cudaEventCreate(e));
     }
-    r.cls = 1; r.flops = 0; r.bytes = 0;
+    r.cls = 8 * 1 + 5 + (plans[0]->aux[0] >= 16 ? 1 : 0); r.flops = 0; r.bytes = 0;   // buckets 5, 6: fused multi-contribution launches
     for (int t = 0; t < T; ++t) { r.flops += plans[t]->flops; r.bytes += plans[t]->bytes - (t ? 16.0 * (double)plans[t]->c_nelem : 0.0); }
     TNE_CUDA(ctx, cudaEventRecord(r.e0, ctx->stream));
     int rc = gett_fast_run_multi(ctx, *plans[0], ops, C);

@@ -212,12 +212,11 @@ __global__ void __launch_bounds__(256, MINB) gett_absorb(const __grid_constant__
 // consumers of one value).  The accumulators stay in registers across the contributions, so C is written once
 // instead of being read and re-written by every further contribution.
 // ---------------------------------------------------------------------------------------
-template <int KS>
-__global__ void __launch_bounds__(256, 2) gett_absorb_multi(const __grid_constant__ GettDesc d, const __grid_constant__ AbsorbMulti ops,
+template <int KS, int NTMAX>
+__global__ void __launch_bounds__(256, 3) gett_absorb_multi(const __grid_constant__ GettDesc d, const __grid_constant__ AbsorbMulti ops,
                                                             cplx* __restrict__ C, int Np) {
     constexpr int KP = 2 * KS;
-    constexpr int STRIDE = 4 * KS + 4;
-    constexpr int NTMAX = 8;              // Np <= 32
+    constexpr int STRIDE = 4 * KS + 4;    // NTMAX = Np / 4 n-tiles, all accumulated at once
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* Bs = reinterpret_cast<double*>(smem_raw);                                   // [T][2 Np][STRIDE]
     long long* offAk = reinterpret_cast<long long*>(Bs + ops.T * 2 * Np * STRIDE);       // [KP]
@@ -259,7 +258,6 @@ __global__ void __launch_bounds__(256, 2) gett_absorb_multi(const __grid_constan
     const int lrow = lane >> 2, lcol = lane & 3;
     const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
     const long long ntiles = (d.Msz + 7) >> 3;
-    const int NT = Np >> 2;
     const long long g = (long long)blockIdx.x * (blockDim.x >> 5) + (tid >> 5);
     RowCache rc;
     constexpr int CH = 4;
@@ -288,14 +286,12 @@ __global__ void __launch_bounds__(256, 2) gett_absorb_multi(const __grid_constan
 #pragma unroll
                 for (int ks = 0; ks < KS; ++ks) {
 #pragma unroll
-                    for (int nt = 0; nt < NTMAX; ++nt)
-                        if (nt < NT) dmma884(c[nt][0], c[nt][1], a[ks], brow[nt * 8 * STRIDE + 4 * ks]);
+                    for (int nt = 0; nt < NTMAX; ++nt) dmma884(c[nt][0], c[nt][1], a[ks], brow[nt * 8 * STRIDE + 4 * ks]);
                 }
             }
             if (ok) {
 #pragma unroll
                 for (int nt = 0; nt < NTMAX; ++nt) {
-                    if (nt >= NT) continue;
                     const long long ofn = offCn[4 * nt + lcol];
                     if (ofn < 0) continue;
                     cplx* p = C + oC + ofn;
@@ -752,17 +748,17 @@ int launch_absorb(tne_ctx* ctx, const ContractPlan& plan, const cplx* A, const c
     return TNE_OK;
 }
 
-template <int KS>
+template <int KS, int NT>
 int launch_absorb_multi(tne_ctx* ctx, const ContractPlan& plan, const AbsorbMulti& ops, cplx* C) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(gett_absorb_multi<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
+        cudaFuncSetAttribute(gett_absorb_multi<KS, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 75 * 1024);
         attr_set = true;
     }
     const int Np = plan.aux[1];
     const size_t smem = (size_t)ops.T * (2 * Np) * (4 * KS + 4) * sizeof(double) + (size_t)(2 * KS + Np) * sizeof(long long);
-    unsigned gx = (unsigned)std::min<long long>((long long)plan.gx, ((plan.d.Msz + 7) / 8 + 7) / 8);
-    gett_absorb_multi<KS><<<gx, 256, smem, ctx->stream>>>(plan.d, ops, C, Np);
+    unsigned gx = (unsigned)std::min<long long>((long long)plan.gx / 2 * 3, ((plan.d.Msz + 7) / 8 + 7) / 8);
+    gett_absorb_multi<KS, NT><<<gx, 256, smem, ctx->stream>>>(plan.d, ops, C, Np);
     TNE_LAUNCH_CHECK(ctx);
     return TNE_OK;
 }
@@ -812,7 +808,7 @@ int gett_fast_plan(tne_ctx* ctx, ContractPlan* plan) {
         while (2 * ks < d.Ksz) ks <<= 1;
         // n-tiles are processed NTU = 4 / MTW at a time: pad N so that the tile count is a multiple of NTU
         // (zero columns of B', never stored) unless that would more than double the math
-        const int ntu = 4;   // MTW = 1
+        const int ntu = ks >= 8 ? 4 : 1;   // n-tiles per pass = 4 / MTW (MTW = 1 for the dense steps, 4 for K <= 8)
         int Np = (int)((d.Nsz + 3) / 4 * 4);
         Np = (Np + 4 * ntu - 1) / (4 * ntu) * (4 * ntu);
         sort_legs_by(d.N, 1);  // B is staged in shared memory: order the N legs by the OUTPUT stride
@@ -910,17 +906,14 @@ int gett_fast_plan(tne_ctx* ctx, ContractPlan* plan) {
 }
 
 bool gett_multi_capable(const ContractPlan& plan) {
-    return plan.kernel == KERNEL_ABSORB && plan.aux[1] <= 32;
+    // instantiated shapes: (K <= 32, N <= 16) and (K <= 16, N <= 32) -- the two dense steps of the sweep
+    return plan.kernel == KERNEL_ABSORB && ((plan.aux[0] == 16 && plan.aux[1] == 16) || (plan.aux[0] == 8 && plan.aux[1] == 32));
 }
 
 int gett_fast_run_multi(tne_ctx* ctx, const ContractPlan& plan, const AbsorbMulti& ops, cplx* C) {
-    switch (plan.aux[0]) {
-        case 2: return launch_absorb_multi<2>(ctx, plan, ops, C);
-        case 4: return launch_absorb_multi<4>(ctx, plan, ops, C);
-        case 8: return launch_absorb_multi<8>(ctx, plan, ops, C);
-        case 16: return launch_absorb_multi<16>(ctx, plan, ops, C);
-    }
-    return tne_fail(ctx, TNE_ERR_UNSUPPORTED, "absorb (multi) kernel: bad k-step count %d", plan.aux[0]);
+    if (plan.aux[0] == 16 && plan.aux[1] == 16) return launch_absorb_multi<16, 4>(ctx, plan, ops, C);
+    if (plan.aux[0] == 8 && plan.aux[1] == 32) return launch_absorb_multi<8, 8>(ctx, plan, ops, C);
+    return tne_fail(ctx, TNE_ERR_UNSUPPORTED, "absorb (multi) kernel: shape (%d k-steps, %d columns) not instantiated", plan.aux[0], plan.aux[1]);
 }
 
 int gett_fast_run(tne_ctx* ctx, const ContractPlan& plan, const cplx* A, const cplx* B, cplx* C) {
@@ -935,8 +928,8 @@ int gett_fast_run(tne_ctx* ctx, const ContractPlan& plan, const cplx* A, const c
     }
     if (plan.kernel == KERNEL_ABSORB) {
         switch (plan.aux[0]) {   // 3 CTAs of 8 warps per SM, one 8-row m-tile per warp iteration
-            case 2: return launch_absorb<2, 1, 3>(ctx, plan, A, B, C);
-            case 4: return launch_absorb<4, 1, 3>(ctx, plan, A, B, C);
+            case 2: return launch_absorb<2, 4, 3>(ctx, plan, A, B, C);   // bandwidth-only steps: 32 rows per warp iteration
+            case 4: return launch_absorb<4, 4, 3>(ctx, plan, A, B, C);
             case 8: return launch_absorb<8, 1, 3>(ctx, plan, A, B, C);
             case 16: return launch_absorb<16, 1, 3>(ctx, plan, A, B, C);
         }

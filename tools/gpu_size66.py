@@ -20,7 +20,7 @@ print("build", time.time() - t0, flush=True)
 def timed(name, f):
     if os.environ.get("TNE_PROFILE") and "again" in name:
         ctx.set_option("profile", 1); ctx.profile_collect(); f()
-        for k, v in ctx.profile_collect().items():
+        for k, v in sorted(ctx.profile_collect(fine=True).items()):
             if v["launches"]: print("   ", k, v["launches"], "launches %.1f ms  %.2f TFLOP/s  %.2f TB/s" % (v["ms"], v["flops"] / v["ms"] / 1e9, v["bytes"] / v["ms"] / 1e9))
         ctx.set_option("profile", 0)
     ctx.sync(); t0 = time.time(); r = f(); t1 = time.time(); ctx.sync(); t2 = time.time()
