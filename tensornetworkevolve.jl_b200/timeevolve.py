@@ -29,6 +29,18 @@ def normalized_overlap(peps, v1, v2):  # src/timeevolve.jl:6-12
 
 
 def apply_smatrix(peps, v1, v2, x):  # src/timeevolve.jl:15-52
+    """Metric-vector product ``sx = d/dv1 Re(conj(x) . dy/dv2)`` of ``y = Re<psi^(v1)|psi^(v2)>``.
+
+    The reference differentiates the taped backward pass a second time (reverse over reverse).  With fused
+    trees the same quantity is evaluated by an explicit tree-level algorithm: ``Re(conj(x) . dy/dv2)`` is the
+    directional derivative of ``y`` along ``x`` in ``v2``; because the PEPS is multilinear in its tensors that
+    derivative is ``z(v1) = Re<psi^(v1)|phi>`` with the fixed ket
+    ``phi = (sum_s psi2[s -> x_s] - c psi2) / n2``, ``c = Re<psi2|sum_s psi2[s -> x_s]> / n2^2``, i.e. a sum of
+    one-site replacement terms -- exactly what ``tne_expect_terms`` contracts in one device programme
+    (shared sub-contractions, checkpointed reverse pass).  ``sx`` is then the ordinary first-order gradient
+    of ``z``.  Works at sizes where the reference's tape cannot exist (6x6, D=4)."""
+    if es.FUSED_TREES and peps.kind == "simple":
+        return _apply_smatrix_fused(peps, v1, v2, x)
     fused = es.FUSED_TREES
     es.FUSED_TREES = False
     try:
@@ -51,6 +63,27 @@ def apply_smatrix(peps, v1, v2, x):  # src/timeevolve.jl:15-52
         return ad.getgrad(storage, v1)
     finally:
         es.FUSED_TREES = fused
+
+
+def _apply_smatrix_fused(peps, v1, v2, x):
+    ad.requires_grad_(v1, True)
+    nt = len(peps.alltensors())
+    p2 = P.load_variables(peps, v2.data if isinstance(v2, DiffTensor) else v2)          # plain device tensors
+    xs = P.load_variables(peps, x.data if isinstance(x, DiffTensor) else x).alltensors()
+    code = peps.code_inner_product
+    ket = [P._dev(t) for t in p2.alltensors()]
+    n2sq = es.contract_tree_device(code, ket + ket, [1] * nt + [0] * nt).item()       # <psi2|psi2>
+    n2 = float(np.sqrt(abs(n2sq)))
+    site_terms = [(1.0 + 0j, [(nt + s, P._dev(xs[s]))]) for s in range(nt)]
+    dval, _ = es.expect_terms_device(code, ket + ket, [1] * nt + [0] * nt, site_terms)  # <psi2|dpsi2>
+    c = float(np.real(dval.item())) / (n2 * n2)
+    terms = [(1.0 / n2, {s + 1: P._dev(xs[s])}) for s in range(nt)] + [(-c / n2, {})]
+
+    def z_of(v):
+        pl = P.load_variables(peps, v)
+        pl = P.mul(pl, _inv(P.norm(pl)))
+        return _real(P._expect_fused(terms, pl, p2, (0, 1)))
+    return ad.gradient(z_of, v1)[0]
 
 
 def iloss2(h, peps, variables, shard=(0, 1)):  # src/timeevolve.jl:55-60

@@ -138,6 +138,36 @@ def test_apply_smatrix(tne):  # test/timeevolve.jl:50-67
     assert rel(got, ref) < 1e-9
 
 
+def test_apply_smatrix_tree_level_vs_taped_and_oracle(tne):
+    """The explicit tree-level metric-vector product (fused trees) equals the reference's reverse-over-reverse
+    (op-by-op tape, einsum.FUSED_TREES = False) and the oracle, also for v1 != v2 and on a grid with segments."""
+    rng = np.random.default_rng(4)
+    g = OG.test_graph()
+    op1, op2 = oracle_peps(g, 2, 11, Dmax=4), oracle_peps(g, 2, 12, Dmax=4)
+    dp1 = device_peps_like(tne, op1, g, 2, Dmax=4)
+    v1, v2 = OP.variables(op1), OP.variables(op2)
+    x = crand(rng, v1.size) / np.sqrt(2)
+    ref = OTE.apply_smatrix(op1, OAD.DiffTensor(v1.copy()), OAD.DiffTensor(v2.copy()), OAD.DiffTensor(x, requires_grad=False)).data
+    got = tne.apply_smatrix(dp1, tne.DiffTensor(v1.copy()), tne.DiffTensor(v2.copy()), tne.DiffTensor(x, requires_grad=False)).to_numpy()
+    assert rel(got, ref) < 1e-9
+    tne.einsum.FUSED_TREES = False
+    try:
+        taped = tne.apply_smatrix(dp1, tne.DiffTensor(v1.copy()), tne.DiffTensor(v2.copy()), tne.DiffTensor(x, requires_grad=False)).to_numpy()
+    finally:
+        tne.einsum.FUSED_TREES = True
+    assert rel(got, taped) < 1e-9
+    L, D = 3, 2
+    gg = OG.grid([L, L])
+    order, segs = tne.sweep_plan(tne.grid([L, L]), L)
+    op = oracle_peps(gg, D, seed_for(L, D), optimizer=order)
+    dp = device_peps_like(tne, op, gg, D, optimizer=order, segments=segs)
+    v = OP.variables(op)
+    x = crand(rng, v.size) / np.sqrt(2)
+    ref = OTE.apply_smatrix(op, OAD.DiffTensor(v.copy()), OAD.DiffTensor(v.copy()), OAD.DiffTensor(x, requires_grad=False)).data
+    got = tne.apply_smatrix(dp, tne.DiffTensor(v.copy()), tne.DiffTensor(v.copy()), tne.DiffTensor(x, requires_grad=False)).to_numpy()
+    assert rel(got, ref) < 1e-9
+
+
 def test_normalized_overlap_gradient_zero(tne):  # test/timeevolve.jl:37-48
     g = OG.test_graph()
     op1 = oracle_peps(g, 2, 11, Dmax=4)

@@ -35,6 +35,12 @@ if "normgrad" in what:
     gfun = lambda: TA.gradient(lambda x: T.norm(T.load_variables(p, x)), T.DiffTensor(T.variables(p)))[0]
     gn = timed("norm gradient", gfun); print(np.abs(gn.to_numpy()).max())
     gn = timed("norm gradient again", gfun)
+if "smatrix" in what:
+    v = T.variables(p).to_numpy()
+    xx = (rng.standard_normal(v.size) + 1j * rng.standard_normal(v.size)) / np.sqrt(2)
+    sfun = lambda: T.apply_smatrix(p, T.DiffTensor(v.copy()), T.DiffTensor(v.copy()), T.DiffTensor(xx, requires_grad=False))
+    sx = timed("apply_smatrix", sfun); print(np.abs(sx.to_numpy()).max())
+    sx = timed("apply_smatrix again", sfun)
 if "expect" in what:
     e = timed("expect", lambda: T.expect(h, p, p)); print(e.to_numpy())
 if "grad" in what:
