@@ -289,7 +289,8 @@ def run_gpu(args):
     }
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "traffic_r01.json")))
-        roof["traffic"] = tr.get(dom)
+        roof["traffic"] = (tr.get(dom) or {}).get("dram_bytes_read_plus_write_per_launch")
+        roof["traffic_note"] = tr.get(dom)
     except Exception:
         pass
 
@@ -299,6 +300,26 @@ def run_gpu(args):
     ems, _, _ = timed(step_e2e, args.steps)
     e2e_value = args.steps / (ems / 1e3)
 
+    # secondary measurements of the same path (not part of the metric): the metric-vector product of the TDVP
+    # step (src/timeevolve.jl:15-52) on the same PEPS and one TEBD sweep of an 8x8, D=4 PEPS (BASELINE configs 3, 4)
+    extras = {}
+    if world == 1 and not args.no_extras:
+        v = T.variables(p).to_numpy()
+        xr = np.random.default_rng(seed_for(L, D) + 1)
+        xx = (xr.standard_normal(v.size) + 1j * xr.standard_normal(v.size)) / np.sqrt(2.0)
+        sfun = lambda: T.apply_smatrix(p, T.DiffTensor(v.copy()), T.DiffTensor(v.copy()), T.DiffTensor(xx, requires_grad=False))
+        sfun()
+        sms, _, sx = timed(sfun, 1)
+        extras["apply_smatrix"] = {"ms": sms, "max_abs": float(np.abs(sx.to_numpy()).max()),
+                                   "note": "S.x of the same %dx%d D=%d PEPS, tree-level algorithm (one tne_expect_terms + reverse pass)" % (L, L, D)}
+        Lt = 8
+        gt = T.grid([Lt, Lt])
+        pt = T.rand_simplepeps(gt, 4, np.random.default_rng(seed_for(Lt, 4)))
+        sweep = lambda: T.rydberg_tebd_sweep_(pt, gt, C_, DELTA_, OMEGA_, 0.03)
+        sweep()
+        tms, tl, _ = timed(sweep, 1)
+        extras["tebd_sweep_8x8_D4"] = {"ms": tms, "bonds": gt.ne(), "bonds_per_s": gt.ne() / (tms * 1e-3), "wavefronts": len(T.tebd.wavefronts(gt.edges())),
+                                       "note": "one rydberg_tebd_sweep!: 112 bond gates, QR-reduced Jacobi SVD truncation to D=4, latency-bound"}
     if rank == 0:
         cpu, _ = cpu_sample(L, D, budget_s=args.cpu_seconds) if world == 1 and not args.no_cpu else (None, None)
         line = {
@@ -322,6 +343,7 @@ def run_gpu(args):
             "gpu_launches": launches,
             "clocks": clk,
             "check": {"energy_re": energy.real, "force_max_abs": fmax},
+            "extras": extras,
         }
         print(json.dumps(line))
     if dist is not None:
@@ -339,6 +361,7 @@ def main():
     ap.add_argument("--D", type=int, default=4)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
