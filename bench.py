@@ -192,6 +192,8 @@ def run_gpu(args):
     ctx = T.context()
     if os.environ.get("TNE_VARIANT"):
         ctx.set_option("absorb_tma", int(os.environ["TNE_VARIANT"]))
+    if os.environ.get("TNE_NO_PDL"):
+        ctx.set_option("no_pdl", 1)
     if world > 1:
         T.array.init_comm(ctx, dist, rank, world)
     L, D = args.L, args.D

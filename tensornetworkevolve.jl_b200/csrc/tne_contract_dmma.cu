@@ -28,6 +28,23 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                  : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
+// Programmatic dependent launch: the next absorb kernel may become resident while this one drains; it builds its
+// shared-memory tables and B' (which never depend on the previous absorb kernel: small operands are leaves or are
+// produced by non-triggering kernels) and then waits for full completion of its predecessors before touching A or C.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st, bool pdl, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 enum { KERNEL_ABSORB = 1, KERNEL_REDUCE = 2, KERNEL_ABSORB_TMA = 3, KERNEL_REDUCE_TMA = 4 };
 
 // ---------------------------------------------------------------------------------------
@@ -140,7 +157,11 @@ __device__ __forceinline__ void absorb_compute(const AbsorbTile<KS, MTW>& t, con
     }
 }
 
-template <int KS, int MTW, int MINB>
+// ROWS: A's rows are contiguous (its fastest leg is the fastest M leg) and K is small.  A lane-per-fragment load
+// would touch four far-apart 128-byte lines per instruction (measured 3.4 TB/s for 8 read planes, tools/mem_pattern2.cu);
+// instead every instruction reads 32 consecutive rows of ONE k-plane (512 contiguous bytes, 5.3 TB/s) into a
+// warp-private shared-memory slab from which the DMMA fragments of the four 8-row tiles are gathered.
+template <int KS, int MTW, int MINB, bool ROWS>
 __global__ void __launch_bounds__(256, MINB) gett_absorb(const __grid_constant__ GettDesc d, const cplx* __restrict__ A,
                                                          const cplx* __restrict__ B, cplx* __restrict__ C, int Np) {
     constexpr int KP = 2 * KS;            // padded complex K
@@ -149,7 +170,9 @@ __global__ void __launch_bounds__(256, MINB) gett_absorb(const __grid_constant__
     double* Bs = reinterpret_cast<double*>(smem_raw);                       // [2 Np][STRIDE]
     long long* offAk = reinterpret_cast<long long*>(Bs + 2 * Np * STRIDE);   // [KP]
     long long* offCn = offAk + KP;                                          // [Np]
+    cplx* slab = reinterpret_cast<cplx*>(offCn + Np + (Np & 1)) + (threadIdx.x >> 5) * (KP * 34);   // ROWS: [KP][32 + 2] per warp
     const int tid = threadIdx.x;
+    pdl_trigger();
     for (int k = tid; k < KP; k += blockDim.x) {
         long long a = -1, b = 0;
         if (k < d.Ksz) decomp2(d.K, k, a, b);
@@ -181,6 +204,7 @@ __global__ void __launch_bounds__(256, MINB) gett_absorb(const __grid_constant__
         r1[jre] = bi; r1[jim] = sA * br;
     }
     __syncthreads();
+    pdl_wait();
 
     const int lane = tid & 31;
     const int lrow = lane >> 2, lcol = lane & 3;
@@ -199,7 +223,37 @@ __global__ void __launch_bounds__(256, MINB) gett_absorb(const __grid_constant__
         for (long long c = g; c < nchunks; c += nwarps) {
             const long long wlast = min(ntiles, (c + 1) * CH);
             for (long long w = c * CH; w < wlast; ++w) {
-                absorb_load(t0, d, A, offAk, w, lrow, lcol, rc);
+                if (ROWS) {   // MTW == 4: the tile is 32 consecutive rows inside M leg 0 (the host guarantees size0 % 32 == 0)
+                    long long oA0, oC0;
+                    RowCache r0 = rc[0];
+                    row_offsets(d, r0, w * 32, oA0, oC0);
+                    const bool okrow = w * 32 + lane < d.Msz;
+#pragma unroll
+                    for (int k = 0; k < KP; ++k) {
+                        const long long ofk = offAk[k];
+                        cplx v = make_double2(0.0, 0.0);
+                        if (okrow && ofk >= 0) v = __ldcs(A + oA0 + lane + ofk);
+                        slab[k * 34 + lane] = v;
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int mt = 0; mt < MTW; ++mt) {
+                        const long long row = w * 32 + (mt << 3) + lrow;
+                        long long oA;
+                        t0.ok[mt] = row < d.Msz;
+                        t0.oC[mt] = 0;
+                        if (t0.ok[mt]) row_offsets(d, rc[mt], row, oA, t0.oC[mt]);
+#pragma unroll
+                        for (int q = 0; q < KS / 2; ++q) {
+                            const cplx v = slab[(4 * q + lcol) * 34 + (mt << 3) + lrow];
+                            t0.a[mt][2 * q] = v.x;
+                            t0.a[mt][2 * q + 1] = v.y;
+                        }
+                    }
+                    __syncwarp();
+                } else {
+                    absorb_load(t0, d, A, offAk, w, lrow, lcol, rc);
+                }
                 absorb_compute(t0, d, C, Bs, offCn, NT, lrow, lcol);
             }
         }
@@ -222,6 +276,7 @@ __global__ void __launch_bounds__(256, 3) gett_absorb_multi(const __grid_constan
     long long* offAk = reinterpret_cast<long long*>(Bs + ops.T * 2 * Np * STRIDE);       // [KP]
     long long* offCn = offAk + KP;                                                      // [Np]
     const int tid = threadIdx.x;
+    pdl_trigger();
     for (int k = tid; k < KP; k += blockDim.x) {
         long long a = -1, b = 0;
         if (k < d.Ksz) decomp2(d.K, k, a, b);
@@ -253,6 +308,7 @@ __global__ void __launch_bounds__(256, 3) gett_absorb_multi(const __grid_constan
         r1[jre] = bi; r1[jim] = sA * br;
     }
     __syncthreads();
+    pdl_wait();
 
     const int lane = tid & 31;
     const int lrow = lane >> 2, lcol = lane & 3;
@@ -735,15 +791,15 @@ void sort_legs_by(LegSet& L, int which) {  // insertion sort of the legs by stri
         }
 }
 
-template <int KS, int MTW, int MINB>
+template <int KS, int MTW, int MINB, bool ROWS>
 int launch_absorb(tne_ctx* ctx, const ContractPlan& plan, const cplx* A, const cplx* B, cplx* C) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(gett_absorb<KS, MTW, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        cudaFuncSetAttribute(gett_absorb<KS, MTW, MINB, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
         attr_set = true;
     }
     unsigned gx = (unsigned)std::min<long long>((long long)plan.gx / 2 * MINB, ((plan.d.Msz + 8 * MTW - 1) / (8 * MTW) + 7) / 8);
-    gett_absorb<KS, MTW, MINB><<<gx, plan.threads, plan.smem, ctx->stream>>>(plan.d, A, B, C, plan.aux[1]);
+    TNE_CUDA(ctx, launch_pdl(gett_absorb<KS, MTW, MINB, ROWS>, gx, (unsigned)plan.threads, plan.smem + (ROWS ? (size_t)8 * (2 * KS) * 34 * sizeof(cplx) + 16 : 0), ctx->stream, !ctx->opt_no_pdl, plan.d, A, B, C, plan.aux[1]));
     TNE_LAUNCH_CHECK(ctx);
     return TNE_OK;
 }
@@ -758,7 +814,7 @@ int launch_absorb_multi(tne_ctx* ctx, const ContractPlan& plan, const AbsorbMult
     const int Np = plan.aux[1];
     const size_t smem = (size_t)ops.T * (2 * Np) * (4 * KS + 4) * sizeof(double) + (size_t)(2 * KS + Np) * sizeof(long long);
     unsigned gx = (unsigned)std::min<long long>((long long)plan.gx / 2 * 3, ((plan.d.Msz + 7) / 8 + 7) / 8);
-    gett_absorb_multi<KS, NT><<<gx, 256, smem, ctx->stream>>>(plan.d, ops, C, Np);
+    TNE_CUDA(ctx, launch_pdl(gett_absorb_multi<KS, NT>, gx, 256u, smem, ctx->stream, !ctx->opt_no_pdl, plan.d, ops, C, Np));
     TNE_LAUNCH_CHECK(ctx);
     return TNE_OK;
 }
@@ -815,9 +871,10 @@ int gett_fast_plan(tne_ctx* ctx, ContractPlan* plan) {
         plan->kernel = KERNEL_ABSORB;
         plan->aux[0] = ks;
         plan->aux[1] = Np;
+        plan->aux[3] = (ks <= 4 && d.M.n >= 1 && d.M.s0[0] == 1 && d.M.size[0] % 32 == 0 && !ctx->opt_no_rows) ? 1 : 0;   // ROWS load path
         plan->threads = 256;
         // TMA-staged variant when a tile of R rows is made of long contiguous runs of A (see gett_absorb_tma)
-        if (ctx->opt_absorb_tma && d.M.n >= 1) {
+        if ((ctx->opt_absorb_tma == 1 || (ctx->opt_absorb_tma == 2 && ks <= 4)) && d.M.n >= 1) {
             const int mtw = ks >= 16 ? 1 : (ks >= 8 ? 2 : 4);
             const int R = 8 * mtw * TMA_CONSUMERS;
             LegSet Ks = d.K;
@@ -928,10 +985,10 @@ int gett_fast_run(tne_ctx* ctx, const ContractPlan& plan, const cplx* A, const c
     }
     if (plan.kernel == KERNEL_ABSORB) {
         switch (plan.aux[0]) {   // 3 CTAs of 8 warps per SM, one 8-row m-tile per warp iteration
-            case 2: return launch_absorb<2, 4, 3>(ctx, plan, A, B, C);   // bandwidth-only steps: 32 rows per warp iteration
-            case 4: return launch_absorb<4, 4, 3>(ctx, plan, A, B, C);
-            case 8: return launch_absorb<8, 1, 3>(ctx, plan, A, B, C);
-            case 16: return launch_absorb<16, 1, 3>(ctx, plan, A, B, C);
+            case 2: return plan.aux[3] ? launch_absorb<2, 4, 3, true>(ctx, plan, A, B, C) : launch_absorb<2, 4, 3, false>(ctx, plan, A, B, C);
+            case 4: return plan.aux[3] ? launch_absorb<4, 4, 3, true>(ctx, plan, A, B, C) : launch_absorb<4, 4, 3, false>(ctx, plan, A, B, C);
+            case 8: return launch_absorb<8, 1, 3, false>(ctx, plan, A, B, C);
+            case 16: return launch_absorb<16, 1, 3, false>(ctx, plan, A, B, C);
         }
         return tne_fail(ctx, TNE_ERR_UNSUPPORTED, "absorb kernel: bad k-step count %d", plan.aux[0]);
     }

@@ -51,6 +51,8 @@ struct tne_ctx {
     int64_t opt_debug = 0;
     int64_t opt_profile = 0;
     int64_t opt_pad = 0;                   // stride padding (elements) of workspace tensors, see tne_tree.cu
+    int64_t opt_no_rows = 1;               // 0: row-contiguous staged loads in the small-K absorb kernel (measured slower: off)
+    int64_t opt_no_pdl = 1;                // 1: no programmatic dependent launch of the absorb kernels
     int64_t opt_no_fuse = 0;               // 1: one launch per contribution (no gett_absorb_multi)
     int64_t opt_absorb_tma = 0;            // 1: TMA-staged absorb kernel where applicable (default: register-fed)
     int64_t opt_no_reduce_tma = 0;         // 1: register-fed reduce kernel instead of the TMA-staged one

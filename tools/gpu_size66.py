@@ -9,6 +9,7 @@ from helpers import seed_for
 L = int(sys.argv[1]); D = int(sys.argv[2]); what = sys.argv[3:] or ["norm", "expect", "grad"]
 ctx = T.context(); ctx.set_option("debug", int(os.environ.get("TNE_DEBUG", "2")))
 if os.environ.get("TNE_VARIANT"): ctx.set_option("absorb_tma", int(os.environ["TNE_VARIANT"]))
+if os.environ.get("TNE_NO_PDL"): ctx.set_option("no_pdl", 1)
 if os.environ.get("TNE_PAD"): ctx.set_option("pad", int(os.environ["TNE_PAD"]))
 g = T.grid([L, L])
 rng = np.random.default_rng(seed_for(L, D))
