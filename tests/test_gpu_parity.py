@@ -253,3 +253,16 @@ def test_segmented_program_matches_oracle(tne, L, D):
     gref = OAD.gradient(lambda x: OP.norm(OP.load_variables(op, x)), OAD.DiffTensor(OP.variables(op)))[0].data
     gdev = tne.gradient(lambda x: tne.norm(tne.load_variables(dp, x)), tne.DiffTensor(tne.variables(dp)))[0].to_numpy()
     assert rel(gdev, gref) < TOL
+
+
+def test_sr_step_matches_oracle(tne):
+    """src/timeevolve.jl:1-4 as intended (GMRES on S x = -i f with the device metric-vector product): the same
+    Krylov iteration on the host around device matvecs gives the oracle's update."""
+    g = OG.test_graph()
+    h = OT.rydberg_hamiltonian(g, 10.0, 0.2, 0.3)
+    hd = to_device_hamiltonian(tne, h)
+    op1 = oracle_peps(g, 2, 11, Dmax=4)
+    dp1 = device_peps_like(tne, op1, g, 2, Dmax=4)
+    ref = OTE.sr_step(op1, h, tol=1e-8, maxiter=3)
+    got = tne.sr_step(dp1, hd, tol=1e-8, maxiter=3)
+    assert rel(tne.variables(got).to_numpy(), OP.variables(ref)) < 1e-6
