@@ -222,20 +222,32 @@ def load_variables(peps, variables):
 
 
 # -- factories, src/peps.jl:244-280 -----------------------------------------------------
-def sweep_plan(g, L):
+def sweep_plan(g, L, nbonds=1):
     """Boundary-sweep contraction plan for an ``L x L`` ``grid`` PEPS (vertex ``v = x + (y-1) L``): the leaf
-    order ``bra_1, ket_1, bra_2, ...`` and one checkpointed segment per lattice column ``y``.  Column
-    ``y >= 2`` loops over the bond between the last sites of columns ``y-1`` and ``y``: it is open during
-    the whole column, so slicing it costs no flops and divides the column's tape by ``D^2``."""
+    order ``bra_1, ket_1, bra_2, ...`` and checkpointed segments with segment-local slices.
+
+    ``nbonds = 1``: one segment per lattice column ``y``; column ``y >= 2`` loops over the bond between the last
+    sites of columns ``y-1`` and ``y``: it is open during the whole column, so slicing it costs no flops and divides
+    the column's tape by ``D^2``.
+    ``nbonds = k > 1`` (bigger lattices): the bonds of the last ``k`` rows between columns ``y-1`` and ``y`` are all
+    looped over (``D^(2k)`` slices).  The bond of row ``r`` closes at site ``(r, y)``, so the column is cut into
+    ``k`` segments -- rows ``1..L-k+1``, then one row each -- and every segment only loops over the bonds that are
+    still open in it: again no flops are repeated."""
     n = g.nv()
     order = []
     for i in range(n):
         order += [i, n + i]
     emap = {e: n + 1 + k for k, e in enumerate(g.edges())}
+    site = lambda x, y: x + (y - 1) * L
+    hbond = lambda x, y: emap[(site(x, y - 1), site(x, y))]    # bond between (x, y-1) and (x, y)
+    k = max(1, min(int(nbonds), L - 1))
     segments = [(1, [])]
     for y in range(2, L + 1):
-        a, b = L + (y - 2) * L, L + (y - 1) * L
-        segments.append((1 + (y - 1) * L, [emap[(a, b)]]))
+        # segment 0 of the column: rows 1 .. L-k+1, all k bonds open; then one segment per remaining row
+        first_rows = [1] + list(range(L - k + 2, L + 1))
+        for j, x0 in enumerate(first_rows):
+            open_rows = range(L - k + 1 + j, L + 1) if j > 0 else range(L - k + 1, L + 1)
+            segments.append((site(x0, y), [hbond(x, y) for x in open_rows]))
     return order, segments
 
 

@@ -206,6 +206,24 @@ def test_grid_norm_energy_gradient(tne, L, D):
     assert ctx.launch_count() > 0
 
 
+@pytest.mark.parametrize("nbonds", [2, 3])
+def test_multi_bond_segments(tne, nbonds):
+    """sweep_plan with several sliced bonds per column (row-wise sub-segments; checkpoints that carry sliced labels
+    are written and read through strided views): same numbers as the oracle."""
+    L, D = 4, 3
+    g = OG.grid([L, L])
+    order, segs = tne.sweep_plan(tne.grid([L, L]), L, nbonds)
+    assert len(segs) == 1 + (L - 1) * nbonds
+    op = oracle_peps(g, D, seed_for(L, D), optimizer=order)
+    dp = device_peps_like(tne, op, g, D, optimizer=order, segments=segs)
+    h = OT.rydberg_hamiltonian(g, 10.0, 0.2, 0.3)
+    hd = to_device_hamiltonian(tne, h)
+    assert rel(tne.norm(dp).to_numpy(), OP.norm(op)) < TOL
+    y, f = tne.energy_and_gradient(dp, hd)
+    assert rel(f.to_numpy(), OTE.fvec(op, h).data) < TOL
+    assert rel(y.to_numpy(), OTE.iloss2(h, op, OP.variables(op))) < TOL
+
+
 def test_linearity_and_scaling_properties(tne):
     """size-independent properties: <a p|p> = conj(a) <p|p>; norm scales; gradient of a real loss is
     orthogonal to the radial direction after normalisation (iloss2 is scale-invariant in x)."""

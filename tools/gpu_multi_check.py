@@ -33,10 +33,18 @@ dq = device_peps_like(T, op, g, D, optimizer=order, segments=segs)
 y2, f2 = T.energy_and_gradient(dq, hd, shard=(rank, world))
 T.array.allreduce_sum(ctx, [y2.data, f2.data])
 e2 = max(rel(f2.to_numpy(), fref), rel(y2.to_numpy(), yref))
-t = torch.tensor([e1, n1, e2], device="cuda", dtype=torch.float64)
+# 3. BASELINE configs[4] at the validation size: 10x10, D=2 exact norm, bond slices dealt to the ranks
+L2, D2 = 10, 2
+g2 = OG.grid([L2, L2])
+order2, segs2 = T.sweep_plan(T.grid([L2, L2]), L2)
+op2 = oracle_peps(g2, D2, seed_for(L2, D2), optimizer=order2)
+dp2 = device_peps_like(T, op2, g2, D2, optimizer=order2, segments=segs2)
+dp2.code_inner_product.seg_shard = True
+n10 = rel(T.norm(dp2).to_numpy(), OP.norm(op2))
+t = torch.tensor([e1, n1, e2, n10], device="cuda", dtype=torch.float64)
 dist.all_reduce(t, op=dist.ReduceOp.MAX)
 if rank == 0:
-    print("MULTI-GPU CHECK world %d: slice-sharded energy+grad rel err %.2e, norm %.2e; term-sharded %.2e" % (world, *t.tolist()))
+    print("MULTI-GPU CHECK world %d: slice-sharded energy+grad rel err %.2e, norm %.2e; term-sharded %.2e; 10x10 D=2 sliced norm %.2e" % (world, *t.tolist()))
     assert t.max().item() < 1e-10
 dist.barrier()
 dist.destroy_process_group()

@@ -14,7 +14,7 @@ if os.environ.get("TNE_PAD"): ctx.set_option("pad", int(os.environ["TNE_PAD"]))
 g = T.grid([L, L])
 rng = np.random.default_rng(seed_for(L, D))
 t0 = time.time()
-order, segs = T.sweep_plan(g, L)
+order, segs = T.sweep_plan(g, L, int(os.environ.get('TNE_NBONDS', '1')))
 p = T.rand_simplepeps(g, D, rng, optimizer=order, segments=segs)
 h = T.rydberg_hamiltonian(g, 10.0, 0.2, 0.3)
 print("build", time.time() - t0, flush=True)
