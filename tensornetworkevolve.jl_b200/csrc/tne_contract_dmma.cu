@@ -649,8 +649,8 @@ struct RedGeom {
     long long nchunks;        // total chunks = (Ksz / size0) * (size0 / KC)
     int chunks_per_row;       // size0 / KC
 };
-constexpr int RED_KC = 32;
-constexpr int RED_STAGES = 4;
+constexpr int RED_KC = 64;       // reduction indices per stage (bulk copies of 1-4 KiB)
+constexpr int RED_STAGES = 2;
 constexpr int RED_CONSUMERS = 4;
 
 template <int MT, int NT>
@@ -737,24 +737,30 @@ gett_reduce_tma(const __grid_constant__ GettDesc d, const cplx* __restrict__ A, 
         mbar_wait(smem_u32(&bars[stage]), phase);
         const unsigned char* sb = stages + stage * g.stage_bytes;
         constexpr int KSTEPS = RED_KC / 2 / RED_CONSUMERS;   // k-steps (2 complex k) per warp and chunk
-        double af[KSTEPS][MT], bf[KSTEPS][NT];
+        constexpr int KB = 4;                                // ... fetched and multiplied KB at a time
 #pragma unroll
-        for (int j = 0; j < KSTEPS; ++j) {
-            const int kl = 2 * (warp + RED_CONSUMERS * j) + kin;
+        for (int j0 = 0; j0 < KSTEPS; j0 += KB) {
+            double af[KB][MT], bf[KB][NT];
 #pragma unroll
-            for (int mt = 0; mt < MT; ++mt) af[j][mt] = okm[mt] ? *reinterpret_cast<const double*>(sb + aoff[mt] + kl * g.fA * 16) : 0.0;
+            for (int j = 0; j < KB; ++j) {
+                const int kl = 2 * (warp + RED_CONSUMERS * (j0 + j)) + kin;
 #pragma unroll
-            for (int nt = 0; nt < NT; ++nt) bf[j][nt] = okn[nt] ? ysgn * *reinterpret_cast<const double*>(sb + boff[nt] + kl * g.fB * 16) : 0.0;
+                for (int mt = 0; mt < MT; ++mt) af[j][mt] = okm[mt] ? *reinterpret_cast<const double*>(sb + aoff[mt] + kl * g.fA * 16) : 0.0;
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) bf[j][nt] = okn[nt] ? ysgn * *reinterpret_cast<const double*>(sb + boff[nt] + kl * g.fB * 16) : 0.0;
+            }
+            if (j0 + KB >= KSTEPS) {   // last batch: the fragments are in registers, the slot can be refilled
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&bars[RED_STAGES + stage]));
+            }
+#pragma unroll
+            for (int j = 0; j < KB; ++j)
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], af[j][mt], bf[j][nt]);
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&bars[RED_STAGES + stage]));
         if (++stage == RED_STAGES) { stage = 0; phase ^= 1; }
-#pragma unroll
-        for (int j = 0; j < KSTEPS; ++j)
-#pragma unroll
-            for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-                for (int nt = 0; nt < NT; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], af[j][mt], bf[j][nt]);
     }
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt)
