@@ -649,12 +649,12 @@ struct RedGeom {
     long long nchunks;        // total chunks = (Ksz / size0) * (size0 / KC)
     int chunks_per_row;       // size0 / KC
 };
-constexpr int RED_KC = 64;       // reduction indices per stage (bulk copies of 1-4 KiB)
+constexpr int RED_KC = 128;      // reduction indices per stage (bulk copies of 1-4 KiB)
 constexpr int RED_STAGES = 2;
 constexpr int RED_CONSUMERS = 4;
 
 template <int MT, int NT>
-__global__ void __launch_bounds__(32 * (RED_CONSUMERS + 1), 2)
+__global__ void __launch_bounds__(32 * (RED_CONSUMERS + 1), 1)
 gett_reduce_tma(const __grid_constant__ GettDesc d, const cplx* __restrict__ A, const cplx* __restrict__ B,
                 cplx* __restrict__ C, const RedGeom g) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -843,7 +843,7 @@ template <int MT, int NT>
 int launch_reduce_tma(tne_ctx* ctx, const ContractPlan& plan, const RedGeom& g, const cplx* A, const cplx* B, cplx* C) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(gett_reduce_tma<MT, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
+        cudaFuncSetAttribute(gett_reduce_tma<MT, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         attr_set = true;
     }
     gett_reduce_tma<MT, NT><<<plan.gx, 32 * (RED_CONSUMERS + 1), plan.smem, ctx->stream>>>(plan.d, A, B, C, g);
@@ -934,14 +934,14 @@ int gett_fast_plan(tne_ctx* ctx, ContractPlan* plan) {
                 g.chunks_per_row = size0 / RED_KC;
                 g.nchunks = (d.Ksz / size0) * g.chunks_per_row;
                 size_t smem = (size_t)RED_STAGES * g.stage_bytes + 64 * sizeof(long long) + (size_t)MT * NT * 64 * sizeof(double) + 2 * RED_STAGES * sizeof(long long) + 128;
-                if (smem <= 110 * 1024) {
+                if (smem <= 220 * 1024) {
                     plan->kernel = KERNEL_REDUCE_TMA;
                     plan->aux[0] = MT * 16 + NT;
                     static_assert(sizeof(RedGeom) <= sizeof(plan->blob), "RedGeom must fit the plan blob");
                     memcpy(plan->blob, &g, sizeof(g));
                     plan->smem = smem;
                     plan->threads = 32 * (RED_CONSUMERS + 1);
-                    plan->gx = (unsigned)std::max<long long>(1, std::min<long long>(g.nchunks, (long long)ctx->sm_count * 2));
+                    plan->gx = (unsigned)std::max<long long>(1, std::min<long long>(g.nchunks, (long long)ctx->sm_count * (smem > 110 * 1024 ? 1 : 2)));
                     plan->zero_first = !d.accumulate;
                     return TNE_OK;
                 }
