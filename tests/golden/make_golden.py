@@ -23,11 +23,11 @@ def make(L, D):
     v = OP.variables(p)
     out = dict(variables=v, norm=np.asarray(OP.norm(p)), inner=np.asarray(OP.inner_product(p, p)),
                energy=np.asarray(OP.expect(h, p, p)), iloss2=np.asarray(OTE.iloss2(h, p, v)), fvec=OTE.fvec(p, h).data)
+    x = np.random.default_rng(seed_for(L, D) + 1)
+    x = (x.standard_normal(v.size) + 1j * x.standard_normal(v.size)) / np.sqrt(2.0)
+    out["x"] = x
+    out["smatrix_x"] = OTE.apply_smatrix(p, AD.DiffTensor(v.copy()), AD.DiffTensor(v.copy()), AD.DiffTensor(x, requires_grad=False)).data
     if L <= 3:
-        x = np.random.default_rng(seed_for(L, D) + 1)
-        x = (x.standard_normal(v.size) + 1j * x.standard_normal(v.size)) / np.sqrt(2.0)
-        out["x"] = x
-        out["smatrix_x"] = OTE.apply_smatrix(p, AD.DiffTensor(v.copy()), AD.DiffTensor(v.copy()), AD.DiffTensor(x, requires_grad=False)).data
         q = oracle_peps(g, D, seed_for(L, D))
         OT.rydberg_tebd_(q, g, t=0.3, C=10.0, delta=0.2, omega=0.3, nstep=10)
         out["tebd_state"] = OP.vec(q)

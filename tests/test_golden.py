@@ -43,10 +43,10 @@ def test_device_reproduces_golden(tne, L, D):
     assert rel(tne.expect(hd, dp, dp).to_numpy(), gold["energy"]) < 1e-10
     y, f = tne.energy_and_gradient(dp, hd)
     assert rel(y.to_numpy(), gold["iloss2"]) < 1e-10 and rel(f.to_numpy(), gold["fvec"]) < 1e-10
+    v = gold["variables"]
+    sx = tne.apply_smatrix(dp, tne.DiffTensor(v.copy()), tne.DiffTensor(v.copy()), tne.DiffTensor(gold["x"], requires_grad=False))
+    assert rel(sx.to_numpy(), gold["smatrix_x"]) < 1e-9             # tree-level metric-vector product vs reverse-over-reverse
     if L == 3:
-        v = gold["variables"]
-        sx = tne.apply_smatrix(dp, tne.DiffTensor(v.copy()), tne.DiffTensor(v.copy()), tne.DiffTensor(gold["x"], requires_grad=False))
-        assert rel(sx.to_numpy(), gold["smatrix_x"]) < 1e-9
         dq = device_peps_like(tne, oracle_peps(g, D, seed_for(L, D)), g, D)
         tne.rydberg_tebd_(dq, tne.grid([L, L]), t=0.3, C=10.0, delta=0.2, omega=0.3, nstep=10)
         assert rel(tne.vec(dq), gold["tebd_state"]) < 1e-8          # gauge-free comparison of the evolved state
