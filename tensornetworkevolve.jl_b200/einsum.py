@@ -257,7 +257,11 @@ def optimize_greedy(ixs, iy, size_dict):
 
 
 def optimize_sequence(ixs, iy, order):
-    """Left-deep tree absorbing tensors in ``order`` (boundary sweep)."""
+    """Left-deep tree absorbing the items of ``order`` one after the other (boundary sweep).  An item is a
+    leaf index or a tuple ``(i, j)``: the two leaves are contracted with each other first and the pair is
+    absorbed in one step (worth it where it costs no extra flops, e.g. a PEPS site without down legs whose
+    left legs are sliced: the boundary is then read and written once for the site instead of twice).
+    The root gets ``first_node_of_item[k]``: the post-order index of the first node created for item k."""
     ixs = [list(ix) for ix in ixs]
     count = {}
     for ix in ixs:
@@ -265,10 +269,26 @@ def optimize_sequence(ixs, iy, order):
             count[l] = count.get(l, 0) + 1
     for l in iy:
         count[l] = count.get(l, 0) + 1
-    cur = NestedEinsum(tensorindex=order[0])
-    lab = list(ixs[order[0]])
+
+    def item_node(t):
+        if isinstance(t, (tuple, list)):
+            i, j = t
+            la, lb = ixs[i], ixs[j]
+            for l in set(la):
+                count[l] -= 1
+            for l in set(lb):
+                count[l] -= 1
+            out = [l for l in dict.fromkeys(la + lb) if count[l] > 0]
+            for l in set(out):
+                count[l] += 1
+            return NestedEinsum([NestedEinsum(tensorindex=i), NestedEinsum(tensorindex=j)], EinCode([la, lb], out)), out, 1
+        return NestedEinsum(tensorindex=t), list(ixs[t]), 0
+    cur, lab, n_nodes = item_node(order[0])
+    first_node = [0]
     for step, t in enumerate(order[1:]):
-        lb = ixs[t]
+        first_node.append(n_nodes)
+        nd, lb, extra = item_node(t)
+        n_nodes += extra
         for l in set(lab):
             count[l] -= 1
         for l in set(lb):
@@ -278,8 +298,10 @@ def optimize_sequence(ixs, iy, order):
             out = list(iy)
         for l in set(out):
             count[l] += 1
-        cur = NestedEinsum([cur, NestedEinsum(tensorindex=t)], EinCode([lab, lb], out))
+        cur = NestedEinsum([cur, nd], EinCode([lab, lb], out))
+        n_nodes += 1
         lab = out
+    cur.first_node_of_item = first_node
     return cur
 
 
@@ -315,8 +337,8 @@ def optimize_code(ixs, iy, size_dict, optimizer="greedy", nslices=0, slicing=Non
     if isinstance(optimizer, (list, tuple)):
         nested = optimize_sequence(ixs, iy, list(optimizer))
         if segments:
-            # left-deep chain: post-order node j absorbs order[j + 1]
-            nested.segments = [(max(0, pos - 1), list(ls)) for pos, ls in segments]
+            # a segment starts at the first node created for order[pos] (post-order numbering)
+            nested.segments = [(nested.first_node_of_item[pos], list(ls)) for pos, ls in segments]
     else:
         nested = optimize_greedy(ixs, iy, size_dict)
     if slicing:

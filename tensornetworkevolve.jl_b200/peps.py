@@ -104,7 +104,12 @@ def _optimized_code(alllabels, physical_labels, virtual_labels, max_ind, nflavor
     ixs = [list(l) for l in alllabels] + [[rep.get(x, x) for x in l] for l in alllabels]
     segs = None
     if segments and isinstance(optimizer, (list, tuple)):
-        segs = [(list(optimizer).index(site - 1), [l for b in bonds for l in (b, rep[b])]) for site, bonds in segments]
+        def pos_of(site):   # position of the item that holds the site's bra tensor (a leaf index or a (bra, ket) pair)
+            for k, it in enumerate(optimizer):
+                if it == site - 1 or (isinstance(it, (tuple, list)) and it[0] == site - 1):
+                    return k
+            raise ValueError("site %d is not in the contraction order" % site)
+        segs = [(pos_of(site), [l for b in bonds for l in (b, rep[b])]) for site, bonds in segments]
     code_ip = es.optimize_code(ixs, [], size_dict, optimizer, nslices, segments=segs)
     return code_st, code_ip
 
@@ -222,13 +227,15 @@ def load_variables(peps, variables):
 
 
 # -- factories, src/peps.jl:244-280 -----------------------------------------------------
-def sweep_plan(g, L, nbonds=1):
+def sweep_plan(g, L, nbonds=1, pair_last_row=True):
     """Boundary-sweep contraction plan for an ``L x L`` ``grid`` PEPS (vertex ``v = x + (y-1) L``): the leaf
     order ``bra_1, ket_1, bra_2, ...`` and checkpointed segments with segment-local slices.
 
     ``nbonds = 1``: one segment per lattice column ``y``; column ``y >= 2`` loops over the bond between the last
     sites of columns ``y-1`` and ``y``: it is open during the whole column, so slicing it costs no flops and divides
     the column's tape by ``D^2``.
+    ``pair_last_row``: the bra and ket tensor of the last site of every sliced column are contracted with each other
+    first (a 16 x 16 matrix at D = 4) and absorbed in one step.
     ``nbonds = k > 1`` (bigger lattices): the bonds of the last ``k`` rows between columns ``y-1`` and ``y`` are all
     looped over (``D^(2k)`` slices).  The bond of row ``r`` closes at site ``(r, y)``, so the column is cut into
     ``k`` segments -- rows ``1..L-k+1``, then one row each -- and every segment only loops over the bonds that are
@@ -236,7 +243,13 @@ def sweep_plan(g, L, nbonds=1):
     n = g.nv()
     order = []
     for i in range(n):
-        order += [i, n + i]
+        x, y = i % L + 1, i // L + 1
+        # last-row sites of the sliced columns have neither down legs nor (inside a slice) left legs: contracting
+        # bra with ket first costs no extra flops and the boundary is read / written once instead of twice
+        if pair_last_row and x == L and y >= 2 and L > 1:
+            order.append((i, n + i))
+        else:
+            order += [i, n + i]
     emap = {e: n + 1 + k for k, e in enumerate(g.edges())}
     site = lambda x, y: x + (y - 1) * L
     hbond = lambda x, y: emap[(site(x, y - 1), site(x, y))]    # bond between (x, y-1) and (x, y)

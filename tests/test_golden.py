@@ -34,7 +34,7 @@ def test_device_reproduces_golden(tne, L, D):
     gold = load(L, D)
     g = OG.grid([L, L])
     order, segs = tne.sweep_plan(tne.grid([L, L]), L)
-    op = oracle_peps(g, D, seed_for(L, D), optimizer=order)
+    op = oracle_peps(g, D, seed_for(L, D), optimizer=sweep_order(L * L))
     dp = device_peps_like(tne, op, g, D, optimizer=order, segments=segs)
     hd = to_device_hamiltonian(tne, OT.rydberg_hamiltonian(g, 10.0, 0.2, 0.3))
     assert rel(tne.variables(dp).to_numpy(), gold["variables"]) == 0.0

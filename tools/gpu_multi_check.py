@@ -19,7 +19,7 @@ T.array.init_comm(ctx, dist, rank, world)
 L, D = 4, 3
 g = OG.grid([L, L]); gd = T.grid([L, L])
 order, segs = T.sweep_plan(gd, L)
-op = oracle_peps(g, D, seed_for(L, D), optimizer=order)
+op = oracle_peps(g, D, seed_for(L, D), optimizer=sweep_order(L * L))
 h = OT.rydberg_hamiltonian(g, 10.0, 0.2, 0.3); hd = to_device_hamiltonian(T, h)
 fref = OTE.fvec(op, h).data; yref = OTE.iloss2(h, op, OP.variables(op))
 # 1. slice sharding inside the library
@@ -37,7 +37,7 @@ e2 = max(rel(f2.to_numpy(), fref), rel(y2.to_numpy(), yref))
 L2, D2 = 10, 2
 g2 = OG.grid([L2, L2])
 order2, segs2 = T.sweep_plan(T.grid([L2, L2]), L2)
-op2 = oracle_peps(g2, D2, seed_for(L2, D2), optimizer=order2)
+op2 = oracle_peps(g2, D2, seed_for(L2, D2), optimizer=sweep_order(L2 * L2))
 dp2 = device_peps_like(T, op2, g2, D2, optimizer=order2, segments=segs2)
 dp2.code_inner_product.seg_shard = True
 n10 = rel(T.norm(dp2).to_numpy(), OP.norm(op2))
