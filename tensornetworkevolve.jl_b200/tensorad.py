@@ -221,20 +221,21 @@ def _tree_rule(nested, slicing, xs):
         return _run_nested_unfused(nested, xs)
     code = _es.SlicedEinsum(slicing, nested) if slicing else nested
     datas = [x.data for x in xs]
-    y = _es.contract_tree_device(code, datas)
-    cache = {}
+    leaves = [j for j in range(len(xs)) if requires_grad(xs[j])]
+    if not leaves or len(nested.eins.iy) != 0:   # nothing to differentiate / non-scalar output (forward only)
+        y = _es.contract_tree_device(code, datas)
+
+        def no_back(dy):
+            raise NotImplementedError("fused trees differentiate scalar outputs only (set einsum.FUSED_TREES = False)")
+        return difftensor(y, "nested_einsum", *[(xs[i], no_back) for i in range(len(xs))])
+    # value and the pullbacks for a unit cotangent in ONE device program (forward + reverse sweep, no second
+    # forward pass); the program is linear in the cotangent, so back(dy) only rescales the stored gradients
+    y, grads = _es.expect_terms_device(code, datas, None, [], leaves, 1.0 + 0j)
+    gmap = dict(zip(leaves, grads))
 
     def mk(i):
         def back(dy):
-            key = id(dy)
-            if key not in cache:
-                cache.clear()
-                leaves = [j for j in range(len(xs)) if requires_grad(xs[j])]
-                _, grads = _es.expect_terms_device(code, datas, None, [], leaves, 1.0 + 0j)
-                cache[key] = (dy, dict(zip(leaves, grads)))
-            g = cache[key][1][i]
-            # the program is linear in the cotangent: G(dy) = dy * G(1) (conj(dy) for nothing: holomorphic)
-            out = g.bmul(dy.data.to_complex())
+            out = gmap[i].bmul(dy.data.to_complex())   # holomorphic: G(dy) = dy * G(1)
             out = out.real() if xs[i].data.is_real else out
             return DiffTensor(out, requires_grad=False)
         return back

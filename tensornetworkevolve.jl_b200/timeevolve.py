@@ -114,7 +114,14 @@ def energy_and_gradient(peps, h, shard=(0, 1)):
     proportional to the rank's partial energy, so partial results add up exactly)."""
     variables = DiffTensor(P.variables(peps))
     ad.GLOBAL_TAPE.instructs.clear()
-    y = iloss2(h, wrap_difftensor(peps, False), variables, shard=shard)
+    # iloss2 (src/timeevolve.jl:55-60) evaluated at x = variables(peps): ||psi(x)|| and ||psi|| are the same number, so
+    # the norm network is contracted once (value + pullbacks in one device program) and its value is reused, detached,
+    # for the constant side
+    pl = P.load_variables(wrap_difftensor(peps, False), variables)
+    nl = P.norm(pl)
+    pl = P.mul(pl, _inv(nl))
+    pr = P.mul(wrap_difftensor(peps, False), _inv(DiffTensor(nl.data, requires_grad=False)))
+    y = _real(P.expect(h, P.conj(pl), pr, shard=shard))
     storage = ad.init_storage_(y)
     ad.back_(ad.GLOBAL_TAPE, storage)
     g = ad.getgrad(storage, variables)
