@@ -61,9 +61,9 @@ int tne_last_program_stats(tne_ctx* ctx, double* stats6);
  * TMA-staged absorb kernel where it applies), "no_reduce_tma" (1: register-fed reduce kernel), "pad" */
 int tne_set_option(tne_ctx* ctx, const char* key, int64_t value);
 /* Per kernel class c = 8 * kernel + bucket (kernel: 0 generic FMA, 1 DMMA absorb, 2 DMMA reduce, 3 DMMA absorb with
- * TMA-staged operand, 4 DMMA reduce with TMA-staged operands; bucket: log2 of the padded K / 2 of absorb kernels): out[4c .. 4c+3] = launches, summed
+ * TMA-staged operand, 4 DMMA reduce with TMA-staged operands, 5 fused two-stage site absorption; bucket: log2 of the padded K / 2 of absorb kernels): out[4c .. 4c+3] = launches, summed
  * device milliseconds, algorithmic real flops, algorithmic bytes since the last collect.  Synchronises. */
-#define TNE_PROFILE_CLASSES 40   /* class = 8 * kernel + log2(k-steps) bucket (0 for kernels without one) */
+#define TNE_PROFILE_CLASSES 48   /* class = 8 * kernel + log2(k-steps) bucket (0 for kernels without one) */
 int tne_profile_collect(tne_ctx* ctx, double* out);
 
 /* ---- device tensors: Array{ComplexF64,N} as used at src/peps.jl:41,132 ---------------- */

@@ -53,6 +53,7 @@ struct tne_ctx {
     int64_t opt_pad = 0;                   // stride padding (elements) of workspace tensors, see tne_tree.cu
     int64_t opt_no_rows = 1;               // 0: row-contiguous staged loads in the small-K absorb kernel (measured slower: off)
     int64_t opt_no_pdl = 1;                // 1: no programmatic dependent launch of the absorb kernels
+    int64_t opt_no_site2 = 0;              // 1: never fuse the bra and ket step of a site into one kernel
     int64_t opt_no_fuse = 0;               // 1: one launch per contribution (no gett_absorb_multi)
     int64_t opt_absorb_tma = 0;            // 1: TMA-staged absorb kernel where applicable (default: register-fed)
     int64_t opt_no_reduce_tma = 0;         // 1: register-fed reduce kernel instead of the TMA-staged one
@@ -138,6 +139,18 @@ struct ContractPlan {
     unsigned char blob[64] = {0};   // kernel-specific geometry (tne_contract_dmma.cu)
     double flops = 0, bytes = 0;
 };
+// fused absorption of one PEPS site, C = (A . B1) . B2 in one kernel (tne_site2.cu)
+struct Legs4 { int n; int size[4]; long long s0[4], s1[4]; };
+struct Site2Desc {
+    GettDesc g;                    // g.M (s0: A stride, s1: C stride), g.Msz: the boundary rows
+    Legs4 K1, X, P, N1, N2;        // (A, B1), (A, B2), (B1, B2), (B1, C), (B2, C) strides
+    int conjA, conjB1, conjB2, accumulate;
+    double a1re, a1im, a2re, a2im;
+};
+bool site2_plan(tne_ctx* ctx, const TensorRef& A, const TensorRef& B1, const TensorRef& B2, const TensorRef& C, bool accumulate,
+                double a1re, double a1im, double a2re, double a2im, Site2Desc* out);
+int site2_run(tne_ctx* ctx, const Site2Desc& d, const cplx* A, const cplx* B1, const cplx* B2, cplx* C);
+
 // several contributions into one output through the DMMA absorb kernel (see gett_absorb_multi)
 #define TNE_MULTI_MAX 3
 struct AbsorbMulti {

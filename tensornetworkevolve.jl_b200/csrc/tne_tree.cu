@@ -402,6 +402,10 @@ struct PhaseOp {
     // further contributions into the same output, fused into one launch (gett_absorb_multi)
     struct Extra { int a, b; ContractPlan plan; };
     std::vector<Extra> extra;
+    // fused site absorption C = (A . B1) . B2 (tne_site2.cu): this op is the second step, s2 holds both
+    std::shared_ptr<Site2Desc> s2;
+    int s2_a = -1, s2_b1 = -1, s2_b2 = -1;
+    double s2_flops = 0, s2_bytes = 0;
 };
 
 struct Phase {
@@ -587,6 +591,48 @@ struct Exec {
             }
             ph.ops.push_back(std::move(po));
         }
+        // fuse the two steps of a site, T = A . B1 then C = T . B2, when T has no other reader in this phase
+        if (!ctx->opt_no_site2) {
+            std::map<int, int> reads, producer;
+            for (int i = 0; i < (int)ph.ops.size(); ++i) {
+                const Op& op = ph.ops[i].op;
+                if (op.a >= 0) reads[op.a]++;
+                if (op.b >= 0) reads[op.b]++;
+                producer[op.out] = producer.count(op.out) ? -2 : i;   // -2: several writers
+            }
+            for (int j = 0; j < (int)ph.ops.size(); ++j) {
+                PhaseOp& pj = ph.ops[j];
+                if (pj.op.kind != OP_CONTRACT || pj.first_slice_only || pj.plan.empty) continue;
+                for (int side = 0; side < 2; ++side) {
+                    const int T = side == 0 ? pj.op.a : pj.op.b, b2 = side == 0 ? pj.op.b : pj.op.a;
+                    const bool conjT = side == 0 ? pj.op.conj_a : pj.op.conj_b, conjB2 = side == 0 ? pj.op.conj_b : pj.op.conj_a;
+                    if (T < 0 || b2 < 0 || conjT) continue;
+                    auto itp = producer.find(T);
+                    if (itp == producer.end() || itp->second < 0 || itp->second >= j || reads[T] != 1) continue;
+                    PhaseOp& pi = ph.ops[itp->second];
+                    if (pi.dead || pi.op.kind != OP_CONTRACT || pi.op.acc || pi.first_slice_only || pi.plan.empty || pi.s2) continue;
+                    if (!ph.views.at(T).temp) continue;
+                    // the big operand of the first step is A
+                    const bool a_big = ph.views.at(pi.op.a).nelem >= ph.views.at(pi.op.b).nelem;
+                    const int vA = a_big ? pi.op.a : pi.op.b, vB1 = a_big ? pi.op.b : pi.op.a;
+                    TensorRef rA = ref_of(ph, vA, a_big ? pi.op.conj_a : pi.op.conj_b);
+                    TensorRef rB1 = ref_of(ph, vB1, a_big ? pi.op.conj_b : pi.op.conj_a);
+                    TensorRef rB2 = ref_of(ph, b2, conjB2);
+                    TensorRef rC = ref_of(ph, pj.op.out, false);
+                    Site2Desc sd;
+                    if (!site2_plan(ctx, rA, rB1, rB2, rC, pj.op.acc, pi.op.are, pi.op.aim, pj.op.are, pj.op.aim, &sd)) continue;
+                    pj.s2 = std::make_shared<Site2Desc>(sd);
+                    pj.s2_a = vA; pj.s2_b1 = vB1; pj.s2_b2 = b2;
+                    pj.s2_flops = pi.plan.flops + pj.plan.flops;
+                    pj.s2_bytes = 16.0 * ((double)ph.views.at(vA).nelem + (double)ph.views.at(pj.op.out).nelem);
+                    pi.dead = true;
+                    break;
+                }
+            }
+            std::vector<PhaseOp> kept;
+            for (auto& po : ph.ops) if (!po.dead) kept.push_back(std::move(po));
+            ph.ops.swap(kept);
+        }
         // fuse consecutive writers of one output that run the absorb kernel with identical geometry: the group
         // moves to the position of its last member (all inputs are ready there), C is written once
         if (!ctx->opt_no_fuse) {
@@ -597,6 +643,7 @@ struct Exec {
                 int ins[2] = {po.op.a, po.op.b};
                 for (int v : ins) if (v >= 0) open.erase(v);   // a reader closes the group of the value it reads
                 auto it = open.find(out);
+                if (po.s2) { merged.push_back(po); open.erase(out); continue; }
                 if (it != open.end() && po.op.kind == OP_CONTRACT && !po.plan.empty) {
                     PhaseOp& g = merged[it->second];
                     if ((int)g.extra.size() + 1 < TNE_MULTI_MAX && g.first_slice_only == po.first_slice_only &&
@@ -624,6 +671,7 @@ struct Exec {
             const Op& op = ph.ops[i].op;
             std::vector<int> ids = {op.out, op.a, op.b};
             for (auto& ex : ph.ops[i].extra) { ids.push_back(ex.a); ids.push_back(ex.b); }
+            if (ph.ops[i].s2) { ids = {op.out, ph.ops[i].s2_a, ph.ops[i].s2_b1, ph.ops[i].s2_b2}; }
             for (int v : ids) {
                 if (v < 0 || !ph.views.at(v).temp) continue;
                 auto it = slot.find(v);
@@ -719,6 +767,22 @@ struct Exec {
         return TNE_OK;
     }
 
+    int site2_launch(const PhaseOp& po, const cplx* A, const cplx* B1, const cplx* B2, cplx* C) {
+        if (!ctx->opt_profile) return site2_run(ctx, *po.s2, A, B1, B2, C);
+        tne_ctx::ProfRec r;
+        cudaEvent_t* ev[2] = {&r.e0, &r.e1};
+        for (auto e : ev) {
+            if (!ctx->event_pool.empty()) { *e = ctx->event_pool.back(); ctx->event_pool.pop_back(); }
+            else TNE_CUDA(ctx, cudaEventCreate(e));
+        }
+        r.cls = 8 * 5; r.flops = po.s2_flops; r.bytes = po.s2_bytes;
+        TNE_CUDA(ctx, cudaEventRecord(r.e0, ctx->stream));
+        int rc = site2_run(ctx, *po.s2, A, B1, B2, C);
+        TNE_CUDA(ctx, cudaEventRecord(r.e1, ctx->stream));
+        ctx->prof.push_back(r);
+        return rc;
+    }
+
     cplx* base_ptr(const Phase& ph, int v) const {
         const Val& val = P.vals[v];
         if (val.ext) return val.ext + val.slice_base;
@@ -750,6 +814,12 @@ struct Exec {
                     if (po.first_slice_only && it > 0) continue;
                     // replicated segment: every rank computes the same thing; only rank 0 may add to the outputs
                     if (world > 1 && !sharded && rank != 0 && P.vals[po.op.out].ext) continue;
+                    if (po.s2) {
+                        TNE_TRY(site2_launch(po, ptr_of(po.s2_a), ptr_of(po.s2_b1), ptr_of(po.s2_b2), ptr_of(po.op.out)));
+                        if (po.op.recompute) P.re_flops += po.s2_flops; else { P.flops += po.s2_flops; P.bytes += po.s2_bytes; }
+                        P.n_contract++;
+                        continue;
+                    }
                     if (po.extra.empty()) {
                         TNE_TRY(contract_run(ctx, po.plan, ptr_of(po.op.a), ptr_of(po.op.b), ptr_of(po.op.out)));
                     } else {

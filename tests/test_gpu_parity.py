@@ -284,3 +284,34 @@ def test_sr_step_matches_oracle(tne):
     ref = OTE.sr_step(op1, h, tol=1e-8, maxiter=3)
     got = tne.sr_step(dp1, hd, tol=1e-8, maxiter=3)
     assert rel(tne.variables(got).to_numpy(), OP.variables(ref)) < 1e-6
+
+
+def test_fused_site_absorption_d4(tne):
+    """D = 4 grid: the bra and ket step of a bulk site run as one two-stage DMMA kernel (tne_site2.cu).  Same numbers
+    as the step-by-step path (option no_site2) and as the oracle."""
+    ctx = tne.context()
+    L, D = 4, 4
+    g = OG.grid([L, L])
+    order, segs = tne.sweep_plan(tne.grid([L, L]), L)
+    op = oracle_peps(g, D, seed_for(L, D), optimizer=sweep_order(L * L))
+    h = OT.rydberg_hamiltonian(g, 10.0, 0.2, 0.3)
+    hd = to_device_hamiltonian(tne, h)
+    nref, eref = OP.norm(op), OP.expect(h, op, op)
+    for segments in (None, segs):
+        dp = device_peps_like(tne, op, g, D, optimizer=order, segments=segments)
+        ctx.set_option("profile", 1); ctx.profile_collect()
+        n1 = tne.norm(dp).to_numpy()
+        y1, f1 = tne.energy_and_gradient(dp, hd)
+        used = ctx.profile_collect(fine=True)
+        ctx.set_option("profile", 0)
+        ctx.set_option("no_site2", 1)
+        try:
+            n0 = tne.norm(dp).to_numpy()
+            y0, f0 = tne.energy_and_gradient(dp, hd)
+        finally:
+            ctx.set_option("no_site2", 0)
+        assert rel(n1, nref) < TOL and rel(n0, nref) < TOL
+        assert rel(tne.expect(hd, dp, dp).to_numpy(), eref) < TOL
+        assert rel(y1.to_numpy(), y0.to_numpy()) < TOL and rel(f1.to_numpy(), f0.to_numpy()) < TOL
+        if segments is None:
+            assert any(k[0] == "gett_site2" for k in used), used   # the fused kernel did run
