@@ -24,7 +24,7 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 constexpr int S2_K1 = 16, S2_X = 16, S2_P = 2, S2_N1 = 16, S2_N2 = 16, S2_TB = 8;
 constexpr int S2_STR1 = 2 * S2_K1 + 4;            // doubles per B1' row (2 K1 reals)
 constexpr int S2_STR2 = 2 * S2_X * S2_P + 4;      // doubles per B2' row (2 X P reals)
-constexpr int S2_TSTR = S2_X * S2_P + 2;          // complex per T row
+constexpr int S2_TSTR = S2_X * S2_P + 4;          // complex per T row (576 B: conflict-free 128-bit fragment reads)
 
 __device__ __forceinline__ long long legs4_off(const Legs4& L, int idx, int which) {
     long long o = 0;
@@ -88,31 +88,31 @@ __global__ void __launch_bounds__(256, 2) gett_site2(const __grid_constant__ Sit
     const int lrow = lane >> 2, lcol = lane & 3;
     const long long ntiles = d.g.Msz / S2_TB;
     long long outer_cached = -1, baseA = 0, baseC = 0;
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        // offsets of this lane's boundary row m'' = 8 tile + lrow
-        long long oA, oC;
-        {
-            const long long row = tile * S2_TB + lrow;
-            const int sh = d.g.M.shift[0];
-            long long i0, outer;
-            if (sh >= 0) { i0 = row & (long long)(d.g.M.size[0] - 1); outer = row >> sh; }
-            else { outer = row / d.g.M.size[0]; i0 = row - outer * d.g.M.size[0]; }
-            if (outer != outer_cached) {
-                outer_cached = outer;
-                long long a = 0, c = 0, idx = outer;
-                for (int i = 1; i < d.g.M.n; ++i) {
-                    long long q, r;
-                    const int s2 = d.g.M.shift[i];
-                    if (s2 >= 0) { r = idx & (long long)(d.g.M.size[i] - 1); q = idx >> s2; }
-                    else { q = idx / d.g.M.size[i]; r = idx - q * d.g.M.size[i]; }
-                    a += r * d.g.M.s0[i]; c += r * d.g.M.s1[i];
-                    idx = q;
-                }
-                baseA = a; baseC = c;
+    auto row_off = [&](long long tile, long long& oA, long long& oC) {   // offsets of this lane's boundary row m'' = 8 tile + lrow
+        const long long row = tile * S2_TB + lrow;
+        const int sh = d.g.M.shift[0];
+        long long i0, outer;
+        if (sh >= 0) { i0 = row & (long long)(d.g.M.size[0] - 1); outer = row >> sh; }
+        else { outer = row / d.g.M.size[0]; i0 = row - outer * d.g.M.size[0]; }
+        if (outer != outer_cached) {
+            outer_cached = outer;
+            long long a = 0, c = 0, idx = outer;
+            for (int i = 1; i < d.g.M.n; ++i) {
+                long long q, r;
+                const int s2 = d.g.M.shift[i];
+                if (s2 >= 0) { r = idx & (long long)(d.g.M.size[i] - 1); q = idx >> s2; }
+                else { q = idx / d.g.M.size[i]; r = idx - q * d.g.M.size[i]; }
+                a += r * d.g.M.s0[i]; c += r * d.g.M.s1[i];
+                idx = q;
             }
-            oA = baseA + i0 * d.g.M.s0[0];
-            oC = baseC + i0 * d.g.M.s1[0];
+            baseA = a; baseC = c;
         }
+        oA = baseA + i0 * d.g.M.s0[0];
+        oC = baseC + i0 * d.g.M.s1[0];
+    };
+    long long oA, oC;
+    if ((long long)blockIdx.x < ntiles) row_off(blockIdx.x, oA, oC);
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         // ---- stage 1: this warp takes x = 2 warp, 2 warp + 1; rows (x, m''), K1 = 16, columns (p, n1) = 32 ----
 #pragma unroll
         for (int xi = 0; xi < 2; ++xi) {
@@ -138,6 +138,15 @@ __global__ void __launch_bounds__(256, 2) gett_site2(const __grid_constant__ Sit
             }
         }
         __syncthreads();
+        const long long oCcur = oC;
+        if (tile + gridDim.x < ntiles) {   // pull the next tile's A rows into L2 while stage 2 runs
+            row_off(tile + gridDim.x, oA, oC);
+#pragma unroll
+            for (int xi = 0; xi < 2; ++xi)
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(A + oA + offA_x[2 * warp + xi] + offA_k1[4 * q + lcol]));
+        }
         // ---- stage 2: this warp takes n1 = 2 warp, 2 warp + 1; rows (n1, m''), K2 = (x, p) = 32, columns n2 = 16 ----
 #pragma unroll
         for (int ni = 0; ni < 2; ++ni) {
@@ -159,7 +168,7 @@ __global__ void __launch_bounds__(256, 2) gett_site2(const __grid_constant__ Sit
                 for (int nt = 0; nt < 4; ++nt) dmma884(c[nt][0], c[nt][1], a[ks], brow[nt * 8 * S2_STR2 + 4 * ks]);
 #pragma unroll
             for (int nt = 0; nt < 4; ++nt) {
-                cplx* p = C + oC + offC_n1[n1] + offC_n2[4 * nt + lcol];
+                cplx* p = C + oCcur + offC_n1[n1] + offC_n2[4 * nt + lcol];
                 cplx v = make_double2(c[nt][0], c[nt][1]);
                 if (d.accumulate) { cplx o = *p; v.x += o.x; v.y += o.y; }
                 __stcs(p, v);
