@@ -1,6 +1,7 @@
 // Context, device tensor pool and the elementwise kernels (K4 of SURVEY.md 2c):
 // the Base/broadcast methods src/TensorAD/rules.jl and src/peps.jl:283-295 call on tensors.
 #include <cstdarg>
+#include <cstdlib>
 #include <algorithm>
 #include <cmath>
 
@@ -38,6 +39,10 @@ static int pool_alloc(tne_ctx* ctx, int64_t bytes, void** out, int64_t* rounded)
     if (it != ctx->free_blocks.end()) {
         *out = it->second;
         ctx->free_blocks.erase(it);
+    } else if (ctx->plan_only) {
+        *out = calloc(1, (size_t)r);   // planner context: host placeholder, never dereferenced by a kernel
+        if (!*out) return tne_fail(ctx, TNE_ERR_OOM, "planner: host allocation failed");
+        ctx->reserved += r;
     } else {
         cudaError_t e = cudaMalloc(out, r);
         if (e != cudaSuccess) {
@@ -115,6 +120,7 @@ int buf_view(tne_ctx* ctx, const Buf& src, int64_t offset, const std::vector<int
 
 int ws_reserve(tne_ctx* ctx, int64_t bytes) {
     if (bytes <= ctx->ws_bytes) return TNE_OK;
+    if (ctx->plan_only) { ctx->ws_bytes = bytes; return TNE_OK; }
     if (ctx->ws) { cudaFree(ctx->ws); ctx->ws = nullptr; ctx->ws_bytes = 0; }
     const int64_t g = 64 << 20;
     int64_t r = (bytes + g - 1) / g * g;
@@ -146,6 +152,17 @@ extern "C" int tne_ctx_create(int device, tne_ctx** out) {
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess || n == 0) {
         cudaGetLastError();
+        const char* po = getenv("TNE_PLAN_ONLY");
+        if (po && po[0] == '1') {
+            // planner context for tools/plan_dump.py: builds and costs tree programs on a machine without a GPU.
+            // It computes NOTHING: every kernel launch is a no-op, tne_download and the tree entry points fail.
+            tne_ctx* ctx = new tne_ctx();
+            ctx->plan_only = true;
+            ctx->total_mem = 180LL << 30;
+            ctx->mem_limit = (int64_t)(0.85 * (double)ctx->total_mem);
+            *out = ctx;
+            return TNE_OK;
+        }
         return tne_fail(nullptr, TNE_ERR_CUDA, "no CUDA device: this engine has no CPU path");
     }
     if (device < 0 || device >= n) return tne_fail(nullptr, TNE_ERR_INVALID, "device %d out of range", device);
@@ -177,6 +194,12 @@ extern "C" int tne_ctx_create(int device, tne_ctx** out) {
 
 extern "C" int tne_ctx_destroy(tne_ctx* ctx) {
     if (!ctx) return TNE_OK;
+    if (ctx->plan_only) {   // host placeholders; leaked blocks of a debugging tool are not worth tracking
+        for (auto& kv : ctx->bufs) if (kv.second.block) kv.second.block->ctx = nullptr;
+        ctx->bufs.clear();
+        delete ctx;
+        return TNE_OK;
+    }
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (auto& kv : ctx->bufs) if (kv.second.block) kv.second.block->ctx = nullptr;  // freed below
@@ -290,6 +313,7 @@ extern "C" int tne_upload(tne_ctx* ctx, tne_buf h, const void* host) {
 extern "C" int tne_download(tne_ctx* ctx, tne_buf h, void* host) {
     Buf* b = buf_get(ctx, h);
     if (!b) return TNE_ERR_INVALID;
+    if (ctx->plan_only) return tne_fail(ctx, TNE_ERR_UNSUPPORTED, "planner context (TNE_PLAN_ONLY): nothing was computed, nothing to download");
     TNE_CUDA(ctx, cudaMemcpyAsync(host, b->ptr(), b->nelem * sizeof(cplx), cudaMemcpyDeviceToHost, ctx->stream));
     TNE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return TNE_OK;

@@ -64,6 +64,9 @@ struct tne_ctx {
     void* nccl = nullptr;                  // ncclComm_t
     void* nccl_lib = nullptr;
     int world = 1, rank = 0;
+    // planner context (TNE_PLAN_ONLY=1 and no device): programs are built, costed and dumped, nothing is ever
+    // computed -- tne_expect_terms / tne_contract_tree return TNE_ERR_UNSUPPORTED after planning (tools/plan_dump.py)
+    bool plan_only = false;
 };
 
 // ---- error helpers ---------------------------------------------------------------------
@@ -71,7 +74,8 @@ int tne_fail(tne_ctx* ctx, int code, const char* fmt, ...);
 #define TNE_CUDA(ctx, call)                                                                   \
     do {                                                                                      \
         cudaError_t e__ = (call);                                                             \
-        if (e__ != cudaSuccess)                                                               \
+        if (e__ != cudaSuccess && (ctx) && (ctx)->plan_only) cudaGetLastError();              \
+        else if (e__ != cudaSuccess)                                                          \
             return tne_fail(ctx, e__ == cudaErrorMemoryAllocation ? TNE_ERR_OOM : TNE_ERR_CUDA, \
                             "CUDA error '%s' at %s:%d", cudaGetErrorString(e__), __FILE__, __LINE__); \
     } while (0)

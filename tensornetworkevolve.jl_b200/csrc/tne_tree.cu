@@ -791,6 +791,35 @@ struct Exec {
         return reinterpret_cast<cplx*>(pv.temp ? ws + persist_bytes + pv.off : ws + val.offset);
     }
 
+    // one line per launch group of the final (fused) phases: what runs, how often, with which algorithmic cost
+    void dump_final() const {
+        for (size_t pi = 0; pi < phases.size(); ++pi) {
+            const Phase& ph = phases[pi];
+            for (auto& po : ph.ops) {
+                const GettDesc& d = po.plan.d;
+                double fl = po.plan.flops, by = po.plan.bytes;
+                const char* kind = po.plan.kernel == 0 ? "generic" : "dmma";
+                if (po.s2) { kind = "site2"; fl = po.s2_flops; by = po.s2_bytes; }
+                else if (!po.extra.empty()) {
+                    kind = "multi";
+                    for (auto& ex : po.extra) { fl += ex.plan.flops; by += ex.plan.bytes - 16.0 * (double)ex.plan.c_nelem; }
+                }
+                fprintf(stderr, "[tne-final] phase %zu seg %d %s nsl %lld first_only %d kind %s kernel %d re %d bwdop %d acc %d M %lld N %lld K %lld B %lld flops %.6e bytes %.6e out %d",
+                        pi, ph.seg, ph.backward ? "bwd" : "fwd", (long long)ph.nsl, (int)po.first_slice_only, kind, po.plan.kernel,
+                        (int)po.op.recompute, (int)po.op.backward, (int)po.op.acc, d.Msz, d.Nsz, d.Ksz, d.Bsz, fl, by, po.op.out);
+                auto pv = [&](const char* nm, int v) {
+                    if (v < 0) return;
+                    const PView& w = ph.views.at(v);
+                    fprintf(stderr, " %s %d:%lld:%s", nm, v, (long long)w.nelem, w.temp ? "t" : (P.vals[v].ext ? "x" : "c"));
+                };
+                if (po.s2) { pv("A", po.s2_a); pv("B1", po.s2_b1); pv("B2", po.s2_b2); }
+                else { pv("a", po.op.a); pv("b", po.op.b); for (auto& ex : po.extra) { pv("a", ex.a); pv("b", ex.b); } }
+                pv("o", po.op.out);
+                fprintf(stderr, "\n");
+            }
+        }
+    }
+
     bool seg_shard = false;   // deal segment-local slices to the ranks; all-reduce the checkpoints of sliced segments
 
     int run() {
@@ -926,6 +955,9 @@ extern "C" int tne_expect_terms(tne_ctx* ctx, const tne_tree* tree, const tne_bu
         int rc = E.build(tree, n_grad > 0);
         if (rc) return fail_cleanup(rc);
     }
+    if (ctx->opt_debug > 2 || ctx->plan_only) E.dump_final();
+    if (ctx->plan_only)
+        return fail_cleanup(tne_fail(ctx, TNE_ERR_UNSUPPORTED, "planner context (TNE_PLAN_ONLY): program built and dumped, nothing computed"));
     const int64_t budget = ctx->mem_limit - ctx->in_use;
     const int64_t peak = E.persist_bytes + E.temp_bytes;
     if (peak > budget)
