@@ -182,6 +182,28 @@ typedef struct {
 
 int tne_apply_onbond_batched(tne_ctx* ctx, int n_jobs, tne_bond_job* jobs);
 
+/* ---- one whole TEBD sweep: rydberg_tebd_sweep! (src/tebd.jl:15-23), i.e. apply_onbond! over edges(g) in order ------
+ * `sites` / `bonds` are tables of handles (vertex tensors in vertex order; Vidal bond vectors in virtual_labels order);
+ * gates refer to them by 0-based index and are given in the reference's sequential order.  The library levels them
+ * into wavefronts of site-disjoint gates (exactly commuting), runs one launch per wavefront with NO host
+ * synchronisation in between (the kept rank is assumed to reach its cap and verified once at the end; otherwise the
+ * sweep is redone with exact ranks) and overwrites the tables with the handles of the new tensors.  The old handles
+ * stay valid and owned by the caller.  `kept` and `trunc_err` are filled per gate (the @info of src/peps.jl:386). */
+typedef struct {
+    int32_t site_i, site_j;          /* 0-based indices into `sites` */
+    int32_t axis_i, axis_j;          /* 0-based position of the shared bond in the two site tensors */
+    int32_t bond;                    /* Vidal: index into `bonds` of the vector this gate rewrites; else ignored */
+    double gate[32];                 /* 4x4 complex, column-major, M[o_i + 2 o_j, i_i + 2 i_j] */
+    int32_t lambda_i[TNE_MAX_RANK];  /* Vidal: index into `bonds` per axis of site_i (-1: none; axis 0 ignored) */
+    int32_t lambda_j[TNE_MAX_RANK];
+    /* outputs */
+    int32_t kept;
+    double trunc_err;
+} tne_sweep_gate;
+
+int tne_tebd_sweep(tne_ctx* ctx, int n_sites, tne_buf* sites, int n_bonds, tne_buf* bonds, int n_gates,
+                   tne_sweep_gate* gates, int Dmax, double eps, int vidal);
+
 /* ---- multi-GPU: sum of partial energies / gradients (serial `sum` at src/peps.jl:470) ------
  * comm is created from an NCCL unique id broadcast by the host program. */
 int tne_nccl_unique_id(void* id128);

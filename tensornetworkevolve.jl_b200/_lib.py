@@ -62,6 +62,19 @@ class TneBondJob(C.Structure):
     ]
 
 
+class TneSweepGate(C.Structure):
+    _fields_ = [
+        ("site_i", C.c_int32), ("site_j", C.c_int32),
+        ("axis_i", C.c_int32), ("axis_j", C.c_int32),
+        ("bond", C.c_int32),
+        ("gate", C.c_double * 32),
+        ("lambda_i", C.c_int32 * MAX_RANK),
+        ("lambda_j", C.c_int32 * MAX_RANK),
+        ("kept", C.c_int32),
+        ("trunc_err", C.c_double),
+    ]
+
+
 # every symbol include/tne.h declares: name -> (restype, argtypes)
 _P = C.POINTER
 SYMBOLS = {
@@ -99,6 +112,8 @@ SYMBOLS = {
     "tne_svd_trunc": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_double, _P(C.c_int64), _P(C.c_int64),
                                 _P(C.c_int64), _P(C.c_int32), _P(C.c_double)]),
     "tne_apply_onbond_batched": (C.c_int, [C.c_void_p, C.c_int, _P(TneBondJob)]),
+    "tne_tebd_sweep": (C.c_int, [C.c_void_p, C.c_int, _P(C.c_int64), C.c_int, _P(C.c_int64), C.c_int, _P(TneSweepGate),
+                                 C.c_int, C.c_double, C.c_int]),
     "tne_nccl_unique_id": (C.c_int, [C.c_void_p]),
     "tne_comm_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "tne_allreduce_sum": (C.c_int, [C.c_void_p, C.c_int, _P(C.c_int64)]),

@@ -18,6 +18,7 @@ namespace {
 constexpr int BOND_THREADS = 256;
 constexpr int MAXI = 32;          // 2 * Ds: columns of a site matricisation (shared bond Ds <= 16)
 constexpr int MAXN = 2 * MAXI;    // rows / columns of the core theta
+constexpr int QS_MAX = 1024;      // elements of one site matricisation kept in shared memory (16 KiB per side)
 
 struct BondDev {
     const cplx* t[2];             // site tensors i, j
@@ -33,6 +34,8 @@ struct BondDev {
     cplx* Q[2];                   // O x I (column-major): the matricisation, orthonormalised in place
     cplx* UV[2];                  // (2 O) x Dcap column-major: reshape(U, (sl..., D)) and reshape(conj(V), (sr..., D))
     cplx* S;                      // Dcap singular values (imaginary part 0)
+    cplx* place[2];               // optional: the new site tensors themselves (bond leg = Dcap entries, site leg order);
+                                  // used by the speculative sweep, which assumes kept == Dcap (no placement launches)
     int Dcap;
     int* kept;
     double* trunc_err;
@@ -112,16 +115,21 @@ __global__ void __launch_bounds__(BOND_THREADS) bond_kernel(const BondDev* __res
     double* sval = red + 64;                              // [MAXN]
     int* perm = reinterpret_cast<int*>(sval + MAXN);      // [MAXN]
     cplx* coef = reinterpret_cast<cplx*>(perm + MAXN);    // [MAXI]
+    // the two matricisations live in shared memory when they fit (O * 2 Ds <= QS_MAX per side: every D <= 4 site of a
+    // square lattice), else in the global scratch J.Q: the Gram-Schmidt loop is a chain of short dependent steps and
+    // runs at memory latency
+    cplx* Qs = coef + MAXI;                               // [2][QS_MAX]
     __shared__ SiteMap map[2];
     __shared__ int s_flag;
     if (tid < 2) map[tid].init(J.dims[tid], J.rank[tid], J.axis[tid]);
     __syncthreads();
+    const long long t_start = clock64();
 
     // ---- 1. matricise (Vidal: absorb sqrt(lambda) on every virtual leg) and orthogonalise: T = Q R ----
     for (int side = 0; side < 2; ++side) {
         const SiteMap& M = map[side];
         const int O = M.O, Ds = M.Ds, I = 2 * Ds;
-        cplx* Q = J.Q[side];
+        cplx* Q = O * I <= QS_MAX ? Qs + side * QS_MAX : J.Q[side];
         for (int e = tid; e < O * I; e += BOND_THREADS) {
             const int o = e % O, c = e / O;       // column c = p + 2 s
             const int p = c & 1, s = c >> 1;
@@ -177,6 +185,7 @@ __global__ void __launch_bounds__(BOND_THREADS) bond_kernel(const BondDev* __res
         }
     }
 
+    const long long t_qr = clock64();
     // ---- 2. the core: theta[(a,p'),(b,q')] = sum_{p,q,s} G[p'+2q', p+2q] R_i[a,(p,s)] R_j[b,(q,s)] ----
     const int Ds = map[0].Ds;
     const int Ii = 2 * Ds, Ij = 2 * Ds;
@@ -204,14 +213,17 @@ __global__ void __launch_bounds__(BOND_THREADS) bond_kernel(const BondDev* __res
     }
     __syncthreads();
 
+    int n_sweeps = 0;
+    const long long t_core = clock64();
     // ---- 3. one-sided Jacobi: rotate column pairs of W (and V) until all pairs are orthogonal ----
     {
         const int lane = tid & 31, warp = tid >> 5, nwarp = BOND_THREADS / 32;
         const int npad = nj + (nj & 1);
         for (int sweep = 0; sweep < 40; ++sweep) {
-            if (tid == 0) s_flag = 0;
-            __syncthreads();
+            n_sweeps = sweep + 1;
+            int again = 0;      // block-uniform: some pair of this sweep was still off by more than the sweep tolerance
             for (int step = 0; step < npad - 1; ++step) {
+                int need = 0;
                 // round-robin tournament: npad / 2 disjoint pairs per step
                 for (int pr = warp; pr < npad / 2; pr += nwarp) {
                     int x = pr == 0 ? npad - 1 : (step + pr) % (npad - 1);
@@ -236,14 +248,21 @@ __global__ void __launch_bounds__(BOND_THREADS) bond_kernel(const BondDev* __res
                         ga.x += __shfl_xor_sync(0xffffffffu, ga.x, sh);
                         ga.y += __shfl_xor_sync(0xffffffffu, ga.y, sh);
                     }
-                    const double g = hypot(ga.x, ga.y);
-                    if (g <= 1e-15 * sqrt(al * be) || g == 0.0) continue;
-                    if (lane == 0) s_flag = 1;
+                    // the scalar part of a rotation is a chain of dependent FP64 divisions and square roots: it sets the
+                    // latency of a Jacobi step, so it is written with reciprocal square roots (2 rsqrt, 1 sqrt, 1 division)
+                    const double g2 = ga.x * ga.x + ga.y * ga.y, ab = al * be;
+                    if (!(g2 > 1e-30 * ab) || ab == 0.0) continue;   // also skips a pair with an exactly vanishing (or underflowing) column
+                    // every pair above rounding level is still rotated, but only a pair that is off by more than 1e-12
+                    // asks for another sweep: Jacobi converges quadratically, so the rotations of this sweep already
+                    // bring such pairs to ~1e-24
+                    if (g2 > 1e-24 * ab) need = 1;
+                    const double ginv = rsqrt(g2);
                     // unitary rotation [c, s e^{i phi}; -s e^{-i phi}, c] that zeroes <w_p', w_q'>
-                    const double zeta = (be - al) / (2.0 * g);
-                    const double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-                    const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
-                    const cplx ph = make_double2(ga.x / g, ga.y / g);   // e^{i phi}, gamma = <w_p, w_q>
+                    const double zeta = 0.5 * (be - al) * ginv;
+                    const double w = 1.0 + zeta * zeta;
+                    const double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(w));   // sqrt, not w * rsqrt(w): w may overflow to inf (t -> 0)
+                    const double c = rsqrt(1.0 + t * t), s = c * t;
+                    const cplx ph = make_double2(ga.x * ginv, ga.y * ginv);   // e^{i phi}, gamma = <w_p, w_q>
                     for (int r = lane; r < ni; r += 32) {
                         cplx u = wp[r], v = wq[r];
                         cplx vph = cmulconj(ph, v);            // e^{-i phi} v
@@ -261,13 +280,13 @@ __global__ void __launch_bounds__(BOND_THREADS) bond_kernel(const BondDev* __res
                         vq[r] = make_double2(s * uph.x + c * v.x, s * uph.y + c * v.y);
                     }
                 }
-                __syncthreads();
+                again |= __syncthreads_or(need);    // the barrier between two tournament steps doubles as the vote
             }
-            if (s_flag == 0) break;
-            __syncthreads();
+            if (!again) break;
         }
     }
 
+    const long long t_jac = clock64();
     // ---- 4. singular values, descending order, truncation (src/peps.jl:383-390) ----
     for (int c = tid; c < nj; c += BOND_THREADS) {
         double a = 0.0;
@@ -293,6 +312,8 @@ __global__ void __launch_bounds__(BOND_THREADS) bond_kernel(const BondDev* __res
         double err = 0.0;
         for (int k = D; k < ncomp; ++k) err += sval[perm[k]];
         *J.kept = D;
+        // diagnostics in the spare words of the job's meta record (read back with option debug >= 2)
+        J.kept[1] = n_sweeps; J.kept[2] = (int)((t_qr - t_start) >> 10); J.kept[3] = (int)((t_jac - t_core) >> 10);
         *J.trunc_err = D < full ? err : -1.0;   // -1: nothing was cut (the reference logs only when D < size(U,2))
         s_flag = D;
     }
@@ -303,7 +324,7 @@ __global__ void __launch_bounds__(BOND_THREADS) bond_kernel(const BondDev* __res
     for (int side = 0; side < 2; ++side) {
         const SiteMap& M = map[side];
         const int O = M.O, I = 2 * M.Ds;
-        const cplx* Q = J.Q[side];
+        const cplx* Q = O * I <= QS_MAX ? Qs + side * QS_MAX : J.Q[side];
         cplx* out = J.UV[side];
         const int rows = 2 * O;
         for (int e = tid; e < rows * D; e += BOND_THREADS) {
@@ -334,13 +355,23 @@ __global__ void __launch_bounds__(BOND_THREADS) bond_kernel(const BondDev* __res
                 acc.x *= sq; acc.y *= sq;
             }
             out[(long long)dd * rows + row] = acc;
+            if (J.place[side]) {
+                // the same element in the site tensor's own layout (column-major over dims with dims[ax] = Dcap)
+                long long off = pp, st = M.dim[0];
+                int oo = o;
+                for (int q = 1; q < M.rank; ++q) {
+                    if (q == M.ax) { off += (long long)dd * st; st *= J.Dcap; }
+                    else { off += (long long)(oo % M.dim[q]) * st; oo /= M.dim[q]; st *= M.dim[q]; }
+                }
+                J.place[side][off] = acc;
+            }
         }
     }
     for (int dd = tid; dd < D; dd += BOND_THREADS) J.S[dd] = make_double2(sval[perm[dd]], 0.0);
 }
 
 size_t bond_smem_bytes() {
-    return (size_t)(2 * MAXI * MAXI + 2 * MAXN * MAXN + MAXI) * sizeof(cplx) + (64 + MAXN) * sizeof(double) + MAXN * sizeof(int) + 64;
+    return (size_t)(2 * MAXI * MAXI + 2 * MAXN * MAXN + MAXI + 2 * QS_MAX) * sizeof(cplx) + (64 + MAXN) * sizeof(double) + MAXN * sizeof(int) + 64;
 }
 
 struct HostJob {
@@ -352,17 +383,27 @@ struct HostJob {
 
 }  // namespace
 
-static int bond_run(tne_ctx* ctx, int n_jobs, const tne_bond_job* in, std::vector<HostJob>& hj, std::vector<int>& kept,
-                    std::vector<double>& err, int svd_only, const tne_buf* svd_A) {
-    (void)svd_only; (void)svd_A;
+// A launched batch of bond jobs whose results (kept rank, truncation error) have not been read back yet.
+struct BondBatch {
+    std::vector<HostJob> hj;
+    std::vector<BondDev> dev;      // stays alive until the batch has been fetched (source of an async H2D copy)
+    tne_buf hmeta = 0, hdev = 0;
+    int n = 0;
+};
+
+// builds the device descriptors and launches the bond kernel for `n_jobs` site-disjoint jobs; does not synchronise
+static int bond_enqueue(tne_ctx* ctx, int n_jobs, const tne_bond_job* in, BondBatch& bb, std::vector<tne_buf>* direct = nullptr) {
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(bond_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bond_smem_bytes());
         attr_set = true;
     }
-    std::vector<BondDev> dev(n_jobs);
-    hj.resize(n_jobs);
-    tne_buf hmeta;
+    std::vector<BondDev>& dev = bb.dev;
+    std::vector<HostJob>& hj = bb.hj;
+    dev.assign(n_jobs, BondDev());
+    hj.assign(n_jobs, HostJob());
+    bb.n = n_jobs;
+    tne_buf& hmeta = bb.hmeta;
     TNE_TRY(buf_new(ctx, {(int64_t)(2 * n_jobs + 1)}, &hmeta));   // kept (as int in .x slot) and error per job
     char* meta = reinterpret_cast<char*>(buf_get(ctx, hmeta)->ptr());
     for (int k = 0; k < n_jobs; ++k) {
@@ -410,21 +451,48 @@ static int bond_run(tne_ctx* ctx, int n_jobs, const tne_bond_job* in, std::vecto
         }
         TNE_TRY(buf_new(ctx, {(int64_t)d.Dcap}, &hj[k].s));
         d.S = buf_get(ctx, hj[k].s)->ptr();
+        if (direct) {   // speculative sweep: allocate the final tensors now (bond leg = Dcap) and let the kernel fill them
+            for (int side = 0; side < 2; ++side) {
+                std::vector<int64_t> od = hj[k].dims[side];
+                od[hj[k].axis[side]] = d.Dcap;
+                tne_buf ho;
+                TNE_TRY(buf_new(ctx, od, &ho));
+                direct->push_back(ho);
+                d.place[side] = buf_get(ctx, ho)->ptr();
+            }
+            tne_buf hs;
+            TNE_TRY(buf_new(ctx, {(int64_t)d.Dcap}, &hs));
+            direct->push_back(hs);
+            d.S = buf_get(ctx, hs)->ptr();
+        }
         d.kept = reinterpret_cast<int*>(meta + 16 * (2 * k));
         d.trunc_err = reinterpret_cast<double*>(meta + 16 * (2 * k + 1));
     }
-    tne_buf hdev;
+    tne_buf& hdev = bb.hdev;
     const int64_t dev_elems = ((int64_t)n_jobs * (int64_t)sizeof(BondDev) + 15) / 16;
     TNE_TRY(buf_new(ctx, {dev_elems}, &hdev));
     TNE_CUDA(ctx, cudaMemcpyAsync(buf_get(ctx, hdev)->ptr(), dev.data(), (size_t)n_jobs * sizeof(BondDev), cudaMemcpyHostToDevice, ctx->stream));
     bond_kernel<<<n_jobs, BOND_THREADS, bond_smem_bytes(), ctx->stream>>>(reinterpret_cast<const BondDev*>(buf_get(ctx, hdev)->ptr()));
     TNE_LAUNCH_CHECK(ctx);
+    return TNE_OK;
+}
+
+// reads back (kept, truncation error) of a launched batch: the only host synchronisation of a bond update
+static int bond_fetch(tne_ctx* ctx, BondBatch& bb, std::vector<int>& kept, std::vector<double>& err) {
+    const int n_jobs = bb.n;
+    tne_buf& hmeta = bb.hmeta;
+    tne_buf& hdev = bb.hdev;
+    const char* meta = reinterpret_cast<const char*>(buf_get(ctx, hmeta)->ptr());
     std::vector<char> hmeta_host((size_t)32 * n_jobs);
     TNE_CUDA(ctx, cudaMemcpyAsync(hmeta_host.data(), meta, hmeta_host.size(), cudaMemcpyDeviceToHost, ctx->stream));
     TNE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // also guarantees `dev` was consumed
     kept.resize(n_jobs); err.resize(n_jobs);
     for (int k = 0; k < n_jobs; ++k) {
         kept[k] = *reinterpret_cast<int*>(hmeta_host.data() + 32 * k);
+        if (ctx->opt_debug > 1) {
+            const int* w = reinterpret_cast<const int*>(hmeta_host.data() + 32 * k);
+            fprintf(stderr, "[tne-bond] job %d: kept %d, %d Jacobi sweeps, QR %d kclk, Jacobi %d kclk\n", k, w[0], w[1], w[2], w[3]);
+        }
         err[k] = *reinterpret_cast<double*>(hmeta_host.data() + 32 * k + 16);
     }
     tne_free(ctx, hdev);
@@ -451,10 +519,12 @@ static int bond_place(tne_ctx* ctx, tne_buf uv, const std::vector<int64_t>& dims
 extern "C" int tne_apply_onbond_batched(tne_ctx* ctx, int n_jobs, tne_bond_job* jobs) {
     if (n_jobs <= 0) return TNE_OK;
     if (!jobs) return tne_fail(ctx, TNE_ERR_INVALID, "null jobs");
-    std::vector<HostJob> hj;
+    BondBatch bb;
     std::vector<int> kept;
     std::vector<double> err;
-    TNE_TRY(bond_run(ctx, n_jobs, jobs, hj, kept, err, 0, nullptr));
+    TNE_TRY(bond_enqueue(ctx, n_jobs, jobs, bb));
+    TNE_TRY(bond_fetch(ctx, bb, kept, err));
+    std::vector<HostJob>& hj = bb.hj;
     for (int k = 0; k < n_jobs; ++k) {
         const int D = kept[k];
         TNE_TRY(bond_place(ctx, hj[k].uv[0], hj[k].dims[0], hj[k].axis[0], D, &jobs[k].ti_out));
@@ -469,6 +539,135 @@ extern "C" int tne_apply_onbond_batched(tne_ctx* ctx, int n_jobs, tne_bond_job* 
         tne_free(ctx, hj[k].s);
     }
     return TNE_OK;
+}
+
+// One whole TEBD sweep (src/tebd.jl:15-23) in one call.  The reference applies the gates strictly one after the other;
+// gates on disjoint sites commute exactly (truncation included), so the sequence is levelled into wavefronts of
+// site-disjoint gates (a gate's level = 1 + the highest level of an earlier gate on one of its sites) and every
+// wavefront is one launch.  The rank a bond keeps is data dependent (src/peps.jl:383-390), but a generic gate always
+// truncates to the cap min(Dmax, 4 Ds, 2 O_i, 2 O_j): the sweep is therefore enqueued SPECULATIVELY with kept = cap, with
+// no host synchronisation between wavefronts, and the kept ranks are checked once at the end.  If any bond kept fewer
+// (singular values below eps), the speculative outputs are dropped and the sweep is redone wavefront by wavefront with
+// the exact ranks (the inputs are immutable buffers, so nothing has to be restored).
+extern "C" int tne_tebd_sweep(tne_ctx* ctx, int n_sites, tne_buf* sites, int n_bonds, tne_buf* bonds, int n_gates,
+                              tne_sweep_gate* gates, int Dmax, double eps, int vidal) {
+    if (n_gates <= 0) return TNE_OK;
+    if (!sites || !gates || (vidal && !bonds)) return tne_fail(ctx, TNE_ERR_INVALID, "null argument");
+    // wavefront levels, order-preserving
+    std::vector<int> site_level(n_sites, -1), level(n_gates, 0);
+    int n_levels = 0;
+    for (int gi = 0; gi < n_gates; ++gi) {
+        const tne_sweep_gate& g = gates[gi];
+        if (g.site_i < 0 || g.site_i >= n_sites || g.site_j < 0 || g.site_j >= n_sites || g.site_i == g.site_j)
+            return tne_fail(ctx, TNE_ERR_INVALID, "sweep gate %d: bad site index", gi);
+        if (vidal && (g.bond < 0 || g.bond >= n_bonds)) return tne_fail(ctx, TNE_ERR_INVALID, "sweep gate %d: bad bond index", gi);
+        level[gi] = 1 + std::max(site_level[g.site_i], site_level[g.site_j]);
+        site_level[g.site_i] = site_level[g.site_j] = level[gi];
+        n_levels = std::max(n_levels, level[gi] + 1);
+    }
+    std::vector<std::vector<int>> by_level(n_levels);
+    for (int gi = 0; gi < n_gates; ++gi) by_level[level[gi]].push_back(gi);
+
+    const std::vector<tne_buf> sites0(sites, sites + n_sites);
+    const std::vector<tne_buf> bonds0(bonds, bonds + (vidal ? n_bonds : 0));
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        const bool speculative = attempt == 0;
+        std::vector<tne_buf> cur_s = sites0, cur_b = bonds0, created;
+        std::vector<BondBatch> batches(n_levels);
+        std::vector<std::vector<int>> cap(n_levels);
+        bool ok = true;
+        int rc = TNE_OK;
+        auto drop_created = [&]() { for (auto h : created) tne_free(ctx, h); created.clear(); };
+        for (int lv = 0; lv < n_levels && rc == TNE_OK; ++lv) {
+            const std::vector<int>& ids = by_level[lv];
+            std::vector<tne_bond_job> jobs(ids.size());
+            for (size_t q = 0; q < ids.size(); ++q) {
+                const tne_sweep_gate& g = gates[ids[q]];
+                tne_bond_job& jb = jobs[q];
+                memset(&jb, 0, sizeof(jb));
+                jb.ti = cur_s[g.site_i]; jb.tj = cur_s[g.site_j];
+                jb.axis_i = g.axis_i; jb.axis_j = g.axis_j;
+                memcpy(jb.gate, g.gate, sizeof(jb.gate));
+                jb.Dmax = Dmax; jb.eps = eps; jb.vidal = vidal;
+                if (vidal)
+                    for (int a = 1; a < TNE_MAX_RANK; ++a) {
+                        if (g.lambda_i[a] >= 0 && g.lambda_i[a] < n_bonds) jb.lambda_i[a] = cur_b[g.lambda_i[a]];
+                        if (g.lambda_j[a] >= 0 && g.lambda_j[a] < n_bonds) jb.lambda_j[a] = cur_b[g.lambda_j[a]];
+                    }
+            }
+            BondBatch& bb = batches[lv];
+            std::vector<tne_buf> direct;
+            rc = bond_enqueue(ctx, (int)jobs.size(), jobs.data(), bb, speculative ? &direct : nullptr);
+            for (auto h : direct) created.push_back(h);
+            if (rc) break;
+            std::vector<int> kept;
+            std::vector<double> err;
+            if (!speculative) {
+                rc = bond_fetch(ctx, bb, kept, err);
+                if (rc) break;
+            }
+            cap[lv].resize(ids.size());
+            for (size_t q = 0; q < ids.size() && rc == TNE_OK; ++q) {
+                tne_sweep_gate& g = gates[ids[q]];
+                HostJob& h = bb.hj[q];
+                const int D = speculative ? bb.dev[q].Dcap : kept[q];
+                cap[lv][q] = D;
+                if (!speculative) { g.kept = kept[q]; g.trunc_err = err[q]; }
+                tne_buf ti = 0, tj = 0, sb = 0;
+                if (speculative) {   // the kernel wrote the final tensors itself
+                    cur_s[g.site_i] = direct[3 * q]; cur_s[g.site_j] = direct[3 * q + 1];
+                    if (vidal) cur_b[g.bond] = direct[3 * q + 2];
+                    for (int side = 0; side < 2; ++side) { tne_free(ctx, h.q[side]); tne_free(ctx, h.uv[side]); }
+                    tne_free(ctx, h.s);
+                    continue;
+                }
+                rc = bond_place(ctx, h.uv[0], h.dims[0], h.axis[0], D, &ti);
+                if (!rc) { created.push_back(ti); rc = bond_place(ctx, h.uv[1], h.dims[1], h.axis[1], D, &tj); }
+                if (!rc) { created.push_back(tj); rc = buf_new(ctx, {(int64_t)D}, &sb); }
+                if (!rc) {
+                    created.push_back(sb);
+                    if (D > 0)
+                        TNE_CUDA(ctx, cudaMemcpyAsync(buf_get(ctx, sb)->ptr(), buf_get(ctx, h.s)->ptr(), (size_t)D * sizeof(cplx),
+                                                      cudaMemcpyDeviceToDevice, ctx->stream));
+                    cur_s[g.site_i] = ti; cur_s[g.site_j] = tj;
+                    if (vidal) cur_b[g.bond] = sb;
+                }
+                for (int side = 0; side < 2; ++side) { tne_free(ctx, h.q[side]); tne_free(ctx, h.uv[side]); }
+                tne_free(ctx, h.s);
+            }
+        }
+        if (rc == TNE_OK && speculative) {   // one synchronisation for the whole sweep: were all the caps reached?
+            for (int lv = 0; lv < n_levels && rc == TNE_OK; ++lv) {
+                std::vector<int> kept;
+                std::vector<double> err;
+                rc = bond_fetch(ctx, batches[lv], kept, err);
+                for (size_t q = 0; q < by_level[lv].size() && rc == TNE_OK; ++q) {
+                    tne_sweep_gate& g = gates[by_level[lv][q]];
+                    g.kept = kept[q]; g.trunc_err = err[q];
+                    if (kept[q] != cap[lv][q]) ok = false;
+                }
+            }
+        }
+        if (rc != TNE_OK) {
+            for (auto& bb : batches) { if (bb.hmeta) tne_free(ctx, bb.hmeta); if (bb.hdev) tne_free(ctx, bb.hdev); }
+            drop_created();
+            return rc;
+        }
+        if (ok) {
+            // hand the final tensors out; intermediate generations (a site touched by several gates) are released
+            for (auto h : created) {
+                bool live = false;
+                for (int i = 0; i < n_sites && !live; ++i) live = cur_s[i] == h;
+                for (size_t i = 0; i < cur_b.size() && !live; ++i) live = cur_b[i] == h;
+                if (!live) tne_free(ctx, h);
+            }
+            for (int i = 0; i < n_sites; ++i) sites[i] = cur_s[i];
+            for (size_t i = 0; i < cur_b.size(); ++i) bonds[i] = cur_b[i];
+            return TNE_OK;
+        }
+        drop_created();   // a bond kept fewer singular values than its cap: redo with exact ranks
+    }
+    return tne_fail(ctx, TNE_ERR_UNSUPPORTED, "tebd sweep: exact-rank pass did not complete");
 }
 
 // LinearAlgebra.svd(A) + truncation for a matrix: the same kernel on the trivial "bond" whose sites are

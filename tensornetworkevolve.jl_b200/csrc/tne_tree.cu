@@ -793,6 +793,19 @@ struct Exec {
 
     // one line per launch group of the final (fused) phases: what runs, how often, with which algorithmic cost
     void dump_final() const {
+        double tot_flops = 0;
+        long long tot_launches = 0;
+        for (auto& ph : phases)
+            for (auto& po : ph.ops) {
+                const long long n = po.first_slice_only ? 1 : ph.nsl;
+                double fl = po.s2 ? po.s2_flops : po.plan.flops;
+                for (auto& ex : po.extra) fl += ex.plan.flops;
+                tot_flops += fl * (double)n;
+                tot_launches += n;
+            }
+        fprintf(stderr, "[tne-plan] %zu phases, %lld launches, %.4e flops, workspace %.3f GiB (checkpoints %.3f + segment %.3f)\n", phases.size(),
+                tot_launches, tot_flops, (persist_bytes + temp_bytes) / 1073741824.0, persist_bytes / 1073741824.0, temp_bytes / 1073741824.0);
+        if (ctx->opt_debug == 2) return;   // summary only
         for (size_t pi = 0; pi < phases.size(); ++pi) {
             const Phase& ph = phases[pi];
             for (auto& po : ph.ops) {

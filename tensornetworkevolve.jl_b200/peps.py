@@ -460,6 +460,62 @@ def apply_onbond_batch_(peps, gates):
     return peps
 
 
+def apply_sweep_(peps, gates):
+    """``apply_onbond!`` for a whole sequence ``[(i, j, mat), ...]`` (one TEBD sweep, src/tebd.jl:16-21) in ONE library
+    call: ``tne_tebd_sweep`` levels the sequence into wavefronts of site-disjoint gates and enqueues them without any
+    host synchronisation in between.  Results and the ``LOG`` order are those of the sequential loop."""
+    if not gates:
+        return peps
+    for i, j, _ in gates:
+        if getphysicallabel(peps, i) != getvlabel(peps, i)[0] or getphysicallabel(peps, j) != getvlabel(peps, j)[0]:
+            raise ValueError("the device bond update expects the physical leg first (src/peps.jl:253)")
+    vidal = peps.kind == "vidal"
+    ctx = _dev(peps.vertex_tensors[0]).ctx
+    nv, nb = len(peps.vertex_tensors), len(peps.virtual_labels)
+    bond_index = {l: k for k, l in enumerate(peps.virtual_labels)}
+    arr = (_lib.TneSweepGate * len(gates))()
+    shared_of = []
+    for q, (i, j, mat) in enumerate(gates):
+        li, lj = getvlabel(peps, i), getvlabel(peps, j)
+        shared = [l for l in li if l in lj]
+        if len(shared) != 1:
+            raise AssertionError("length(shared_label) == 1")
+        sg = arr[q]
+        sg.site_i, sg.site_j = i - 1, j - 1
+        sg.axis_i, sg.axis_j = li.index(shared[0]), lj.index(shared[0])
+        sg.bond = bond_index[shared[0]]
+        g = np.asarray(mat, dtype=np.complex128).reshape(4, 4, order="F")  # (o_i + 2 o_j, i_i + 2 i_j)
+        sg.gate[:] = np.asfortranarray(g).reshape(-1, order="F").view(np.float64).tolist()
+        for a in range(_lib.MAX_RANK):
+            sg.lambda_i[a] = bond_index[li[a]] if vidal and 0 < a < len(li) else -1
+            sg.lambda_j[a] = bond_index[lj[a]] if vidal and 0 < a < len(lj) else -1
+        shared_of.append(shared[0])
+    old_sites = [_dev(t) for t in peps.vertex_tensors]
+    sites = (C.c_int64 * nv)(*[t.handle for t in old_sites])
+    old_bonds = [_dev(t) for t in peps.bond_tensors] if vidal else []
+    bonds = (C.c_int64 * max(1, nb))(*([t.handle for t in old_bonds] if vidal else [0]))
+    ctx.check(ctx.L.tne_tebd_sweep(ctx.h, nv, sites, nb if vidal else 0, bonds, len(gates), arr, int(peps.Dmax), float(peps.eps),
+                                   1 if vidal else 0))
+    # shapes: the bond a gate rewrote now has the rank it kept (the last gate on a bond wins)
+    shapes = [list(t.shape) for t in old_sites]
+    blen = {}
+    for q, (i, j, _) in enumerate(gates):
+        sg = arr[q]
+        shapes[i - 1][sg.axis_i] = sg.kept
+        shapes[j - 1][sg.axis_j] = sg.kept
+        blen[sg.bond] = sg.kept
+        if sg.trunc_err >= 0:
+            LOG.append("truncation error is %r" % sg.trunc_err)
+    for k in range(nv):
+        if sites[k] != old_sites[k].handle:
+            peps.vertex_tensors[k] = B200Array(sites[k], shapes[k], False, ctx)
+    if vidal:
+        for k in range(nb):
+            if bonds[k] != old_bonds[k].handle:
+                peps.bond_tensors[k] = B200Array(bonds[k], (blen[k],), True, ctx)
+    return peps
+
+
 # -- Yao glue, src/peps.jl:432-477 ------------------------------------------------------
 def apply_block_(peps, block):
     """``YaoBlocks.unsafe_apply!`` methods, src/peps.jl:437-460."""

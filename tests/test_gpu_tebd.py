@@ -110,3 +110,28 @@ def test_tebd_grid_config1(tne):
     assert rel(tne.norm(dp).to_numpy(), OP.norm(op)) < 1e-8
     lv = tne.tebd.wavefronts(g.edges())
     assert sum(len(b) for b in lv) == g.ne() and all(len({s for e in b for s in e}) == 2 * len(b) for b in lv)
+
+
+@pytest.mark.parametrize("kind", ["simple", "vidal"])
+def test_tebd_sweep_from_product_state_exact_ranks(tne, kind):
+    """TEBD from |0...0> (test/tebd.jl starts from random states; this is the data-dependent-rank case): the first
+    sweeps keep FEWER singular values than the cap (absolute eps cut, src/peps.jl:383-390), so tne_tebd_sweep's
+    speculative pass is rejected and the sweep is redone with exact ranks.  Bond dimensions, bond vectors and the state
+    must match the oracle's strictly sequential loop."""
+    L, D = 3, 2
+    g = OG.grid([L, L])
+    kw = dict(Dmax=4, eps=1e-10)
+    f = OP.zero_vidalpeps if kind == "vidal" else OP.zero_simplepeps
+    op = f(g, D, **kw)
+    dp = device_peps_like(tne, op, g, D, **kw)
+    args = dict(t=0.4, C=10.0, delta=0.2, omega=0.3, nstep=4)
+    OP.LOG.clear(); tne.peps.LOG.clear()
+    OT.rydberg_tebd_(op, g, **args)
+    tne.rydberg_tebd_(dp, tne.grid([L, L]), **args)
+    assert [t.shape for t in dp.vertex_tensors] == [np.shape(t) for t in op.vertex_tensors]
+    assert rel(tne.vec(dp), OP.vec(op)) < 1e-8
+    if kind == "vidal":
+        for b in range(g.ne()):
+            assert dp.bond_tensors[b].shape == np.shape(op.bond_tensors[b])
+            assert rel(dp.bond_tensors[b].to_numpy(), op.bond_tensors[b]) < 1e-8
+    assert len(tne.peps.LOG) == len(OP.LOG)
