@@ -318,10 +318,24 @@ def run_gpu(args):
         gt = T.grid([Lt, Lt])
         pt = T.rand_simplepeps(gt, 4, np.random.default_rng(seed_for(Lt, 4)))
         sweep = lambda: T.rydberg_tebd_sweep_(pt, gt, C_, DELTA_, OMEGA_, 0.03)
-        sweep()
-        tms, tl, _ = timed(sweep, 1)
+        sweep(); sweep()
+        nsw = 5
+        tms, tl, _ = timed(lambda: [sweep() for _ in range(nsw)], 1)
+        tms /= nsw
         extras["tebd_sweep_8x8_D4"] = {"ms": tms, "bonds": gt.ne(), "bonds_per_s": gt.ne() / (tms * 1e-3), "wavefronts": len(T.tebd.wavefronts(gt.edges())),
-                                       "note": "one rydberg_tebd_sweep!: 112 bond gates, QR-reduced Jacobi SVD truncation to D=4, latency-bound"}
+                                       "note": "one rydberg_tebd_sweep! (mean of %d): 112 bond gates in one tne_tebd_sweep call (28 wavefront launches, no host "
+                                               "sync in between), QR-reduced Jacobi SVD truncation to D=4, latency-bound" % nsw}
+        # the largest exact D=4 norm contraction of a square lattice that fits one B200 (8x8 D=4 needs a 64 GiB boundary
+        # tensor per variant: see DESIGN.md section 10)
+        Ln = 7
+        gn = T.grid([Ln, Ln])
+        on, sn = T.sweep_plan(gn, Ln)
+        pn = T.rand_simplepeps(gn, 4, np.random.default_rng(seed_for(Ln, 4)), optimizer=on, segments=sn)
+        T.norm(pn)
+        nms, _, nv = timed(lambda: T.norm(pn), 1)
+        st = ctx.program_stats()
+        extras["norm_7x7_D4"] = {"ms": nms, "flops": st["flops"], "tflops": st["flops"] / (nms * 1e-3) / 1e12, "log10_norm": float(np.log10(abs(nv.item()))),
+                                 "note": "exact <psi|psi> of a 7x7 D=4 PEPS (one contraction, forward only)"}
     if rank == 0:
         cpu, _ = cpu_sample(L, D, budget_s=args.cpu_seconds) if world == 1 and not args.no_cpu else (None, None)
         line = {

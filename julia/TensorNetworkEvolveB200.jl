@@ -8,6 +8,9 @@
 module TensorNetworkEvolveB200
 
 using OMEinsum, LinearAlgebra
+using Graphs: edges, src, dst, degree
+using Yao: put, mat, time_evolve
+using ..TensorNetworkEvolve: cterm, xterm, zterm
 using OMEinsum: DynamicEinCode, StaticEinCode, NestedEinsum, SlicedEinsum, getixsv, getiyv
 
 const LIB = Ref{String}("libtne_b200.so")
@@ -162,6 +165,47 @@ function LinearAlgebra.svd(a::B200Array{T,2}; Dmax = minimum(size(a)), ϵ = 0.0)
                 CTX[], a.handle, Dmax, ϵ, u, s, v, kept, err))
     k = Int(kept[])
     return (U = B200Array{T,2}(u[], (size(a, 1), k)), S = B200Array{real(T),1}(s[], (k,)), V = B200Array{T,2}(v[], (size(a, 2), k)))
+end
+
+# ---- rydberg_tebd_sweep! (src/tebd.jl:15-23): the whole sweep in ONE call (tne_tebd_sweep) ---------------------------
+# The library levels the sequential gate list into wavefronts of site-disjoint gates, enqueues them without host
+# synchronisation (kept rank assumed = cap, verified once; exact-rank redo otherwise) and returns the new handles.
+struct SweepGate                                   # mirrors tne_sweep_gate (include/tne.h); isbits, passed by pointer
+    site_i::Int32; site_j::Int32; axis_i::Int32; axis_j::Int32; bond::Int32
+    gate::NTuple{32,Cdouble}
+    lambda_i::NTuple{32,Int32}; lambda_j::NTuple{32,Int32}
+    kept::Int32; trunc_err::Cdouble
+end
+function TensorNetworkEvolve.rydberg_tebd_sweep!(peps::TensorNetworkEvolve.PEPS{T,NF,LT,<:B200Array}, g, C, Δ, Ω, δt) where {T,NF,LT}
+    vidal = peps isa TensorNetworkEvolve.VidalPEPS
+    bondidx = Dict(l => Int32(k - 1) for (k, l) in enumerate(peps.virtual_labels))
+    gates = SweepGate[]
+    for e in edges(g)                                # the reference's order (src/tebd.jl:16)
+        i, j = src(e), dst(e)
+        hij = cterm(C) + put(2, 1 => xterm(Ω / degree(g, i))) + put(2, 2 => xterm(Ω / degree(g, j))) +
+              put(2, 1 => zterm(Δ / degree(g, i))) + put(2, 2 => zterm(Δ / degree(g, j)))      # src/tebd.jl:19
+        m = Matrix(mat(time_evolve(hij, δt)))      # M[o_i + 2 o_j, i_i + 2 i_j], column-major
+        li, lj = peps.vertex_labels[i], peps.vertex_labels[j]
+        shared = only(li ∩ lj)
+        lam(ls) = ntuple(a -> (vidal && 1 < a <= length(ls)) ? bondidx[ls[a]] : Int32(-1), 32)
+        push!(gates, SweepGate(i - 1, j - 1, findfirst(==(shared), li) - 1, findfirst(==(shared), lj) - 1, bondidx[shared],
+                               ntuple(k -> reinterpret(Cdouble, vec(ComplexF64.(m)))[k], 32), lam(li), lam(lj), 0, 0.0))
+    end
+    sites = Int64[t.handle for t in peps.vertex_tensors]
+    bonds = vidal ? Int64[t.handle for t in peps.bond_tensors] : Int64[0]
+    check(ccall((:tne_tebd_sweep, LIB[]), Cint,
+                (Ptr{Cvoid}, Cint, Ptr{Int64}, Cint, Ptr{Int64}, Cint, Ptr{SweepGate}, Cint, Cdouble, Cint),
+                CTX[], length(sites), sites, vidal ? length(bonds) : 0, bonds, length(gates), gates, peps.Dmax, peps.ϵ, vidal))
+    for (q, e) in enumerate(edges(g))                # new shapes: the bond a gate rewrote has the rank it kept
+        gq = gates[q]
+        gq.trunc_err >= 0 && @info "truncation error is $(gq.trunc_err)"                       # src/peps.jl:386
+        for (s, ax) in ((src(e), gq.axis_i + 1), (dst(e), gq.axis_j + 1))
+            sz = collect(size(peps.vertex_tensors[s])); sz[ax] = gq.kept
+            peps.vertex_tensors[s] = B200Array{T,length(sz)}(sites[s], Tuple(sz))
+        end
+        vidal && (peps.bond_tensors[gq.bond + 1] = B200Array{T,1}(bonds[gq.bond + 1], (Int(gq.kept),)))
+    end
+    return peps
 end
 
 to_b200(peps) = TensorNetworkEvolve.replace_tensors(peps, B200Array.(TensorNetworkEvolve.alltensors(peps)))
