@@ -102,6 +102,56 @@ struct SiteMap {
     }
 };
 
+// In-place QR of the O x I column-major matrix Q (shared or global memory) by classical Gram-Schmidt with one
+// re-orthogonalisation pass ("twice is enough"); a column that is numerically in the span of the previous ones becomes
+// zero with a zero pivot.  The triangular factor goes to Rm (leading dimension ld): Rm[k + c ld] = r_kc, or, with herm,
+// its conjugate transpose Rm[c + k ld] = conj(r_kc).  Rm must be zeroed by the caller.  Block-wide; ends synchronised.
+__device__ void cgs2(cplx* Q, int O, int I, cplx* Rm, int ld, bool herm, cplx* coef, double* red) {
+    const int tid = threadIdx.x;
+    for (int c = 0; c < I; ++c) {
+        cplx* vc = Q + (long long)c * O;
+        double nrm0 = 0.0;
+        {
+            cplx a = make_double2(0.0, 0.0);
+            for (int o = tid; o < O; o += BOND_THREADS) { cplx x = vc[o]; a.x += x.x * x.x + x.y * x.y; }
+            nrm0 = sqrt(block_sum(a, red).x);
+        }
+        for (int pass = 0; pass < 2; ++pass) {
+            // coef[k] = <q_k, v> for k < c: warp w takes k = w, w + 8, ...
+            const int lane = tid & 31, warp = tid >> 5;
+            for (int k = warp; k < c; k += BOND_THREADS / 32) {
+                const cplx* qk = Q + (long long)k * O;
+                cplx a = make_double2(0.0, 0.0);
+                for (int o = lane; o < O; o += 32) { cplx t = cmulconj(qk[o], vc[o]); a.x += t.x; a.y += t.y; }
+                for (int sh = 16; sh > 0; sh >>= 1) { a.x += __shfl_xor_sync(0xffffffffu, a.x, sh); a.y += __shfl_xor_sync(0xffffffffu, a.y, sh); }
+                if (lane == 0) coef[k] = a;
+            }
+            __syncthreads();
+            for (int o = tid; o < O; o += BOND_THREADS) {
+                cplx x = vc[o];
+                for (int k = 0; k < c; ++k) { cplx t = cmulc(coef[k], Q[(long long)k * O + o]); x.x -= t.x; x.y -= t.y; }
+                vc[o] = x;
+            }
+            if (tid < c) {
+                cplx* dst = herm ? Rm + c + tid * ld : Rm + c * ld + tid;
+                cplx r = *dst;
+                r.x += coef[tid].x; r.y += herm ? -coef[tid].y : coef[tid].y;
+                *dst = r;
+            }
+            __syncthreads();
+        }
+        cplx a = make_double2(0.0, 0.0);
+        for (int o = tid; o < O; o += BOND_THREADS) { cplx x = vc[o]; a.x += x.x * x.x + x.y * x.y; }
+        const double nrm = sqrt(block_sum(a, red).x);
+        // a column that is (numerically) in the span of the previous ones contributes nothing
+        const bool dead = !(nrm > 1e-13 * nrm0) || nrm0 == 0.0;
+        const double inv = dead ? 0.0 : 1.0 / nrm;
+        for (int o = tid; o < O; o += BOND_THREADS) { cplx x = vc[o]; vc[o] = make_double2(x.x * inv, x.y * inv); }
+        if (tid == 0) Rm[c * ld + c] = make_double2(dead ? 0.0 : nrm, 0.0);
+        __syncthreads();
+    }
+}
+
 __global__ void __launch_bounds__(BOND_THREADS) bond_kernel(const BondDev* __restrict__ jobs) {
     extern __shared__ __align__(16) unsigned char smem[];
     const BondDev& J = jobs[blockIdx.x];
@@ -119,6 +169,7 @@ __global__ void __launch_bounds__(BOND_THREADS) bond_kernel(const BondDev* __res
     // square lattice), else in the global scratch J.Q: the Gram-Schmidt loop is a chain of short dependent steps and
     // runs at memory latency
     cplx* Qs = coef + MAXI;                               // [2][QS_MAX]
+    __shared__ int pidx[MAXN];                            // column order of the preconditioning QR
     __shared__ SiteMap map[2];
     __shared__ int s_flag;
     if (tid < 2) map[tid].init(J.dims[tid], J.rank[tid], J.axis[tid]);
@@ -145,44 +196,7 @@ __global__ void __launch_bounds__(BOND_THREADS) bond_kernel(const BondDev* __res
         }
         for (int e = tid; e < MAXI * MAXI; e += BOND_THREADS) R[side][e] = make_double2(0.0, 0.0);
         __syncthreads();
-        // classical Gram-Schmidt with one re-orthogonalisation pass ("twice is enough")
-        for (int c = 0; c < I; ++c) {
-            cplx* vc = Q + (long long)c * O;
-            double nrm0 = 0.0;
-            {
-                cplx a = make_double2(0.0, 0.0);
-                for (int o = tid; o < O; o += BOND_THREADS) { cplx x = vc[o]; a.x += x.x * x.x + x.y * x.y; }
-                nrm0 = sqrt(block_sum(a, red).x);
-            }
-            for (int pass = 0; pass < 2; ++pass) {
-                // coef[k] = <q_k, v> for k < c: warp w takes k = w, w + 8, ...
-                const int lane = tid & 31, warp = tid >> 5;
-                for (int k = warp; k < c; k += BOND_THREADS / 32) {
-                    const cplx* qk = Q + (long long)k * O;
-                    cplx a = make_double2(0.0, 0.0);
-                    for (int o = lane; o < O; o += 32) { cplx t = cmulconj(qk[o], vc[o]); a.x += t.x; a.y += t.y; }
-                    for (int sh = 16; sh > 0; sh >>= 1) { a.x += __shfl_xor_sync(0xffffffffu, a.x, sh); a.y += __shfl_xor_sync(0xffffffffu, a.y, sh); }
-                    if (lane == 0) coef[k] = a;
-                }
-                __syncthreads();
-                for (int o = tid; o < O; o += BOND_THREADS) {
-                    cplx x = vc[o];
-                    for (int k = 0; k < c; ++k) { cplx t = cmulc(coef[k], Q[(long long)k * O + o]); x.x -= t.x; x.y -= t.y; }
-                    vc[o] = x;
-                }
-                if (tid < c) { cplx r = R[side][c * MAXI + tid]; r.x += coef[tid].x; r.y += coef[tid].y; R[side][c * MAXI + tid] = r; }
-                __syncthreads();
-            }
-            cplx a = make_double2(0.0, 0.0);
-            for (int o = tid; o < O; o += BOND_THREADS) { cplx x = vc[o]; a.x += x.x * x.x + x.y * x.y; }
-            const double nrm = sqrt(block_sum(a, red).x);
-            // a column that is (numerically) in the span of the previous ones contributes nothing
-            const bool dead = !(nrm > 1e-13 * nrm0) || nrm0 == 0.0;
-            const double inv = dead ? 0.0 : 1.0 / nrm;
-            for (int o = tid; o < O; o += BOND_THREADS) { cplx x = vc[o]; vc[o] = make_double2(x.x * inv, x.y * inv); }
-            if (tid == 0) R[side][c * MAXI + c] = make_double2(dead ? 0.0 : nrm, 0.0);
-            __syncthreads();
-        }
+        cgs2(Q, O, I, R[side], MAXI, false, coef, red);
     }
 
     const long long t_qr = clock64();
@@ -207,11 +221,49 @@ __global__ void __launch_bounds__(BOND_THREADS) bond_kernel(const BondDev* __res
             }
         W[col * MAXN + row] = acc;
     }
-    for (int e = tid; e < nj * nj; e += BOND_THREADS) {
-        const int r = e % nj, c = e / nj;
-        V[c * MAXN + r] = make_double2(r == c ? 1.0 : 0.0, 0.0);
-    }
     __syncthreads();
+    // ---- 2b. preconditioning (Drmac-Veselic): theta P = Q1 Rt with the columns sorted by decreasing norm, then Jacobi on
+    // X = Rt^H instead of theta.  The Rydberg gate at small dt makes theta strongly graded (sigma_16 / sigma_1 ~ 1e-9) and the
+    // edge bonds make it rank deficient: plain one-sided Jacobi needs 12-13 sweeps (up to the cap of 40 for the
+    // rank-deficient ones), on X it needs 5-7.  theta = (Q1 Vj) Sigma (P X' / Sigma)^H with X' = X Vj the rotated columns.
+    // Needs ni, nj <= MAXI (Ds <= 8): Q1 lives in V's buffer, X and Vj in the two halves of W's buffer.
+    const bool precond = ni <= MAXI && nj <= MAXI;
+    cplx* jw = W;           // the matrix whose columns the Jacobi rotations orthogonalise (jr rows)
+    cplx* jv = V;           // the accumulated rotations (nj rows)
+    int jr = ni;
+    if (precond) {
+        for (int c = tid; c < nj; c += BOND_THREADS) {
+            double a = 0.0;
+            for (int r = 0; r < ni; ++r) { cplx u = W[c * MAXN + r]; a += u.x * u.x + u.y * u.y; }
+            sval[c] = a;
+        }
+        __syncthreads();
+        for (int c = tid; c < nj; c += BOND_THREADS) {
+            int rank = 0;
+            for (int k = 0; k < nj; ++k) if (sval[k] > sval[c] || (sval[k] == sval[c] && k < c)) ++rank;
+            pidx[rank] = c;
+        }
+        __syncthreads();
+        cplx* Q1 = V;                                   // ni x nj, contiguous columns of ni elements
+        for (int e = tid; e < ni * nj; e += BOND_THREADS) { const int r = e % ni, c = e / ni; Q1[c * ni + r] = W[pidx[c] * MAXN + r]; }
+        __syncthreads();
+        cplx* X = W;                                    // nj x nj, leading dimension MAXN
+        cplx* Vj = W + MAXI * MAXN;
+        for (int e = tid; e < nj * nj; e += BOND_THREADS) {
+            const int r = e % nj, c = e / nj;
+            X[c * MAXN + r] = make_double2(0.0, 0.0);
+            Vj[c * MAXN + r] = make_double2(r == c ? 1.0 : 0.0, 0.0);
+        }
+        __syncthreads();
+        cgs2(Q1, ni, nj, X, MAXN, true, coef, red);
+        jw = X; jv = Vj; jr = nj;
+    } else {
+        for (int e = tid; e < nj * nj; e += BOND_THREADS) {
+            const int r = e % nj, c = e / nj;
+            V[c * MAXN + r] = make_double2(r == c ? 1.0 : 0.0, 0.0);
+        }
+        __syncthreads();
+    }
 
     int n_sweeps = 0;
     const long long t_core = clock64();
@@ -231,11 +283,11 @@ __global__ void __launch_bounds__(BOND_THREADS) bond_kernel(const BondDev* __res
                     if (pr == 0) y = step % (npad - 1);
                     int p = min(x, y), q = max(x, y);
                     if (q >= nj || p == q) continue;
-                    cplx* wp = W + p * MAXN;
-                    cplx* wq = W + q * MAXN;
+                    cplx* wp = jw + p * MAXN;
+                    cplx* wq = jw + q * MAXN;
                     double al = 0.0, be = 0.0;
                     cplx ga = make_double2(0.0, 0.0);
-                    for (int r = lane; r < ni; r += 32) {
+                    for (int r = lane; r < jr; r += 32) {
                         cplx u = wp[r], v = wq[r];
                         al += u.x * u.x + u.y * u.y;
                         be += v.x * v.x + v.y * v.y;
@@ -263,15 +315,15 @@ __global__ void __launch_bounds__(BOND_THREADS) bond_kernel(const BondDev* __res
                     const double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(w));   // sqrt, not w * rsqrt(w): w may overflow to inf (t -> 0)
                     const double c = rsqrt(1.0 + t * t), s = c * t;
                     const cplx ph = make_double2(ga.x * ginv, ga.y * ginv);   // e^{i phi}, gamma = <w_p, w_q>
-                    for (int r = lane; r < ni; r += 32) {
+                    for (int r = lane; r < jr; r += 32) {
                         cplx u = wp[r], v = wq[r];
                         cplx vph = cmulconj(ph, v);            // e^{-i phi} v
                         cplx uph = cmulc(ph, u);               // e^{ i phi} u
                         wp[r] = make_double2(c * u.x - s * vph.x, c * u.y - s * vph.y);
                         wq[r] = make_double2(s * uph.x + c * v.x, s * uph.y + c * v.y);
                     }
-                    cplx* vp = V + p * MAXN;
-                    cplx* vq = V + q * MAXN;
+                    cplx* vp = jv + p * MAXN;
+                    cplx* vq = jv + q * MAXN;
                     for (int r = lane; r < nj; r += 32) {
                         cplx u = vp[r], v = vq[r];
                         cplx vph = cmulconj(ph, v);
@@ -290,10 +342,33 @@ __global__ void __launch_bounds__(BOND_THREADS) bond_kernel(const BondDev* __res
     // ---- 4. singular values, descending order, truncation (src/peps.jl:383-390) ----
     for (int c = tid; c < nj; c += BOND_THREADS) {
         double a = 0.0;
-        for (int r = 0; r < ni; ++r) { cplx u = W[c * MAXN + r]; a += u.x * u.x + u.y * u.y; }
+        for (int r = 0; r < jr; ++r) { cplx u = jw[c * MAXN + r]; a += u.x * u.x + u.y * u.y; }
         sval[c] = sqrt(a);
     }
     __syncthreads();
+    // Wf[:, c] = sigma_c u_c (ni rows), Vf[:, c] = v_c (nj rows)
+    const cplx* Wf = W;
+    const cplx* Vf = V;
+    int ldw = MAXN, ldv = MAXN;
+    if (precond) {
+        const cplx* Q1 = V;
+        cplx* wf = R[0];                                // the R factors of the sites are no longer needed
+        cplx* vf = R[1];
+        for (int e = tid; e < ni * nj; e += BOND_THREADS) {          // sigma u = sigma Q1 Vj[:, c]
+            const int r = e % ni, c = e / ni;
+            cplx acc = make_double2(0.0, 0.0);
+            for (int k = 0; k < nj; ++k) { cplx t = cmulc(Q1[k * ni + r], jv[c * MAXN + k]); acc.x += t.x; acc.y += t.y; }
+            wf[c * MAXI + r] = make_double2(acc.x * sval[c], acc.y * sval[c]);
+        }
+        for (int e = tid; e < nj * nj; e += BOND_THREADS) {          // v = P X'[:, c] / sigma_c
+            const int r = e % nj, c = e / nj;
+            const double inv = sval[c] > 0.0 ? 1.0 / sval[c] : 0.0;
+            const cplx x = jw[c * MAXN + r];
+            vf[c * MAXI + pidx[r]] = make_double2(x.x * inv, x.y * inv);
+        }
+        Wf = wf; Vf = vf; ldw = MAXI; ldv = MAXI;
+        __syncthreads();
+    }
     for (int c = tid; c < nj; c += BOND_THREADS) {
         int rank = 0;
         for (int k = 0; k < nj; ++k) if (sval[k] > sval[c] || (sval[k] == sval[c] && k < c)) ++rank;
@@ -334,12 +409,12 @@ __global__ void __launch_bounds__(BOND_THREADS) bond_kernel(const BondDev* __res
             const double s = sval[col];
             cplx acc = make_double2(0.0, 0.0);
             if (side == 0) {
-                for (int a = 0; a < I; ++a) { cplx t = cmulc(Q[(long long)a * O + o], W[col * MAXN + pp + 2 * a]); acc.x += t.x; acc.y += t.y; }
+                for (int a = 0; a < I; ++a) { cplx t = cmulc(Q[(long long)a * O + o], Wf[col * ldw + pp + 2 * a]); acc.x += t.x; acc.y += t.y; }
                 const double inv = s > 0.0 ? 1.0 / s : 0.0;   // u = W / s
                 acc.x *= inv; acc.y *= inv;
             } else {
                 for (int b = 0; b < I; ++b) {
-                    cplx v = V[col * MAXN + pp + 2 * b];
+                    cplx v = Vf[col * ldv + pp + 2 * b];
                     v.y = -v.y;
                     cplx t = cmulc(Q[(long long)b * O + o], v);
                     acc.x += t.x; acc.y += t.y;
