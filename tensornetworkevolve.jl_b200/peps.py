@@ -460,52 +460,76 @@ def apply_onbond_batch_(peps, gates):
     return peps
 
 
+class SweepPlan:
+    """The label bookkeeping of a gate sequence, done once: the ``tne_sweep_gate`` array of ``tne_tebd_sweep`` (site and bond
+    indices, shared-leg positions, gate matrices).  Valid for every PEPS with the same labels; ``kept`` / ``trunc_err`` are
+    overwritten by each sweep."""
+
+    def __init__(self, peps, gates):
+        for i, j, _ in gates:
+            if getphysicallabel(peps, i) != getvlabel(peps, i)[0] or getphysicallabel(peps, j) != getvlabel(peps, j)[0]:
+                raise ValueError("the device bond update expects the physical leg first (src/peps.jl:253)")
+        self.vidal = peps.kind == "vidal"
+        self.sites = [(i, j) for i, j, _ in gates]
+        bond_index = {l: k for k, l in enumerate(peps.virtual_labels)}
+        n = len(gates)
+        # filled through a numpy view of the ctypes array (one vectorised store per field instead of ~70 per gate)
+        self.arr = (_lib.TneSweepGate * n)()
+        view = np.frombuffer(self.arr, dtype=np.dtype(_lib.TneSweepGate))
+        lam_i = np.full((n, _lib.MAX_RANK), -1, dtype=np.int32)
+        lam_j = np.full((n, _lib.MAX_RANK), -1, dtype=np.int32)
+        gmat = np.empty((n, 32), dtype=np.float64)
+        head = np.empty((n, 5), dtype=np.int32)
+        for q, (i, j, mat) in enumerate(gates):
+            li, lj = getvlabel(peps, i), getvlabel(peps, j)
+            shared = [l for l in li if l in lj]
+            if len(shared) != 1:
+                raise AssertionError("length(shared_label) == 1")
+            head[q] = (i - 1, j - 1, li.index(shared[0]), lj.index(shared[0]), bond_index[shared[0]])
+            g = np.asarray(mat, dtype=np.complex128).reshape(4, 4, order="F")  # (o_i + 2 o_j, i_i + 2 i_j)
+            gmat[q] = np.asfortranarray(g).reshape(-1, order="F").view(np.float64)
+            if self.vidal:
+                lam_i[q, 1:len(li)] = [bond_index[l] for l in li[1:]]
+                lam_j[q, 1:len(lj)] = [bond_index[l] for l in lj[1:]]
+        for k, name in enumerate(("site_i", "site_j", "axis_i", "axis_j", "bond")):
+            view[name] = head[:, k]
+        view["gate"] = gmat
+        view["lambda_i"] = lam_i
+        view["lambda_j"] = lam_j
+        self.view = view
+
+
 def apply_sweep_(peps, gates):
     """``apply_onbond!`` for a whole sequence ``[(i, j, mat), ...]`` (one TEBD sweep, src/tebd.jl:16-21) in ONE library
     call: ``tne_tebd_sweep`` levels the sequence into wavefronts of site-disjoint gates and enqueues them without any
-    host synchronisation in between.  Results and the ``LOG`` order are those of the sequential loop."""
-    if not gates:
+    host synchronisation in between.  Results and the ``LOG`` order are those of the sequential loop.  ``gates`` may be a
+    prepared :class:`SweepPlan` (the drivers reuse one plan for all sweeps)."""
+    plan = gates if isinstance(gates, SweepPlan) else SweepPlan(peps, gates)
+    n = len(plan.sites)
+    if n == 0:
         return peps
-    for i, j, _ in gates:
-        if getphysicallabel(peps, i) != getvlabel(peps, i)[0] or getphysicallabel(peps, j) != getvlabel(peps, j)[0]:
-            raise ValueError("the device bond update expects the physical leg first (src/peps.jl:253)")
     vidal = peps.kind == "vidal"
+    if vidal != plan.vidal:
+        raise ValueError("the sweep plan was prepared for the other PEPS kind")
     ctx = _dev(peps.vertex_tensors[0]).ctx
     nv, nb = len(peps.vertex_tensors), len(peps.virtual_labels)
-    bond_index = {l: k for k, l in enumerate(peps.virtual_labels)}
-    arr = (_lib.TneSweepGate * len(gates))()
-    shared_of = []
-    for q, (i, j, mat) in enumerate(gates):
-        li, lj = getvlabel(peps, i), getvlabel(peps, j)
-        shared = [l for l in li if l in lj]
-        if len(shared) != 1:
-            raise AssertionError("length(shared_label) == 1")
-        sg = arr[q]
-        sg.site_i, sg.site_j = i - 1, j - 1
-        sg.axis_i, sg.axis_j = li.index(shared[0]), lj.index(shared[0])
-        sg.bond = bond_index[shared[0]]
-        g = np.asarray(mat, dtype=np.complex128).reshape(4, 4, order="F")  # (o_i + 2 o_j, i_i + 2 i_j)
-        sg.gate[:] = np.asfortranarray(g).reshape(-1, order="F").view(np.float64).tolist()
-        for a in range(_lib.MAX_RANK):
-            sg.lambda_i[a] = bond_index[li[a]] if vidal and 0 < a < len(li) else -1
-            sg.lambda_j[a] = bond_index[lj[a]] if vidal and 0 < a < len(lj) else -1
-        shared_of.append(shared[0])
     old_sites = [_dev(t) for t in peps.vertex_tensors]
     sites = (C.c_int64 * nv)(*[t.handle for t in old_sites])
     old_bonds = [_dev(t) for t in peps.bond_tensors] if vidal else []
     bonds = (C.c_int64 * max(1, nb))(*([t.handle for t in old_bonds] if vidal else [0]))
-    ctx.check(ctx.L.tne_tebd_sweep(ctx.h, nv, sites, nb if vidal else 0, bonds, len(gates), arr, int(peps.Dmax), float(peps.eps),
+    ctx.check(ctx.L.tne_tebd_sweep(ctx.h, nv, sites, nb if vidal else 0, bonds, n, plan.arr, int(peps.Dmax), float(peps.eps),
                                    1 if vidal else 0))
     # shapes: the bond a gate rewrote now has the rank it kept (the last gate on a bond wins)
     shapes = [list(t.shape) for t in old_sites]
     blen = {}
-    for q, (i, j, _) in enumerate(gates):
-        sg = arr[q]
-        shapes[i - 1][sg.axis_i] = sg.kept
-        shapes[j - 1][sg.axis_j] = sg.kept
-        blen[sg.bond] = sg.kept
-        if sg.trunc_err >= 0:
-            LOG.append("truncation error is %r" % sg.trunc_err)
+    kept, err = plan.view["kept"].tolist(), plan.view["trunc_err"].tolist()
+    ax_i, ax_j, bnd = plan.view["axis_i"].tolist(), plan.view["axis_j"].tolist(), plan.view["bond"].tolist()
+    for q, (i, j) in enumerate(plan.sites):
+        shapes[i - 1][ax_i[q]] = kept[q]
+        shapes[j - 1][ax_j[q]] = kept[q]
+        blen[bnd[q]] = kept[q]
+        if err[q] >= 0:
+            LOG.append("truncation error is %r" % err[q])
     for k in range(nv):
         if sites[k] != old_sites[k].handle:
             peps.vertex_tensors[k] = B200Array(sites[k], shapes[k], False, ctx)

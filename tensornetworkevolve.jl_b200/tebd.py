@@ -55,8 +55,16 @@ def rydberg_tebd_sweep_(reg, g, C, delta, omega, dt):  # src/tebd.jl:15-23
             reg.apply_(yao.put(n, (src, dst), gate(src, dst)))
         return reg
     # the whole sweep in one library call (tne_tebd_sweep): wavefronts of site-disjoint gates, one launch each, no host
-    # synchronisation in between; `wavefronts` above states the same levelling for the host-side tests
-    P.apply_sweep_(reg, [(src, dst, np.reshape(gate(src, dst), (2, 2, 2, 2), order="F")) for src, dst in g.edges()])
+    # synchronisation in between; `wavefronts` above states the same levelling for the host-side tests.  The label
+    # bookkeeping of the gate list (a SweepPlan) depends on the PEPS structure and the parameters only: it is kept on the
+    # PEPS object and reused by the following sweeps of rydberg_tebd!
+    key = (float(C), float(delta), float(omega), float(dt), tuple(g.edges()))
+    cached = getattr(reg, "_sweep_plan", None)
+    if cached is None or cached[0] != key:
+        plan = P.SweepPlan(reg, [(src, dst, np.reshape(gate(src, dst), (2, 2, 2, 2), order="F")) for src, dst in g.edges()])
+        cached = (key, plan)
+        reg._sweep_plan = cached
+    P.apply_sweep_(reg, cached[1])
     return reg
 
 
