@@ -59,3 +59,43 @@ except T.TneError as e:
     assert m, res.stderr[-1500:]
     # the memory wall of the exact 8x8 D=4 norm: a 64 GiB boundary per checkpoint
     assert abs(float(m.group(3)) - 1.354e15) / 1.354e15 < 0.02 and float(m.group(4)) > 180.0
+
+
+def test_sweep_plan_layout_on_cpu():
+    """The gate list of a TEBD sweep as ``tne_tebd_sweep`` receives it (SweepPlan, filled through a numpy view of the ctypes
+    array): 0-based sites, shared-leg positions, bond indices, gate matrices M[o_i + 2 o_j, i_i + 2 i_j] and, for Vidal, the
+    bond vector of every virtual leg -- checked field by field against the label bookkeeping of src/peps.jl:353-372."""
+    code = r'''
+import os, sys
+os.environ["TNE_PLAN_ONLY"] = "1"
+sys.path.insert(0, %r)
+import numpy as np
+import tne_b200 as T
+from tne_b200 import peps as P, tebd, _lib
+g = T.grid([4, 4])
+for kind in ("simple", "vidal"):
+    p = (T.zero_simplepeps if kind == "simple" else T.zero_vidalpeps)(g, 3)
+    gates = [(s, d, np.reshape(T.yao.time_evolve(tebd.bond_hamiltonian(10.0, 0.2, 0.3, g.degree(s), g.degree(d)), 0.05), (2, 2, 2, 2), order="F"))
+             for s, d in g.edges()]
+    plan = P.SweepPlan(p, gates)
+    assert len(plan.arr) == g.ne() == 24
+    bi = {l: k for k, l in enumerate(p.virtual_labels)}
+    for q, (i, j, mat) in enumerate(gates):
+        a = plan.arr[q]
+        li, lj = P.getvlabel(p, i), P.getvlabel(p, j)
+        sh = [l for l in li if l in lj]
+        assert len(sh) == 1
+        assert (a.site_i, a.site_j, a.axis_i, a.axis_j, a.bond) == (i - 1, j - 1, li.index(sh[0]), lj.index(sh[0]), bi[sh[0]])
+        m = np.asarray(list(a.gate)).view(np.complex128).reshape(4, 4, order="F")
+        assert np.array_equal(m, mat.reshape(4, 4, order="F"))
+        want_i = [-1] + ([bi[l] for l in li[1:]] if kind == "vidal" else [-1] * (len(li) - 1))
+        assert list(a.lambda_i)[:len(li)] == want_i and all(x == -1 for x in list(a.lambda_i)[len(li):])
+        want_j = [-1] + ([bi[l] for l in lj[1:]] if kind == "vidal" else [-1] * (len(lj) - 1))
+        assert list(a.lambda_j)[:len(lj)] == want_j
+    # the levelling the library applies (stated on the host by tebd.wavefronts): site-disjoint, order-preserving
+    lv = tebd.wavefronts(g.edges())
+    assert sum(len(b) for b in lv) == 24 and all(len({s for e in b for s in e}) == 2 * len(b) for b in lv)
+print("SWEEP-PLAN-OK")
+''' % ROOT
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert "SWEEP-PLAN-OK" in res.stdout, res.stdout + res.stderr[-2000:]
