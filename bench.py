@@ -312,8 +312,14 @@ def run_gpu(args):
         sfun = lambda: T.apply_smatrix(p, T.DiffTensor(v.copy()), T.DiffTensor(v.copy()), T.DiffTensor(xx, requires_grad=False))
         sfun()
         sms, _, sx = timed(sfun, 1)
-        extras["apply_smatrix"] = {"ms": sms, "max_abs": float(np.abs(sx.to_numpy()).max()),
-                                   "note": "S.x of the same %dx%d D=%d PEPS, tree-level algorithm (one tne_expect_terms + reverse pass)" % (L, L, D)}
+        memo = {}
+        mfun = lambda: T.apply_smatrix(p, T.DiffTensor(v.copy()), T.DiffTensor(v.copy()), T.DiffTensor(xx, requires_grad=False), memo=memo)
+        mfun()
+        mms, _, mx = timed(mfun, 1)
+        extras["apply_smatrix"] = {"ms": sms, "ms_inside_gmres": mms, "max_abs": float(np.abs(sx.to_numpy()).max()),
+                                   "memo_max_abs_diff": float(np.abs(mx.to_numpy() - sx.to_numpy()).max()),
+                                   "note": "S.x of the same %dx%d D=%d PEPS, tree-level algorithm (one tne_expect_terms + reverse pass); "
+                                           "ms_inside_gmres: with sr_step's memo of the x-independent contractions" % (L, L, D)}
         Lt = 8
         gt = T.grid([Lt, Lt])
         pt = T.rand_simplepeps(gt, 4, np.random.default_rng(seed_for(Lt, 4)))

@@ -231,6 +231,12 @@ def _tree_rule(nested, slicing, xs):
     # value and the pullbacks for a unit cotangent in ONE device program (forward + reverse sweep, no second
     # forward pass); the program is linear in the cotangent, so back(dy) only rescales the stored gradients
     y, grads = _es.expect_terms_device(code, datas, None, [], leaves, 1.0 + 0j)
+    return wrap_tree_result(xs, leaves, y, grads)
+
+
+def wrap_tree_result(xs, leaves, y, grads):
+    """The taped result of a fused scalar tree: value ``y`` and, per differentiable leaf, the pullback for a unit
+    cotangent.  Also used to re-attach a memoised (value, pullbacks) pair to new leaf objects holding the same numbers."""
     gmap = dict(zip(leaves, grads))
 
     def mk(i):

@@ -28,7 +28,7 @@ def normalized_overlap(peps, v1, v2):  # src/timeevolve.jl:6-12
     return _real(P.inner_product(pl, pr))
 
 
-def apply_smatrix(peps, v1, v2, x):  # src/timeevolve.jl:15-52
+def apply_smatrix(peps, v1, v2, x, memo=None):  # src/timeevolve.jl:15-52
     """Metric-vector product ``sx = d/dv1 Re(conj(x) . dy/dv2)`` of ``y = Re<psi^(v1)|psi^(v2)>``.
 
     The reference differentiates the taped backward pass a second time (reverse over reverse).  With fused
@@ -38,9 +38,13 @@ def apply_smatrix(peps, v1, v2, x):  # src/timeevolve.jl:15-52
     ``phi = (sum_s psi2[s -> x_s] - c psi2) / n2``, ``c = Re<psi2|sum_s psi2[s -> x_s]> / n2^2``, i.e. a sum of
     one-site replacement terms -- exactly what ``tne_expect_terms`` contracts in one device programme
     (shared sub-contractions, checkpointed reverse pass).  ``sx`` is then the ordinary first-order gradient
-    of ``z``.  Works at sizes where the reference's tape cannot exist (6x6, D=4)."""
+    of ``z``.  Works at sizes where the reference's tape cannot exist (6x6, D=4).
+
+    ``memo``: a dict the caller keeps across calls with the SAME ``v1`` and ``v2`` (the matvecs of one GMRES solve in
+    ``sr_step``): the x-independent pieces -- ``<psi2|psi2>`` and the norm programme of ``v1`` (value + pullbacks) -- are then
+    contracted once instead of once per product."""
     if es.FUSED_TREES and peps.kind == "simple":
-        return _apply_smatrix_fused(peps, v1, v2, x)
+        return _apply_smatrix_fused(peps, v1, v2, x, memo)
     fused = es.FUSED_TREES
     es.FUSED_TREES = False
     try:
@@ -65,14 +69,32 @@ def apply_smatrix(peps, v1, v2, x):  # src/timeevolve.jl:15-52
         es.FUSED_TREES = fused
 
 
-def _apply_smatrix_fused(peps, v1, v2, x):
+def _norm_memo(pl, memo):
+    """``norm(pl)`` for a PEPS of DiffTensors; with ``memo`` the fused norm programme (value and pullbacks for a unit
+    cotangent) runs once and is re-attached to the current leaf objects afterwards."""
+    if memo is None:
+        return P.norm(pl)
+    xs = P.conj(pl).alltensors() + pl.alltensors()
+    leaves = [j for j in range(len(xs)) if ad.requires_grad(xs[j])]
+    if "norm" not in memo:
+        memo["norm"] = es.expect_terms_device(pl.code_inner_product, [t.data for t in xs], None, [], leaves, 1.0 + 0j)
+    y, grads = memo["norm"]
+    return ad.bsqrt(ad.babs(ad.wrap_tree_result(xs, leaves, y, grads)))
+
+
+def _apply_smatrix_fused(peps, v1, v2, x, memo=None):
     ad.requires_grad_(v1, True)
     nt = len(peps.alltensors())
     p2 = P.load_variables(peps, v2.data if isinstance(v2, DiffTensor) else v2)          # plain device tensors
     xs = P.load_variables(peps, x.data if isinstance(x, DiffTensor) else x).alltensors()
     code = peps.code_inner_product
     ket = [P._dev(t) for t in p2.alltensors()]
-    n2sq = es.contract_tree_device(code, ket + ket, [1] * nt + [0] * nt).item()       # <psi2|psi2>
+    if memo is not None and "n2sq" in memo:
+        n2sq = memo["n2sq"]
+    else:
+        n2sq = es.contract_tree_device(code, ket + ket, [1] * nt + [0] * nt).item()   # <psi2|psi2>
+        if memo is not None:
+            memo["n2sq"] = n2sq
     n2 = float(np.sqrt(abs(n2sq)))
     site_terms = [(1.0 + 0j, [(nt + s, P._dev(xs[s]))]) for s in range(nt)]
     dval, _ = es.expect_terms_device(code, ket + ket, [1] * nt + [0] * nt, site_terms)  # <psi2|dpsi2>
@@ -81,7 +103,7 @@ def _apply_smatrix_fused(peps, v1, v2, x):
 
     def z_of(v):
         pl = P.load_variables(peps, v)
-        pl = P.mul(pl, _inv(P.norm(pl)))
+        pl = P.mul(pl, _inv(_norm_memo(pl, memo)))
         return _real(P._expect_fused(terms, pl, p2, (0, 1)))
     return ad.gradient(z_of, v1)[0]
 
@@ -136,9 +158,11 @@ def sr_step(peps, h, tol=1e-10, maxiter=200):
     v = P.variables(peps).to_numpy()
     n = v.size
 
+    memo = {}   # v1 = v2 = variables(peps) for every matvec: the x-independent contractions run once per solve
+
     def matvec(xr):
         xc = xr[:n] + 1j * xr[n:]
-        sx = apply_smatrix(peps, DiffTensor(v.copy()), DiffTensor(v.copy()), DiffTensor(xc, requires_grad=False)).to_numpy()
+        sx = apply_smatrix(peps, DiffTensor(v.copy()), DiffTensor(v.copy()), DiffTensor(xc, requires_grad=False), memo=memo).to_numpy()
         return np.concatenate([sx.real, sx.imag])
     b = -1j * fvec(peps, h).to_numpy()
     op = sla.LinearOperator((2 * n, 2 * n), matvec=matvec, dtype=np.float64)

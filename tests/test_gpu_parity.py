@@ -166,6 +166,16 @@ def test_apply_smatrix_tree_level_vs_taped_and_oracle(tne):
     ref = OTE.apply_smatrix(op, OAD.DiffTensor(v.copy()), OAD.DiffTensor(v.copy()), OAD.DiffTensor(x, requires_grad=False)).data
     got = tne.apply_smatrix(dp, tne.DiffTensor(v.copy()), tne.DiffTensor(v.copy()), tne.DiffTensor(x, requires_grad=False)).to_numpy()
     assert rel(got, ref) < 1e-9
+    # the memo of sr_step's GMRES loop (same v1 = v2 for every product): x-independent contractions run once
+    memo = {}
+    launches = []
+    for xk in (x, crand(rng, v.size) / np.sqrt(2)):
+        refk = OTE.apply_smatrix(op, OAD.DiffTensor(v.copy()), OAD.DiffTensor(v.copy()), OAD.DiffTensor(xk, requires_grad=False)).data
+        l0 = tne.context().launch_count()
+        gotk = tne.apply_smatrix(dp, tne.DiffTensor(v.copy()), tne.DiffTensor(v.copy()), tne.DiffTensor(xk, requires_grad=False), memo=memo).to_numpy()
+        launches.append(tne.context().launch_count() - l0)
+        assert rel(gotk, refk) < 1e-9
+    assert set(memo) == {"n2sq", "norm"} and launches[1] < launches[0]
 
 
 def test_normalized_overlap_gradient_zero(tne):  # test/timeevolve.jl:37-48
