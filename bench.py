@@ -194,6 +194,9 @@ def run_gpu(args):
         ctx.set_option("absorb_tma", int(os.environ["TNE_VARIANT"]))
     if os.environ.get("TNE_NO_PDL"):
         ctx.set_option("no_pdl", 1)
+    rs_comm = world > 1 and os.environ.get("TNE_RS_COMM", "0") == "1"
+    if rs_comm:   # reduce-scatter / all-gather of the column checkpoints (validated at world 2; all-reduce is the default)
+        ctx.set_option("rs_comm", 1)
     if world > 1:
         T.array.init_comm(ctx, dist, rank, world)
     L, D = args.L, args.D
@@ -350,7 +353,8 @@ def run_gpu(args):
             "dtype": "c128 (f64)", "data": "synthetic",
             "config": {"workload": "%dx%d D=%d SimplePEPS, Rydberg H (%d terms), energy + full gradient (%d complex variables)" % (L, L, D, K, nvars),
                        "plan": "boundary sweep, one checkpointed segment per column, D^2 segment-local slices",
-                       "parallelism": "1 GPU" if world == 1 else "segment-local bond slices dealt to %d GPUs, NCCL all-reduce of column checkpoints and outputs" % world,
+                       "parallelism": "1 GPU" if world == 1 else ("segment-local bond slices dealt to %d GPUs, NCCL %s of column checkpoints, all-reduce of the outputs"
+                                                                       % (world, "reduce-scatter / all-gather" if rs_comm else "all-reduce")),
                        "l2": "no flush needed: a step streams a %.0f GiB workspace (>> 126 MB L2)" % (ctx.mem_info()["workspace"] / 2 ** 30),
                        "seed": seed_for(L, D)},
             "executed_tflops_per_gpu": tot_flops / (prof_ms * 1e-3) / 1e12 if prof_ms else None,

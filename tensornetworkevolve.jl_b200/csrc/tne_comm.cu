@@ -9,6 +9,8 @@ typedef struct { char internal[128]; } nccl_uid;
 typedef int (*fn_get_uid)(nccl_uid*);
 typedef int (*fn_comm_init)(void**, int, nccl_uid, int);
 typedef int (*fn_allreduce)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*fn_reduce_scatter)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*fn_all_gather)(const void*, void*, size_t, int, void*, cudaStream_t);
 typedef int (*fn_group)(void);
 typedef const char* (*fn_errstr)(int);
 struct NcclApi {
@@ -16,6 +18,8 @@ struct NcclApi {
     fn_get_uid get_uid = nullptr;
     fn_comm_init comm_init = nullptr;
     fn_allreduce allreduce = nullptr;
+    fn_reduce_scatter reduce_scatter = nullptr;
+    fn_all_gather all_gather = nullptr;
     fn_group group_start = nullptr, group_end = nullptr;
     fn_errstr errstr = nullptr;
 };
@@ -32,6 +36,8 @@ int load_nccl(tne_ctx* ctx) {
     g_nccl.get_uid = (fn_get_uid)dlsym(g_nccl.lib, "ncclGetUniqueId");
     g_nccl.comm_init = (fn_comm_init)dlsym(g_nccl.lib, "ncclCommInitRank");
     g_nccl.allreduce = (fn_allreduce)dlsym(g_nccl.lib, "ncclAllReduce");
+    g_nccl.reduce_scatter = (fn_reduce_scatter)dlsym(g_nccl.lib, "ncclReduceScatter");
+    g_nccl.all_gather = (fn_all_gather)dlsym(g_nccl.lib, "ncclAllGather");
     g_nccl.group_start = (fn_group)dlsym(g_nccl.lib, "ncclGroupStart");
     g_nccl.group_end = (fn_group)dlsym(g_nccl.lib, "ncclGroupEnd");
     g_nccl.errstr = (fn_errstr)dlsym(g_nccl.lib, "ncclGetErrorString");
@@ -67,6 +73,31 @@ int comm_allreduce_ptr(tne_ctx* ctx, cplx* p, int64_t n) {
     if (rc != 0) return tne_fail(ctx, TNE_ERR_NCCL, "ncclAllReduce failed: %s", g_nccl.errstr ? g_nccl.errstr(rc) : "?");
     return TNE_OK;
 }
+
+// Blocks dealt round-robin to the ranks (block b belongs to rank b % world), `world` consecutive blocks per NCCL call,
+// in place (recvbuff = sendbuff + rank * count for the reduce-scatter, sendbuff = recvbuff + rank * count for the
+// all-gather: the in-place forms NCCL documents).
+static int comm_blocks(tne_ctx* ctx, cplx* p, int64_t block, int64_t nblocks, bool gather) {
+    if (ctx->world <= 1 || block <= 0 || nblocks <= 0) return TNE_OK;
+    if (!ctx->nccl) return tne_fail(ctx, TNE_ERR_NCCL, "tne_comm_init has not been called");
+    if (!g_nccl.reduce_scatter || !g_nccl.all_gather) return tne_fail(ctx, TNE_ERR_NCCL, "libnccl lacks ncclReduceScatter / ncclAllGather");
+    if (nblocks % ctx->world != 0) return tne_fail(ctx, TNE_ERR_INVALID, "%lld blocks cannot be dealt to %d ranks", (long long)nblocks, ctx->world);
+    const int NCCL_DOUBLE = 8, NCCL_SUM = 0;
+    const size_t count = (size_t)(2 * block);
+    int rc = g_nccl.group_start();
+    for (int64_t j = 0; j < nblocks / ctx->world && rc == 0; ++j) {
+        cplx* base = p + j * ctx->world * block;
+        cplx* mine = base + (int64_t)ctx->rank * block;
+        rc = gather ? g_nccl.all_gather(mine, base, count, NCCL_DOUBLE, ctx->nccl, ctx->stream)
+                    : g_nccl.reduce_scatter(base, mine, count, NCCL_DOUBLE, NCCL_SUM, ctx->nccl, ctx->stream);
+    }
+    int rc2 = g_nccl.group_end();
+    if (rc != 0 || rc2 != 0)
+        return tne_fail(ctx, TNE_ERR_NCCL, "%s failed: %s", gather ? "ncclAllGather" : "ncclReduceScatter", g_nccl.errstr ? g_nccl.errstr(rc ? rc : rc2) : "?");
+    return TNE_OK;
+}
+int comm_reduce_scatter_blocks(tne_ctx* ctx, cplx* p, int64_t block, int64_t nblocks) { return comm_blocks(ctx, p, block, nblocks, false); }
+int comm_all_gather_blocks(tne_ctx* ctx, cplx* p, int64_t block, int64_t nblocks) { return comm_blocks(ctx, p, block, nblocks, true); }
 
 extern "C" int tne_allreduce_sum(tne_ctx* ctx, int n, const tne_buf* bufs) {
     if (ctx->world <= 1) return TNE_OK;

@@ -272,6 +272,7 @@ extern "C" int tne_set_option(tne_ctx* ctx, const char* key, int64_t value) {
     else if (k == "no_pdl") ctx->opt_no_pdl = value;   // default 1: measured no gain from programmatic dependent launch
     else if (k == "no_reduce_tma") ctx->opt_no_reduce_tma = value;
     else if (k == "pad") ctx->opt_pad = value;
+    else if (k == "rs_comm") ctx->opt_rs_comm = value;
     else return tne_fail(ctx, TNE_ERR_INVALID, "unknown option '%s'", k.c_str());
     return TNE_OK;
 }

@@ -57,6 +57,7 @@ struct tne_ctx {
     int64_t opt_no_fuse = 0;               // 1: one launch per contribution (no gett_absorb_multi)
     int64_t opt_absorb_tma = 0;            // 1: TMA-staged absorb kernel where applicable (default: register-fed)
     int64_t opt_no_reduce_tma = 0;         // 1: register-fed reduce kernel instead of the TMA-staged one
+    int64_t opt_rs_comm = 0;               // 1: reduce-scatter / all-gather of column checkpoints instead of all-reduce (tne_tree.cu)
     struct ProfRec { cudaEvent_t e0, e1; int cls; double flops, bytes; };
     std::vector<ProfRec> prof;              // pending event pairs
     std::vector<cudaEvent_t> event_pool;
@@ -178,6 +179,11 @@ void contract_cost(const TensorRef& A, const TensorRef& B, const TensorRef& C, d
 
 // ---- multi-GPU (tne_comm.cu): in-place sum over the ranks of `n` complex elements at a device pointer
 int comm_allreduce_ptr(tne_ctx* ctx, cplx* p, int64_t n);
+// `nblocks` contiguous blocks of `block` complex elements at p, block b owned by rank b % world:
+// reduce-scatter: on return the blocks a rank owns hold the sum over ranks (the others are unspecified);
+// all-gather: every rank contributes the blocks it owns, on return all blocks are complete everywhere.
+int comm_reduce_scatter_blocks(tne_ctx* ctx, cplx* p, int64_t block, int64_t nblocks);
+int comm_all_gather_blocks(tne_ctx* ctx, cplx* p, int64_t block, int64_t nblocks);
 
 // ---- elementwise helpers used across units ---------------------------------------------
 int launch_fill_zero(tne_ctx* ctx, cplx* p, int64_t n);

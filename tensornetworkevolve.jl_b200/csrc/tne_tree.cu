@@ -417,6 +417,11 @@ struct Phase {
     std::vector<PhaseOp> ops;
     std::map<int, PView> views;
     std::vector<int> zero_at_start;   // checkpoint values this phase accumulates into
+    // how the checkpoints this phase produced are combined over the ranks when its slices are dealt to them (seg_shard):
+    // 0 all-reduce; 1 reduce-scatter (every consumer reads only the slices its rank owns); 2 all-gather (every rank wrote
+    // only the slices it owns).  block / nblocks: the contiguous slice blocks, block b owned by rank b % world.
+    struct Comm { int kind = 0; int64_t block = 0, nblocks = 0; };
+    std::map<int, Comm> comm;
     int64_t temp_bytes = 0;
 };
 
@@ -767,6 +772,60 @@ struct Exec {
         return TNE_OK;
     }
 
+    // the slices of value v, as phase ph loops over them, are `nsl` contiguous blocks in iteration order
+    bool contiguous_slices(const Phase& ph, int v, int64_t* block) const {
+        auto it = ph.views.find(v);
+        if (it == ph.views.end() || ph.nsl <= 1) return false;
+        const PView& pv = it->second;
+        const int64_t ext = extent_of(P.vals[v]);
+        if (ext % ph.nsl != 0) return false;
+        int64_t want = ext / ph.nsl;
+        *block = want;
+        for (size_t q = 0; q < ph.ssz.size(); ++q) {
+            if (pv.sl_stride[q] != want) return false;
+            want *= ph.ssz[q];
+        }
+        return true;
+    }
+
+    // Decide, per checkpoint a sliced phase produces, which collective combines it over the ranks (option rs_comm).
+    // A forward checkpoint is a sum over the producer's slices of a tensor that carries the NEXT column's sliced legs: if
+    // every later phase that touches it loops over those legs (and they are its slowest ones), a rank only ever reads the
+    // slices it owns -> reduce-scatter.  A cotangent checkpoint carries the producer's own sliced legs: every rank writes
+    // only the slices it owns -> all-gather.  Anything else keeps the all-reduce.  Half the NVLink traffic either way.
+    void plan_comm(int world) {
+        for (size_t pi = 0; pi < phases.size(); ++pi) {
+            Phase& ph = phases[pi];
+            ph.comm.clear();
+            if (!ctx->opt_rs_comm || world <= 1 || ph.nsl <= 1) continue;
+            for (int v : ph.zero_at_start) {
+                Phase::Comm c;
+                const PView& pv = ph.views.at(v);
+                bool all_sliced = !pv.sl_stride.empty(), none_sliced = true;
+                for (auto st : pv.sl_stride) { if (st == 0) all_sliced = false; else none_sliced = false; }
+                int64_t block = 0;
+                if (all_sliced && ph.nsl % world == 0 && contiguous_slices(ph, v, &block)) {
+                    c.kind = 2; c.block = block; c.nblocks = ph.nsl;
+                } else if (none_sliced) {
+                    bool ok = true, any = false;
+                    int64_t nb = 0;
+                    for (size_t pj = 0; pj < phases.size() && ok; ++pj) {
+                        if (pj == pi || !phases[pj].views.count(v)) continue;
+                        const Phase& cons = phases[pj];
+                        int64_t b2 = 0;
+                        if (cons.nsl % world != 0 || !contiguous_slices(cons, v, &b2)) { ok = false; break; }
+                        for (int z : cons.zero_at_start) if (z == v) ok = false;          // a second writer
+                        for (auto& po : cons.ops) if (po.op.out == v) ok = false;
+                        if (any && (b2 != block || cons.nsl != nb)) ok = false;
+                        block = b2; nb = cons.nsl; any = true;
+                    }
+                    if (ok && any) { c.kind = 1; c.block = block; c.nblocks = nb; }
+                }
+                ph.comm[v] = c;
+            }
+        }
+    }
+
     int site2_launch(const PhaseOp& po, const cplx* A, const cplx* B1, const cplx* B2, cplx* C) {
         if (!ctx->opt_profile) return site2_run(ctx, *po.s2, A, B1, B2, C);
         tne_ctx::ProfRec r;
@@ -805,6 +864,19 @@ struct Exec {
             }
         fprintf(stderr, "[tne-plan] %zu phases, %lld launches, %.4e flops, workspace %.3f GiB (checkpoints %.3f + segment %.3f)\n", phases.size(),
                 tot_launches, tot_flops, (persist_bytes + temp_bytes) / 1073741824.0, persist_bytes / 1073741824.0, temp_bytes / 1073741824.0);
+        for (size_t pi = 0; pi < phases.size(); ++pi) {
+            const Phase& ph = phases[pi];
+            if (ph.nsl <= 1 || ph.zero_at_start.empty()) continue;
+            double by[3] = {0, 0, 0};
+            int n[3] = {0, 0, 0};
+            for (int v : ph.zero_at_start) {
+                auto ci = ph.comm.find(v);
+                const int k = ci == ph.comm.end() ? 0 : ci->second.kind;
+                by[k] += 16.0 * (double)extent_of(P.vals[v]); n[k]++;
+            }
+            fprintf(stderr, "[tne-plan] phase %zu seg %d %s: checkpoints combined by all-reduce %d (%.2f GiB), reduce-scatter %d (%.2f GiB), all-gather %d (%.2f GiB)\n",
+                    pi, ph.seg, ph.backward ? "bwd" : "fwd", n[0], by[0] / 1073741824.0, n[1], by[1] / 1073741824.0, n[2], by[2] / 1073741824.0);
+        }
         if (ctx->opt_debug == 2) return;   // summary only
         for (size_t pi = 0; pi < phases.size(); ++pi) {
             const Phase& ph = phases[pi];
@@ -881,7 +953,13 @@ struct Exec {
                 }
             }
             if (sharded)
-                for (int v : ph.zero_at_start) TNE_TRY(comm_allreduce_ptr(ctx, base_ptr(ph, v), extent_of(P.vals[v])));
+                for (int v : ph.zero_at_start) {
+                    auto ci = ph.comm.find(v);
+                    const int kind = ci == ph.comm.end() ? 0 : ci->second.kind;
+                    if (kind == 1) TNE_TRY(comm_reduce_scatter_blocks(ctx, base_ptr(ph, v), ci->second.block, ci->second.nblocks));
+                    else if (kind == 2) TNE_TRY(comm_all_gather_blocks(ctx, base_ptr(ph, v), ci->second.block, ci->second.nblocks));
+                    else TNE_TRY(comm_allreduce_ptr(ctx, base_ptr(ph, v), extent_of(P.vals[v])));
+                }
         }
         return TNE_OK;
     }
@@ -967,6 +1045,11 @@ extern "C" int tne_expect_terms(tne_ctx* ctx, const tne_tree* tree, const tne_bu
     {
         int rc = E.build(tree, n_grad > 0);
         if (rc) return fail_cleanup(rc);
+    }
+    {
+        int w = E.seg_shard ? ctx->world : 1;
+        if (ctx->plan_only && ctx->opt_rs_comm > 1) w = (int)ctx->opt_rs_comm;   // planner: rs_comm = the world size to plan for
+        E.plan_comm(w);
     }
     if (ctx->opt_debug > 2 || ctx->plan_only) E.dump_final();
     if (ctx->plan_only)
