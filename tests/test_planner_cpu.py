@@ -99,3 +99,35 @@ print("SWEEP-PLAN-OK")
 ''' % ROOT
     res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert "SWEEP-PLAN-OK" in res.stdout, res.stdout + res.stderr[-2000:]
+
+
+def test_checkpoint_exchange_plan_for_8_ranks():
+    """Option rs_comm (planner: its value is the world size to plan for): at 6x6 D=4 every forward checkpoint of a sliced column
+    qualifies for a reduce-scatter (its consumers loop over its slowest legs) and every cotangent checkpoint for an all-gather."""
+    code = r'''
+import os, sys
+os.environ["TNE_PLAN_ONLY"] = "1"
+sys.path.insert(0, %r)
+import numpy as np
+import tne_b200 as T
+from tne_b200 import peps as P, einsum as es
+ctx = T.context(); ctx.set_option("debug", 2); ctx.set_option("rs_comm", 8)
+L, D = 6, 4
+g = T.grid([L, L]); order, segs = T.sweep_plan(g, L)
+p = T.rand_simplepeps(g, D, np.random.default_rng(1), optimizer=order, segments=segs)
+h = T.rydberg_hamiltonian(g, 10.0, 0.2, 0.3)
+nt = L * L
+cache = {}
+terms = [P._term_replacements(p, t, cache) for t in h.blocks]
+tl = [(c, [(nt + s - 1, t) for s, t in sorted(r.items())]) for c, r in terms]
+leaves = [P._dev(t) for t in p.alltensors()] * 2
+try:
+    es.expect_terms_device(p.code_inner_product, leaves, [1] * nt + [0] * nt, tl, list(range(nt)), 1 + 0j)
+except T.TneError:
+    pass
+''' % ROOT
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    rows = re.findall(r"checkpoints combined by all-reduce (\d+) .*?reduce-scatter (\d+) .*?all-gather (\d+)", res.stderr)
+    assert len(rows) == 9, res.stderr[-2000:]
+    ar, rs, ag = (sum(int(r[k]) for r in rows) for k in range(3))
+    assert ar == 0 and rs == 32 and ag == 40
