@@ -114,6 +114,51 @@ function (ne::NestedEinsum)(xs::B200Array...; slicing = Int32[], conj_flags = ze
 end
 (se::SlicedEinsum)(xs::B200Array...) = se.eins(xs...; slicing = Int32.(se.slicing))
 
+# ---- Yao.expect(op::Add, pa, pb) fused fast path (src/peps.jl:469-477): ONE tne_expect_terms call ---------------------
+# The reference contracts the whole network once per term; the library shares sub-contractions between the terms
+# (term dynamic programme) and, with grad_leaves, returns the pullbacks of the bra leaves from the same programme
+# (this is what the `einsum` rule of TensorAD sees as one instruction; mirror of peps.py::_expect_fused).
+struct TneTerm          # layout of `tne_term` in include/tne.h
+    n_repl::Int32
+    leaf::NTuple{4,Int32}
+    repl::NTuple{4,Int64}
+    coef_re::Cdouble; coef_im::Cdouble
+end
+# terms: Vector of (coef, [(site, 2x2 matrix), ...]) -- one-site-product terms (kron / put of one-site blocks);
+# the replaced ket leaf of a term is apply_onsite(pb, site, matrix) (src/peps.jl:338-347), built with tne_einsum
+function expect_terms(pa::TensorNetworkEvolve.PEPS, pb::TensorNetworkEvolve.PEPS, terms; grad_leaves = Int32[])
+    code = pa.code_inner_product
+    ne = code isa SlicedEinsum ? code.eins : code
+    slicing = code isa SlicedEinsum ? Int32.(code.slicing) : Int32[]
+    nt = length(TensorNetworkEvolve.alltensors(pa))
+    bra, ket = TensorNetworkEvolve.alltensors(pa), TensorNetworkEvolve.alltensors(pb)
+    leaves = Int64[t.handle for t in vcat(bra, ket)]
+    conj_flags = vcat(ones(Int32, nt), zeros(Int32, nt))          # bra leaves enter conjugated (src/peps.jl:107)
+    keep = B200Array[]                                             # replaced leaves must outlive the call
+    cterms = TneTerm[]
+    for (coef, repl) in terms
+        ls, hs = zeros(Int32, 4), zeros(Int64, 4)
+        for (k, (site, m)) in enumerate(repl)
+            t = TensorNetworkEvolve.apply_onsite(pb, site, B200Array(ComplexF64.(m))).vertex_tensors[site]
+            push!(keep, t); ls[k] = nt + site - 1; hs[k] = t.handle
+        end
+        push!(cterms, TneTerm(length(repl), Tuple(ls), Tuple(hs), real(coef), imag(coef)))
+    end
+    leaf_ixs = OMEinsum.getixsv(ne)
+    children, out_rank, out_labels = serialize(ne, leaf_ixs)
+    lr = Int32[length(ix) for ix in leaf_ixs]; ll = Int32[l for ix in leaf_ixs for l in ix]
+    val = Ref{Int64}(0); grads = zeros(Int64, max(1, length(grad_leaves)))
+    GC.@preserve lr ll children out_rank out_labels slicing keep begin
+        t = Ref(TneTree(2nt, length(out_rank), pointer(lr), pointer(ll), pointer(children), pointer(out_rank),
+                        pointer(out_labels), length(slicing), pointer(slicing), 0, 1, 0, 0, C_NULL, C_NULL, C_NULL))
+        check(ccall((:tne_expect_terms, LIB[]), Cint,
+                    (Ptr{Cvoid}, Ptr{TneTree}, Ptr{Int64}, Ptr{Int32}, Cint, Ptr{TneTerm}, Cint, Ptr{Int32}, Cdouble, Cdouble, Ptr{Int64}, Ptr{Int64}),
+                    CTX[], t, leaves, conj_flags, length(cterms), cterms, length(grad_leaves), grad_leaves, 1.0, 0.0, val, grads))
+    end
+    value = B200Array{ComplexF64,0}(val[], ())
+    return isempty(grad_leaves) ? value : (value, [B200Array{ComplexF64,ndims(bra[g + 1])}(grads[k], size(bra[g + 1])) for (k, g) in enumerate(grad_leaves)])
+end
+
 # ---- Base / broadcast methods TensorAD's rules and src/peps.jl:283-295 call on tensors -----------------------------
 const MAP = Dict(:copy => 0, :conj => 1, :real => 2, :imag => 3, :abs => 4, :sqrt => 5, :inv => 6, :neg => 7, :scale => 8, :pow => 9)
 function tne_map(op::Symbol, x::B200Array{T,N}, s::Number = 0.0; RT = T) where {T,N}
