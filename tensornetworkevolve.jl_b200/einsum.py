@@ -305,6 +305,123 @@ def optimize_sequence(ixs, iy, order):
     return cur
 
 
+def optimize_treesa(ixs, iy, size_dict, sc_target=None, betas=None, ntrials=1, niters=20, sc_weight=3.0, seed=0):
+    """Simulated annealing over binary contraction trees (the role of OMEinsumContractionOrders' ``TreeSA``, which the
+    reference's tests use: ``TreeSA(ntrials=1, nslices=...)``, test/peps.jl:9).  Starts from the greedy tree and applies
+    the local rewrites of Kalachev et al. -- ``((a b) c) -> ((a c) b)`` or ``(a (b c))`` and their mirror images -- accepted
+    with the Metropolis rule on ``log2(flops) + sc_weight * max(0, log2(largest intermediate) - sc_target)``.  Deterministic
+    for a given ``seed`` (the reference's optimiser is randomised).  Host-side only; the result is an ordinary NestedEinsum."""
+    rng = np.random.default_rng(seed)
+    ixs = [list(ix) for ix in ixs]
+    iy = list(iy)
+    n = len(ixs)
+    lsz = {l: float(np.log2(size_dict[l])) for ix in ixs for l in ix}
+    for l in iy:
+        lsz.setdefault(l, float(np.log2(size_dict[l])))
+    ext = {}                      # label -> number of tensors (plus the output) it sits on
+    for ix in ixs:
+        for l in set(ix):
+            ext[l] = ext.get(l, 0) + 1
+    for l in iy:
+        ext[l] = ext.get(l, 0) + 1
+
+    # a tree is a nested tuple of leaf indices; labels of a subtree = labels that still have an owner outside it
+    def from_nested(nd):
+        return nd.tensorindex if nd.isleaf() else (from_nested(nd.args[0]), from_nested(nd.args[1]))
+
+    def counts(t, acc):
+        if isinstance(t, tuple):
+            counts(t[0], acc); counts(t[1], acc)
+        else:
+            for l in set(ixs[t]):
+                acc[l] = acc.get(l, 0) + 1
+        return acc
+
+    def out_labels(t):
+        inside = counts(t, {})
+        return [l for l, c in inside.items() if ext[l] - c > 0]
+
+    def cost(t):
+        """(log2 sum of flops, log2 of the largest intermediate) of the whole tree."""
+        tcs, sc = [], [0.0]
+
+        def walk(u):
+            if not isinstance(u, tuple):
+                return set(ixs[u]), counts(u, {})
+            la, ca = walk(u[0])
+            lb, cb = walk(u[1])
+            c = dict(ca)
+            for l, k in cb.items():
+                c[l] = c.get(l, 0) + k
+            out = {l for l in (la | lb) if ext[l] - c[l] > 0}
+            tcs.append(sum(lsz[l] for l in (la | lb)))
+            sc[0] = max(sc[0], sum(lsz[l] for l in out))
+            return out, c
+        walk(t)
+        m = max(tcs)
+        return m + float(np.log2(sum(2.0 ** (x - m) for x in tcs))), sc[0]
+
+    def score(t):
+        tc, sc = cost(t)
+        return tc + (sc_weight * max(0.0, sc - sc_target) if sc_target is not None else 0.0)
+
+    def subtrees(t, path=()):
+        if isinstance(t, tuple):
+            yield path
+            yield from subtrees(t[0], path + (0,))
+            yield from subtrees(t[1], path + (1,))
+
+    def get(t, path):
+        for k in path:
+            t = t[k]
+        return t
+
+    def put(t, path, new):
+        if not path:
+            return new
+        k = path[0]
+        return (put(t[0], path[1:], new), t[1]) if k == 0 else (t[0], put(t[1], path[1:], new))
+
+    def rewrites(u):
+        a, b = u
+        out = []
+        if isinstance(a, tuple):
+            out += [((a[0], b), a[1]), (a[0], (a[1], b))]
+        if isinstance(b, tuple):
+            out += [((a, b[0]), b[1]), (b[0], (a, b[1]))]
+        return out
+
+    start = from_nested(optimize_greedy(ixs, iy, size_dict))
+    if betas is None:
+        betas = np.arange(0.5, 12.0, 0.5)
+    best = (score(start), start)
+    nit = niters if niters else 1
+    for _ in range(max(1, ntrials)):
+        cur, cur_s = start, score(start)
+        for beta in betas:
+            for _ in range(max(nit, 2 * n)):
+                paths = list(subtrees(cur))
+                path = paths[int(rng.integers(len(paths)))]
+                opts = rewrites(get(cur, path))
+                if not opts:
+                    continue
+                cand = put(cur, path, opts[int(rng.integers(len(opts)))])
+                cs = score(cand)
+                if cs <= cur_s or rng.random() < np.exp(-beta * (cs - cur_s)):
+                    cur, cur_s = cand, cs
+                    if cur_s < best[0]:
+                        best = (cur_s, cur)     # the best tree visited, not the last one
+
+    def to_nested(t, root=False):
+        if not isinstance(t, tuple):
+            return NestedEinsum(tensorindex=t), list(ixs[t])
+        na, la = to_nested(t[0])
+        nb, lb = to_nested(t[1])
+        out = list(iy) if root else [l for l in dict.fromkeys(la + lb) if l in set(out_labels(t))]
+        return NestedEinsum([na, nb], EinCode([la, lb], out)), out
+    return to_nested(best[1], root=True)[0]
+
+
 def pick_slices(nested, iy, size_dict, nslices):
     inter = []
 
@@ -327,7 +444,7 @@ def pick_slices(nested, iy, size_dict, nslices):
 def optimize_code(ixs, iy, size_dict, optimizer="greedy", nslices=0, slicing=None, segments=None):
     """``optimize_code(EinCode(ixs, iy), size_dict, optimizer, simplifier)`` (src/peps.jl:87,91).
 
-    ``optimizer``: ``"greedy"`` or an explicit leaf order (list).  ``nslices`` / ``slicing``
+    ``optimizer``: ``"greedy"``, ``"treesa"`` (simulated annealing from the greedy tree) or an explicit leaf order (list).  ``nslices`` / ``slicing``
     produce a ``SlicedEinsum`` (the role of ``TreeSA(nslices=k)``, test/peps.jl:9).
     ``segments`` (explicit leaf order only): ``[(position in the order, [labels]), ...]`` -- a
     checkpointed segment starts at the node that absorbs ``order[position]`` and loops over the
@@ -339,6 +456,8 @@ def optimize_code(ixs, iy, size_dict, optimizer="greedy", nslices=0, slicing=Non
         if segments:
             # a segment starts at the first node created for order[pos] (post-order numbering)
             nested.segments = [(nested.first_node_of_item[pos], list(ls)) for pos, ls in segments]
+    elif optimizer == "treesa":
+        nested = optimize_treesa(ixs, iy, size_dict)
     else:
         nested = optimize_greedy(ixs, iy, size_dict)
     if slicing:

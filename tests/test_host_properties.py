@@ -58,8 +58,10 @@ def test_optimisers_produce_valid_trees(net, seed):
     rng = np.random.default_rng(seed)
     xs = [rng.standard_normal([sizes[l] for l in ix]) + 1j * rng.standard_normal([sizes[l] for l in ix]) for ix in ixs]
     want = _reference(ixs, iy, xs)
-    for opt in ("greedy", list(rng.permutation(len(ixs)))):
+    costs = {}
+    for opt in ("greedy", "treesa", list(rng.permutation(len(ixs)))):
         code = es.optimize_code(ixs, iy, sizes, opt)
+        costs[str(opt)] = es.tree_cost(code, sizes)[0]
         leaves = []
 
         def walk(nd):
@@ -73,6 +75,7 @@ def test_optimisers_produce_valid_trees(net, seed):
         assert sorted(leaves) == list(range(len(ixs)))          # every tensor exactly once, binary nodes only
         got = _evaluate(code, xs)
         assert got.shape == want.shape and np.allclose(got, want, rtol=1e-10, atol=1e-10)
+    assert costs["treesa"] <= costs["greedy"] * (1 + 1e-12)     # annealing starts from the greedy tree and keeps the best one
 
 
 @settings(max_examples=100, deadline=None)
