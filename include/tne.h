@@ -82,10 +82,17 @@ void* tne_device_ptr(tne_ctx* ctx, tne_buf buf);
  * Call sites: src/peps.jl:334,344,373,376,392-393,429; src/TensorAD/rules.jl:2-5 (forward and
  * einsum_grad); src/timeevolve.jl:38.  `labels_flat` concatenates the inputs' labels,
  * `conj_flags[i] != 0` conjugates input i while it is loaded (fuses the conj copies of
- * src/peps.jl:107 and of einsum_grad).  Repeated labels inside one tensor are unsupported. */
+ * src/peps.jl:107 and of einsum_grad). */
 int tne_einsum(tne_ctx* ctx, int n_in, const int32_t* labels_flat, const int32_t* ranks,
                const tne_buf* in, const int32_t* conj_flags,
                const int32_t* out_labels, int out_rank, tne_buf* out);
+/* The same with OMEinsum's `size_dict` argument: sizes of labels that only the output carries (the "repeat" rule, e.g.
+ * the pullback of ein"ii->" is ein"->ii").  A label repeated inside one operand reads its diagonal (trace / diag
+ * rules); repeated inside the output, only the diagonal is written and the rest is zero. */
+int tne_einsum_sized(tne_ctx* ctx, int n_in, const int32_t* labels_flat, const int32_t* ranks,
+                     const tne_buf* in, const int32_t* conj_flags,
+                     const int32_t* out_labels, int out_rank,
+                     int n_sizes, const int32_t* size_labels, const int64_t* size_values, tne_buf* out);
 
 /* ---- Base / broadcast methods used by src/TensorAD/rules.jl and src/peps.jl:283-295 ----- */
 enum tne_map_op {

@@ -1,24 +1,23 @@
 # TensorNetworkEvolveB200.jl -- the reference-side binding of libtne_b200.so (include/tne.h).
 #
-# NOT EXECUTED in the build environment (no Julia runtime in the image or on the GPU boxes); it mirrors, call for
-# call, the ctypes binding `tensornetworkevolve.jl_b200/_lib.py` + `array.py` that the tests drive.  A maintainer of
-# TensorNetworkEvolve.jl adds this file, `include`s it after `src/TensorAD/TensorAD.jl`, and converts a PEPS with
-# `to_b200(peps)`; every method below hooks the SAME dispatch point the in-tree plug-ins use
+# NOT EXECUTED in the build environment (no Julia runtime in the image or on the GPU boxes).  It mirrors, call for
+# call, the ctypes binding `tensornetworkevolve.jl_b200/_lib.py` + `array.py` that the tests drive, and every `ccall`
+# below is checked mechanically against the prototypes of include/tne.h by tools/check_julia_ccalls.py (a CPU test).
+# A maintainer of TensorNetworkEvolve.jl adds this file, `include`s it at the end of src/TensorNetworkEvolve.jl and
+# converts a PEPS with `to_b200(peps)`; every method below hooks the SAME dispatch point the in-tree plug-ins use
 # (`OMEinsum.einsum(code, xs, size_dict)`: src/TensorAD/rules.jl:1-8, src/cracker.jl:4-8).
 module TensorNetworkEvolveB200
 
 using OMEinsum, LinearAlgebra
 using Graphs: edges, src, dst, degree
 using Yao: put, mat, time_evolve
-using ..TensorNetworkEvolve: cterm, xterm, zterm
+import ..TensorNetworkEvolve
+using ..TensorNetworkEvolve: cterm, xterm, zterm, PEPS, SimplePEPS, VidalPEPS, alltensors, replace_tensors
+using ..TensorNetworkEvolve.TensorAD: DiffTensor, difftensor, debug_info, projectto
 using OMEinsum: DynamicEinCode, StaticEinCode, NestedEinsum, SlicedEinsum, getixsv, getiyv
 
 const LIB = Ref{String}("libtne_b200.so")
 const CTX = Ref{Ptr{Cvoid}}(C_NULL)
-
-struct TneError <: Exception
-    msg::String
-end
 
 function check(rc::Cint)
     rc == 0 && return
@@ -27,12 +26,14 @@ end
 
 function __init__()
     ctx = Ref{Ptr{Cvoid}}(C_NULL)
-    rc = ccall((:tne_ctx_create, LIB[]), Cint, (Cint, Ptr{Ptr{Cvoid}}), parse(Int, get(ENV, "LOCAL_RANK", "0")), ctx)
+    rc = ccall((:tne_ctx_create, LIB[]), Cint, (Cint, Ptr{Ptr{Cvoid}}), parse(Cint, get(ENV, "LOCAL_RANK", "0")), ctx)
     rc == 0 || error("tne_ctx_create failed: there is no CPU fallback, a B200 is required")
     CTX[] = ctx[]
 end
 
 # ---- device array: slots into `vertex_tensors::Vector{<:AbstractArray{T}}` (src/peps.jl:41) and DiffTensor ------
+# Storage on the device is always ComplexF64; `T` only records whether the Julia-side element type is real (norms,
+# singular values), exactly like `is_real` in array.py.
 mutable struct B200Array{T,N} <: AbstractArray{T,N}
     handle::Int64
     dims::NTuple{N,Int}
@@ -43,6 +44,13 @@ mutable struct B200Array{T,N} <: AbstractArray{T,N}
     end
 end
 Base.size(x::B200Array) = x.dims
+Base.IndexStyle(::Type{<:B200Array}) = IndexLinear()
+# scalar indexing works (AbstractArray fallbacks such as `≈`, `iterate`, `collect` rely on it) but downloads the whole
+# tensor: the hot path never calls it, it is there so that generic code and the REPL do not hit a MethodError
+Base.getindex(x::B200Array, i::Int) = Array(x)[i]
+Base.getindex(x::B200Array{T,0}) where T = Array(x)[]
+Base.show(io::IO, x::B200Array{T,N}) where {T,N} = print(io, "B200Array{$T,$N}(handle=$(x.handle), size=$(x.dims))")
+Base.show(io::IO, ::MIME"text/plain", x::B200Array) = show(io, x)
 
 function B200Array(a::AbstractArray{T,N}) where {T,N}
     host = Array{ComplexF64,N}(a)                     # interleaved ComplexF64, column-major
@@ -57,19 +65,22 @@ function Base.Array(x::B200Array{T,N}) where {T,N}
     GC.@preserve host check(ccall((:tne_download, LIB[]), Cint, (Ptr{Cvoid}, Int64, Ptr{Cvoid}), CTX[], x.handle, pointer(host)))
     return T <: Real ? real.(host) : host
 end
-Base.getindex(x::B200Array{T,0}) where T = Array(x)[]
 
 # ---- OMEinsum.einsum: unary and binary (peps.jl:334,344,373,376,392-393,429; rules.jl:2-5; timeevolve.jl:38) -----
+# `size_dict` is forwarded for labels that only the output carries (OMEinsum's repeat rule, e.g. the pullback of a trace)
 function OMEinsum.einsum(code::Union{DynamicEinCode,StaticEinCode}, xs::NTuple{N,B200Array}, size_dict::Dict) where N
     ixs, iy = getixsv(code), getiyv(code)
     flat = Int32[l for ix in ixs for l in ix]
     ranks = Int32[length(ix) for ix in ixs]
+    extra = Int32[l for l in unique(iy) if all(ix -> !(l in ix), ixs)]
+    sizes = Int64[size_dict[l] for l in extra]
     h = Ref{Int64}(0)
-    check(ccall((:tne_einsum, LIB[]), Cint,
-                (Ptr{Cvoid}, Cint, Ptr{Int32}, Ptr{Int32}, Ptr{Int64}, Ptr{Int32}, Ptr{Int32}, Cint, Ptr{Int64}),
-                CTX[], N, flat, ranks, Int64[x.handle for x in xs], zeros(Int32, N), Int32.(iy), length(iy), h))
+    check(ccall((:tne_einsum_sized, LIB[]), Cint,
+                (Ptr{Cvoid}, Cint, Ptr{Int32}, Ptr{Int32}, Ptr{Int64}, Ptr{Int32}, Ptr{Int32}, Cint, Cint, Ptr{Int32}, Ptr{Int64}, Ptr{Int64}),
+                CTX[], N, flat, ranks, Int64[x.handle for x in xs], zeros(Int32, N), Int32.(iy), length(iy),
+                length(extra), extra, sizes, h))
     T = promote_type(map(eltype, xs)...)
-    return B200Array{T,length(iy)}(h[], ntuple(k -> size_dict[iy[k]], length(iy)))
+    return B200Array{T,length(iy)}(h[], ntuple(k -> Int(size_dict[iy[k]]), length(iy)))
 end
 
 # ---- (::NestedEinsum)(xs...) / (::SlicedEinsum)(xs...) fast path (peps.jl:109,321): one tne_contract_tree call ----
@@ -110,7 +121,7 @@ function (ne::NestedEinsum)(xs::B200Array...; slicing = Int32[], conj_flags = ze
     end
     iy = getiyv(ne.eins)
     sd = OMEinsum.get_size_dict(leaf_ixs, xs)
-    return B200Array{ComplexF64,length(iy)}(h[], ntuple(k -> sd[iy[k]], length(iy)))
+    return B200Array{ComplexF64,length(iy)}(h[], ntuple(k -> Int(sd[iy[k]]), length(iy)))
 end
 (se::SlicedEinsum)(xs::B200Array...) = se.eins(xs...; slicing = Int32.(se.slicing))
 
@@ -126,12 +137,12 @@ struct TneTerm          # layout of `tne_term` in include/tne.h
 end
 # terms: Vector of (coef, [(site, 2x2 matrix), ...]) -- one-site-product terms (kron / put of one-site blocks);
 # the replaced ket leaf of a term is apply_onsite(pb, site, matrix) (src/peps.jl:338-347), built with tne_einsum
-function expect_terms(pa::TensorNetworkEvolve.PEPS, pb::TensorNetworkEvolve.PEPS, terms; grad_leaves = Int32[])
+function expect_terms(pa::PEPS, pb::PEPS, terms; grad_leaves = Int32[])
     code = pa.code_inner_product
     ne = code isa SlicedEinsum ? code.eins : code
     slicing = code isa SlicedEinsum ? Int32.(code.slicing) : Int32[]
-    nt = length(TensorNetworkEvolve.alltensors(pa))
-    bra, ket = TensorNetworkEvolve.alltensors(pa), TensorNetworkEvolve.alltensors(pb)
+    nt = length(alltensors(pa))
+    bra, ket = alltensors(pa), alltensors(pb)
     leaves = Int64[t.handle for t in vcat(bra, ket)]
     conj_flags = vcat(ones(Int32, nt), zeros(Int32, nt))          # bra leaves enter conjugated (src/peps.jl:107)
     keep = B200Array[]                                             # replaced leaves must outlive the call
@@ -160,7 +171,9 @@ function expect_terms(pa::TensorNetworkEvolve.PEPS, pb::TensorNetworkEvolve.PEPS
 end
 
 # ---- Base / broadcast methods TensorAD's rules and src/peps.jl:283-295 call on tensors -----------------------------
-const MAP = Dict(:copy => 0, :conj => 1, :real => 2, :imag => 3, :abs => 4, :sqrt => 5, :inv => 6, :neg => 7, :scale => 8, :pow => 9)
+# tne_map_op of include/tne.h
+const MAP = Dict(:copy => 0, :conj => 1, :real => 2, :imag => 3, :abs => 4, :sqrt => 5, :inv => 6, :neg => 7, :scale => 8, :pow => 9,
+                 :sin => 10, :cos => 11, :safe_inv => 12)
 function tne_map(op::Symbol, x::B200Array{T,N}, s::Number = 0.0; RT = T) where {T,N}
     h = Ref{Int64}(0)
     check(ccall((:tne_map, LIB[]), Cint, (Ptr{Cvoid}, Cint, Int64, Cdouble, Cdouble, Ptr{Int64}), CTX[], MAP[op], x.handle, real(s), imag(s), h))
@@ -169,13 +182,25 @@ end
 Base.conj(x::B200Array) = tne_map(:conj, x)
 Base.copy(x::B200Array) = tne_map(:copy, x)
 Base.real(x::B200Array{T}) where T = tne_map(:real, x; RT = real(T))
-Base.:*(x::B200Array, c::Number) = tne_map(:scale, x, c)
-Base.:*(c::Number, x::B200Array) = tne_map(:scale, x, c)
+Base.imag(x::B200Array{T}) where T = tne_map(:imag, x; RT = real(T))
+Base.zero(x::B200Array) = tne_map(:scale, x, 0.0)
+Base.:*(x::B200Array{T}, c::Number) where T = tne_map(:scale, x, c; RT = promote_type(T, typeof(c)))
+Base.:*(c::Number, x::B200Array) = x * c
+Base.:/(x::B200Array, c::Number) = x * inv(c)
 Base.:-(x::B200Array) = tne_map(:neg, x)
 Base.Broadcast.broadcasted(::typeof(abs), x::B200Array{T}) where T = tne_map(:abs, x; RT = real(T))
 Base.Broadcast.broadcasted(::typeof(sqrt), x::B200Array) = tne_map(:sqrt, x)
 Base.Broadcast.broadcasted(::typeof(inv), x::B200Array) = tne_map(:inv, x)
+Base.Broadcast.broadcasted(::typeof(sin), x::B200Array) = tne_map(:sin, x)
+Base.Broadcast.broadcasted(::typeof(cos), x::B200Array) = tne_map(:cos, x)
+Base.Broadcast.broadcasted(::typeof(conj), x::B200Array) = tne_map(:conj, x)
+Base.Broadcast.broadcasted(::typeof(real), x::B200Array{T}) where T = tne_map(:real, x; RT = real(T))
 Base.Broadcast.broadcasted(::typeof(^), x::B200Array, p::Real) = tne_map(:pow, x, p)
+Base.Broadcast.broadcasted(::typeof(Base.literal_pow), ::typeof(^), x::B200Array, ::Val{p}) where p = tne_map(:pow, x, p)
+Base.Broadcast.broadcasted(::Type{Complex}, x::B200Array{T}) where T = tne_map(:copy, x; RT = complex(T))      # rules.jl:158-162
+Base.Broadcast.broadcasted(::typeof(*), x::B200Array, c::Number) = x * c
+Base.Broadcast.broadcasted(::typeof(*), c::Number, x::B200Array) = x * c
+# tne_map2_op of include/tne.h: ADD 0, SUB 1, MUL 2, DIV 3 (an operand with one element broadcasts)
 function tne_map2(op::Int, a::B200Array, b::B200Array)
     h = Ref{Int64}(0)
     check(ccall((:tne_map2, LIB[]), Cint, (Ptr{Cvoid}, Cint, Int64, Int64, Ptr{Int64}), CTX[], op, a.handle, b.handle, h))
@@ -186,15 +211,37 @@ Base.:+(a::B200Array, b::B200Array) = tne_map2(0, a, b)
 Base.:-(a::B200Array, b::B200Array) = tne_map2(1, a, b)
 Base.:*(a::B200Array{T,0}, b::B200Array) where T = tne_map2(2, a, b)      # rules.jl:79-88
 Base.:*(a::B200Array, b::B200Array{T,0}) where T = tne_map2(2, a, b)
+Base.:*(a::B200Array{T1,0}, b::B200Array{T2,0}) where {T1,T2} = tne_map2(2, a, b)
+Base.Broadcast.broadcasted(::typeof(*), a::B200Array, b::B200Array) = tne_map2(2, a, b)
+Base.Broadcast.broadcasted(::typeof(/), a::B200Array, b::B200Array) = tne_map2(3, a, b)
+Base.Broadcast.broadcasted(::typeof(sign), x::B200Array) = tne_map2(3, x, tne_map(:abs, x))                     # x ./ abs.(x), rules.jl:155-157
+function Base.sum(x::B200Array{T}) where T                                   # rules.jl:91-93 (kept as a 0-dim device array)
+    h = Ref{Int64}(0)
+    check(ccall((:tne_reduce_sum, LIB[]), Cint, (Ptr{Cvoid}, Int64, Ptr{Int64}), CTX[], x.handle, h))
+    return B200Array{T,0}(h[], ())
+end
+function Base.fill(x::B200Array{T,0}, dims::Integer...) where T            # rules.jl:94-96 without a host round trip
+    h = Ref{Int64}(0)
+    check(ccall((:tne_fill, LIB[]), Cint, (Ptr{Cvoid}, Int64, Cint, Ptr{Int64}, Ptr{Int64}), CTX[], x.handle, length(dims), collect(Int64, dims), h))
+    return B200Array{T,length(dims)}(h[], Tuple(Int.(dims)))
+end
 function Base.reshape(x::B200Array{T}, dims::Dims{N}) where {T,N}
     h = Ref{Int64}(0)
     check(ccall((:tne_reshape, LIB[]), Cint, (Ptr{Cvoid}, Int64, Cint, Ptr{Int64}, Ptr{Int64}), CTX[], x.handle, N, collect(Int64, dims), h))
     return B200Array{T,N}(h[], dims)
 end
+Base.vec(x::B200Array) = reshape(x, (length(x),))
 function Base.getindex(x::B200Array{T,1}, r::UnitRange{Int}) where T     # variables[a:b], src/peps.jl:217
     h = Ref{Int64}(0)
     check(ccall((:tne_slice, LIB[]), Cint, (Ptr{Cvoid}, Int64, Int64, Int64, Ptr{Int64}), CTX[], x.handle, first(r) - 1, length(r), h))
     return B200Array{T,1}(h[], (length(r),))
+end
+# accum(zero(x), (a:b,), dy) of rules.jl:46-55 as one device op
+function TensorNetworkEvolve.TensorAD.accum(x::B200Array{T,1}, indices::Tuple{UnitRange{Int}}, y::B200Array) where T
+    h = Ref{Int64}(0)
+    r = indices[1]
+    check(ccall((:tne_embed, LIB[]), Cint, (Ptr{Cvoid}, Int64, Int64, Int64, Ptr{Int64}), CTX[], y.handle, first(r) - 1, length(x), h))
+    return x + B200Array{T,1}(h[], size(x))
 end
 function Base.vcat(xs::B200Array...)                                       # variables(peps), src/peps.jl:202
     h = Ref{Int64}(0)
@@ -202,6 +249,19 @@ function Base.vcat(xs::B200Array...)                                       # var
     return B200Array{promote_type(map(eltype, xs)...),1}(h[], (sum(length, xs),))
 end
 OMEinsum.asarray(x::Number, ::B200Array) = B200Array(fill(x))
+OMEinsum.asarray(x::B200Array, ::B200Array) = x
+
+# The rules that read a 0-dim operand on the host (`a.data[] * b.data`, `fill(a.data[], size...)`: rules.jl:79-96) get
+# device versions, so that the normalisation chain of iloss2 never synchronises.
+function Base.:(*)(a::DiffTensor{T1,0,<:B200Array}, b::DiffTensor{T2,N,<:B200Array}) where {T1,T2,N}
+    difftensor(a.data * b.data, debug_info("*", a, b), a => dy -> projectto(a, sum(dy .* conj(b))), b => dy -> projectto(b, dy * conj(a)))
+end
+function Base.:(*)(a::DiffTensor{T1,0,<:B200Array}, b::DiffTensor{T2,0,<:B200Array}) where {T1,T2}
+    difftensor(a.data * b.data, debug_info("*", a, b), a => dz -> projectto(a, conj(b) * dz), b => dz -> projectto(b, conj(a) * dz))
+end
+function Base.fill(a::DiffTensor{T,0,<:B200Array}, size::Integer...) where T
+    difftensor(fill(a.data, size...), debug_info("fill", a), a => dz -> sum(dz))
+end
 
 # ---- LinearAlgebra.svd on the bond matrix (src/peps.jl:381) and the fused apply_onbond! -------------------------------
 function LinearAlgebra.svd(a::B200Array{T,2}; Dmax = minimum(size(a)), ϵ = 0.0) where T
@@ -221,8 +281,12 @@ struct SweepGate                                   # mirrors tne_sweep_gate (inc
     lambda_i::NTuple{32,Int32}; lambda_j::NTuple{32,Int32}
     kept::Int32; trunc_err::Cdouble
 end
-function TensorNetworkEvolve.rydberg_tebd_sweep!(peps::TensorNetworkEvolve.PEPS{T,NF,LT,<:B200Array}, g, C, Δ, Ω, δt) where {T,NF,LT}
-    vidal = peps isa TensorNetworkEvolve.VidalPEPS
+on_device(peps::PEPS) = all(t -> t isa B200Array, alltensors(peps))
+# `PEPS{T,NF,LT}` has three parameters (src/peps.jl:4) and the array type is not one of them: dispatch on the abstract type and
+# look at the tensors; anything that is not on the device takes the reference's own method (src/tebd.jl:15-23)
+function TensorNetworkEvolve.rydberg_tebd_sweep!(peps::PEPS{T}, g, C::Real, Δ::Real, Ω::Real, δt) where T
+    on_device(peps) || return invoke(TensorNetworkEvolve.rydberg_tebd_sweep!, Tuple{Any,Any,Real,Real,Real,Any}, peps, g, C, Δ, Ω, δt)
+    vidal = peps isa VidalPEPS
     bondidx = Dict(l => Int32(k - 1) for (k, l) in enumerate(peps.virtual_labels))
     gates = SweepGate[]
     for e in edges(g)                                # the reference's order (src/tebd.jl:16)
@@ -233,26 +297,41 @@ function TensorNetworkEvolve.rydberg_tebd_sweep!(peps::TensorNetworkEvolve.PEPS{
         li, lj = peps.vertex_labels[i], peps.vertex_labels[j]
         shared = only(li ∩ lj)
         lam(ls) = ntuple(a -> (vidal && 1 < a <= length(ls)) ? bondidx[ls[a]] : Int32(-1), 32)
+        flat = reinterpret(Cdouble, vec(ComplexF64.(m)))
         push!(gates, SweepGate(i - 1, j - 1, findfirst(==(shared), li) - 1, findfirst(==(shared), lj) - 1, bondidx[shared],
-                               ntuple(k -> reinterpret(Cdouble, vec(ComplexF64.(m)))[k], 32), lam(li), lam(lj), 0, 0.0))
+                               ntuple(k -> flat[k], 32), lam(li), lam(lj), 0, 0.0))
     end
-    sites = Int64[t.handle for t in peps.vertex_tensors]
-    bonds = vidal ? Int64[t.handle for t in peps.bond_tensors] : Int64[0]
+    old_sites = Int64[t.handle for t in peps.vertex_tensors]
+    sites = copy(old_sites)
+    old_bonds = vidal ? Int64[t.handle for t in peps.bond_tensors] : Int64[0]
+    bonds = copy(old_bonds)
     check(ccall((:tne_tebd_sweep, LIB[]), Cint,
                 (Ptr{Cvoid}, Cint, Ptr{Int64}, Cint, Ptr{Int64}, Cint, Ptr{SweepGate}, Cint, Cdouble, Cint),
                 CTX[], length(sites), sites, vidal ? length(bonds) : 0, bonds, length(gates), gates, peps.Dmax, peps.ϵ, vidal))
-    for (q, e) in enumerate(edges(g))                # new shapes: the bond a gate rewrote has the rank it kept
+    # final shapes first (the last gate on a bond decides its rank), then exactly ONE new wrapper per tensor whose handle
+    # changed: two wrappers over one handle would free it twice (mirror of peps.py::apply_sweep_)
+    shapes = [collect(size(t)) for t in peps.vertex_tensors]
+    blen = Dict{Int,Int}()
+    for (q, e) in enumerate(edges(g))
         gq = gates[q]
         gq.trunc_err >= 0 && @info "truncation error is $(gq.trunc_err)"                       # src/peps.jl:386
-        for (s, ax) in ((src(e), gq.axis_i + 1), (dst(e), gq.axis_j + 1))
-            sz = collect(size(peps.vertex_tensors[s])); sz[ax] = gq.kept
-            peps.vertex_tensors[s] = B200Array{T,length(sz)}(sites[s], Tuple(sz))
+        shapes[src(e)][gq.axis_i + 1] = gq.kept
+        shapes[dst(e)][gq.axis_j + 1] = gq.kept
+        blen[gq.bond + 1] = gq.kept
+    end
+    for s in eachindex(sites)
+        sites[s] == old_sites[s] && continue
+        peps.vertex_tensors[s] = B200Array{T,length(shapes[s])}(sites[s], Tuple(shapes[s]))
+    end
+    if vidal
+        for b in eachindex(bonds)
+            bonds[b] == old_bonds[b] && continue
+            peps.bond_tensors[b] = B200Array{T,1}(bonds[b], (blen[b],))
         end
-        vidal && (peps.bond_tensors[gq.bond + 1] = B200Array{T,1}(bonds[gq.bond + 1], (Int(gq.kept),)))
     end
     return peps
 end
 
-to_b200(peps) = TensorNetworkEvolve.replace_tensors(peps, B200Array.(TensorNetworkEvolve.alltensors(peps)))
+to_b200(peps::PEPS) = replace_tensors(peps, B200Array.(alltensors(peps)))
 
 end # module

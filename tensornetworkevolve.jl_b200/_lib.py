@@ -98,6 +98,8 @@ SYMBOLS = {
     "tne_device_ptr": (C.c_void_p, [C.c_void_p, C.c_int64]),
     "tne_einsum": (C.c_int, [C.c_void_p, C.c_int, _P(C.c_int32), _P(C.c_int32), _P(C.c_int64), _P(C.c_int32),
                              _P(C.c_int32), C.c_int, _P(C.c_int64)]),
+    "tne_einsum_sized": (C.c_int, [C.c_void_p, C.c_int, _P(C.c_int32), _P(C.c_int32), _P(C.c_int64), _P(C.c_int32),
+                                   _P(C.c_int32), C.c_int, C.c_int, _P(C.c_int32), _P(C.c_int64), _P(C.c_int64)]),
     "tne_map": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_double, C.c_double, _P(C.c_int64)]),
     "tne_map2": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int64, _P(C.c_int64)]),
     "tne_reduce_sum": (C.c_int, [C.c_void_p, C.c_int64, _P(C.c_int64)]),

@@ -286,18 +286,29 @@ def zeros(shape, ctx=None):
     return B200Array.from_numpy(np.zeros(shape, dtype=np.complex128), ctx)
 
 
-def einsum_device(ixs, xs, iy, conj=None):
-    """``OMEinsum.einsum(EinCode(ixs, iy), xs, size_dict)`` for one or two device tensors."""
+def einsum_device(ixs, xs, iy, conj=None, size_dict=None):
+    """``OMEinsum.einsum(EinCode(ixs, iy), xs, size_dict)`` for one or two device tensors.  ``size_dict`` is only
+    consulted for labels that no input carries (OMEinsum's repeat rule, e.g. the pullback ``ein"->ii"`` of a trace)."""
     ctx = xs[0].ctx
     flat = [l for ix in ixs for l in ix]
     h = C.c_int64()
     cj = _i32(conj if conj is not None else [0] * len(xs))
-    ctx.check(ctx.L.tne_einsum(ctx.h, len(xs), _i32(flat), _i32([len(ix) for ix in ixs]),
-                               _i64([x.handle for x in xs]), cj, _i32(iy), len(iy), C.byref(h)))
     sizes = {}
     for ix, x in zip(ixs, xs):
         for l, s in zip(ix, x.shape):
             sizes[l] = s
+    extra = [l for l in dict.fromkeys(iy) if l not in sizes]
+    if extra:
+        if size_dict is None or any(l not in size_dict for l in extra):
+            raise ValueError("einsum: output labels %r are in no input and have no size" % (extra,))
+        for l in extra:
+            sizes[l] = int(size_dict[l])
+        ctx.check(ctx.L.tne_einsum_sized(ctx.h, len(xs), _i32(flat), _i32([len(ix) for ix in ixs]),
+                                         _i64([x.handle for x in xs]), cj, _i32(iy), len(iy),
+                                         len(extra), _i32(extra), _i64([sizes[l] for l in extra]), C.byref(h)))
+    else:
+        ctx.check(ctx.L.tne_einsum(ctx.h, len(xs), _i32(flat), _i32([len(ix) for ix in ixs]),
+                                   _i64([x.handle for x in xs]), cj, _i32(iy), len(iy), C.byref(h)))
     return B200Array(h.value, tuple(sizes[l] for l in iy), all(x.is_real for x in xs), ctx)
 
 

@@ -171,7 +171,8 @@ __global__ void __launch_bounds__(BOND_THREADS) bond_kernel(const BondDev* __res
     cplx* Qs = coef + MAXI;                               // [2][QS_MAX]
     __shared__ int pidx[MAXN];                            // column order of the preconditioning QR
     __shared__ SiteMap map[2];
-    __shared__ int s_flag;
+    __shared__ int s_flag, s_bad;
+    if (tid == 0) s_bad = 0;
     if (tid < 2) map[tid].init(J.dims[tid], J.rank[tid], J.axis[tid]);
     __syncthreads();
     const long long t_start = clock64();
@@ -235,7 +236,7 @@ __global__ void __launch_bounds__(BOND_THREADS) bond_kernel(const BondDev* __res
         for (int c = tid; c < nj; c += BOND_THREADS) {
             double a = 0.0;
             for (int r = 0; r < ni; ++r) { cplx u = W[c * MAXN + r]; a += u.x * u.x + u.y * u.y; }
-            sval[c] = a;
+            sval[c] = isfinite(a) ? a : 0.0;   // keeps the rank sort below a total order (pidx is always a permutation)
         }
         __syncthreads();
         for (int c = tid; c < nj; c += BOND_THREADS) {
@@ -343,6 +344,9 @@ __global__ void __launch_bounds__(BOND_THREADS) bond_kernel(const BondDev* __res
     for (int c = tid; c < nj; c += BOND_THREADS) {
         double a = 0.0;
         for (int r = 0; r < jr; ++r) { cplx u = jw[c * MAXN + r]; a += u.x * u.x + u.y * u.y; }
+        // a non-finite input (diverged state, or garbage handed to a speculative wavefront) must not break the index
+        // bookkeeping: it counts as a zero singular value here and is reported through trunc_err = NaN below
+        if (!isfinite(a)) { a = 0.0; s_bad = 1; }
         sval[c] = sqrt(a);
     }
     __syncthreads();
@@ -390,6 +394,7 @@ __global__ void __launch_bounds__(BOND_THREADS) bond_kernel(const BondDev* __res
         // diagnostics in the spare words of the job's meta record (read back with option debug >= 2)
         J.kept[1] = n_sweeps; J.kept[2] = (int)((t_qr - t_start) >> 10); J.kept[3] = (int)((t_jac - t_core) >> 10);
         *J.trunc_err = D < full ? err : -1.0;   // -1: nothing was cut (the reference logs only when D < size(U,2))
+        if (s_bad || !isfinite(err)) *J.trunc_err = nan("");   // non-finite input: the host turns this into an error status
         s_flag = D;
     }
     __syncthreads();
@@ -402,6 +407,21 @@ __global__ void __launch_bounds__(BOND_THREADS) bond_kernel(const BondDev* __res
         const cplx* Q = O * I <= QS_MAX ? Qs + side * QS_MAX : J.Q[side];
         cplx* out = J.UV[side];
         const int rows = 2 * O;
+        // columns D .. Dcap-1 (a bond that kept fewer singular values than its cap) are written as zeros: later wavefronts
+        // of a speculative sweep read these buffers before the exact-rank redo replaces them
+        for (int e = tid + rows * D; e < rows * J.Dcap; e += BOND_THREADS) {
+            const int row = e % rows, dd = e / rows;
+            out[(long long)dd * rows + row] = make_double2(0.0, 0.0);
+            if (J.place[side]) {
+                long long off = row & 1, st = M.dim[0];
+                int oo = row >> 1;
+                for (int q = 1; q < M.rank; ++q) {
+                    if (q == M.ax) { off += (long long)dd * st; st *= J.Dcap; }
+                    else { off += (long long)(oo % M.dim[q]) * st; oo /= M.dim[q]; st *= M.dim[q]; }
+                }
+                J.place[side][off] = make_double2(0.0, 0.0);
+            }
+        }
         for (int e = tid; e < rows * D; e += BOND_THREADS) {
             const int row = e % rows, dd = e / rows;
             const int pp = row & 1, o = row >> 1;
@@ -442,7 +462,7 @@ __global__ void __launch_bounds__(BOND_THREADS) bond_kernel(const BondDev* __res
             }
         }
     }
-    for (int dd = tid; dd < D; dd += BOND_THREADS) J.S[dd] = make_double2(sval[perm[dd]], 0.0);
+    for (int dd = tid; dd < J.Dcap; dd += BOND_THREADS) J.S[dd] = make_double2(dd < D ? sval[perm[dd]] : 0.0, 0.0);
 }
 
 size_t bond_smem_bytes() {
@@ -468,11 +488,7 @@ struct BondBatch {
 
 // builds the device descriptors and launches the bond kernel for `n_jobs` site-disjoint jobs; does not synchronise
 static int bond_enqueue(tne_ctx* ctx, int n_jobs, const tne_bond_job* in, BondBatch& bb, std::vector<tne_buf>* direct = nullptr) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(bond_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bond_smem_bytes());
-        attr_set = true;
-    }
+    ensure_smem_attr(ctx, bond_kernel, (int)bond_smem_bytes());
     std::vector<BondDev>& dev = bb.dev;
     std::vector<HostJob>& hj = bb.hj;
     dev.assign(n_jobs, BondDev());
@@ -592,6 +608,7 @@ static int bond_place(tne_ctx* ctx, tne_buf uv, const std::vector<int64_t>& dims
 }
 
 extern "C" int tne_apply_onbond_batched(tne_ctx* ctx, int n_jobs, tne_bond_job* jobs) {
+    TNE_ENTER(ctx);
     if (n_jobs <= 0) return TNE_OK;
     if (!jobs) return tne_fail(ctx, TNE_ERR_INVALID, "null jobs");
     BondBatch bb;
@@ -613,6 +630,8 @@ extern "C" int tne_apply_onbond_batched(tne_ctx* ctx, int n_jobs, tne_bond_job* 
         for (int side = 0; side < 2; ++side) { tne_free(ctx, hj[k].q[side]); tne_free(ctx, hj[k].uv[side]); }
         tne_free(ctx, hj[k].s);
     }
+    for (int k = 0; k < n_jobs; ++k)
+        if (std::isnan(err[k])) return tne_fail(ctx, TNE_ERR_INVALID, "bond job %d: non-finite values in the site tensors", k);
     return TNE_OK;
 }
 
@@ -626,6 +645,7 @@ extern "C" int tne_apply_onbond_batched(tne_ctx* ctx, int n_jobs, tne_bond_job* 
 // the exact ranks (the inputs are immutable buffers, so nothing has to be restored).
 extern "C" int tne_tebd_sweep(tne_ctx* ctx, int n_sites, tne_buf* sites, int n_bonds, tne_buf* bonds, int n_gates,
                               tne_sweep_gate* gates, int Dmax, double eps, int vidal) {
+    TNE_ENTER(ctx);
     if (n_gates <= 0) return TNE_OK;
     if (!sites || !gates || (vidal && !bonds)) return tne_fail(ctx, TNE_ERR_INVALID, "null argument");
     // wavefront levels, order-preserving
@@ -710,6 +730,8 @@ extern "C" int tne_tebd_sweep(tne_ctx* ctx, int n_sites, tne_buf* sites, int n_b
                 for (int side = 0; side < 2; ++side) { tne_free(ctx, h.q[side]); tne_free(ctx, h.uv[side]); }
                 tne_free(ctx, h.s);
             }
+            for (size_t q = 0; q < err.size() && rc == TNE_OK; ++q)
+                if (std::isnan(err[q])) rc = tne_fail(ctx, TNE_ERR_INVALID, "tebd sweep gate %d: non-finite values in the site tensors", ids[q]);
         }
         if (rc == TNE_OK && speculative) {   // one synchronisation for the whole sweep: were all the caps reached?
             for (int lv = 0; lv < n_levels && rc == TNE_OK; ++lv) {
@@ -719,7 +741,7 @@ extern "C" int tne_tebd_sweep(tne_ctx* ctx, int n_sites, tne_buf* sites, int n_b
                 for (size_t q = 0; q < by_level[lv].size() && rc == TNE_OK; ++q) {
                     tne_sweep_gate& g = gates[by_level[lv][q]];
                     g.kept = kept[q]; g.trunc_err = err[q];
-                    if (kept[q] != cap[lv][q]) ok = false;
+                    if (kept[q] != cap[lv][q] || std::isnan(err[q])) ok = false;   // NaN: decided by the exact-rank pass
                 }
             }
         }
@@ -749,6 +771,7 @@ extern "C" int tne_tebd_sweep(tne_ctx* ctx, int n_sites, tne_buf* sites, int n_b
 // t_i[p, r, s] = A[(p, r), s] restricted ... (general matrices go through the two-site form with an identity gate)
 extern "C" int tne_svd_trunc(tne_ctx* ctx, tne_buf hA, int Dmax, double eps, tne_buf* U, tne_buf* S, tne_buf* V, int32_t* kept,
                              double* trunc_err) {
+    TNE_ENTER(ctx);
     Buf* a = buf_get(ctx, hA);
     if (!a) return TNE_ERR_INVALID;
     if (a->dims.size() != 2) return tne_fail(ctx, TNE_ERR_INVALID, "svd: a matrix is required");

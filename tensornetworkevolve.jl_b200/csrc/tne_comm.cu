@@ -12,6 +12,7 @@ typedef int (*fn_allreduce)(const void*, void*, size_t, int, int, void*, cudaStr
 typedef int (*fn_reduce_scatter)(const void*, void*, size_t, int, int, void*, cudaStream_t);
 typedef int (*fn_all_gather)(const void*, void*, size_t, int, void*, cudaStream_t);
 typedef int (*fn_group)(void);
+typedef int (*fn_comm_destroy)(void*);
 typedef const char* (*fn_errstr)(int);
 struct NcclApi {
     void* lib = nullptr;
@@ -22,6 +23,7 @@ struct NcclApi {
     fn_all_gather all_gather = nullptr;
     fn_group group_start = nullptr, group_end = nullptr;
     fn_errstr errstr = nullptr;
+    fn_comm_destroy comm_destroy = nullptr;
 };
 NcclApi g_nccl;
 
@@ -41,6 +43,7 @@ int load_nccl(tne_ctx* ctx) {
     g_nccl.group_start = (fn_group)dlsym(g_nccl.lib, "ncclGroupStart");
     g_nccl.group_end = (fn_group)dlsym(g_nccl.lib, "ncclGroupEnd");
     g_nccl.errstr = (fn_errstr)dlsym(g_nccl.lib, "ncclGetErrorString");
+    g_nccl.comm_destroy = (fn_comm_destroy)dlsym(g_nccl.lib, "ncclCommDestroy");
     if (!g_nccl.get_uid || !g_nccl.comm_init || !g_nccl.allreduce || !g_nccl.group_start || !g_nccl.group_end)
         return tne_fail(ctx, TNE_ERR_NCCL, "libnccl is missing required symbols");
     return TNE_OK;
@@ -54,15 +57,23 @@ extern "C" int tne_nccl_unique_id(void* id128) {
 }
 
 extern "C" int tne_comm_init(tne_ctx* ctx, const void* id128, int rank, int world) {
+    TNE_ENTER(ctx);
     TNE_TRY(load_nccl(ctx));
     TNE_CUDA(ctx, cudaSetDevice(ctx->device));
     nccl_uid uid;
     memcpy(&uid, id128, sizeof(uid));
+    if (ctx->nccl) comm_destroy(ctx);   // re-initialisation replaces the communicator
     int rc = g_nccl.comm_init(&ctx->nccl, world, uid, rank);
     if (rc != 0) return tne_fail(ctx, TNE_ERR_NCCL, "ncclCommInitRank failed: %s", g_nccl.errstr ? g_nccl.errstr(rc) : "?");
     ctx->rank = rank;
     ctx->world = world;
     return TNE_OK;
+}
+
+void comm_destroy(tne_ctx* ctx) {
+    if (ctx->nccl && g_nccl.comm_destroy) g_nccl.comm_destroy(ctx->nccl);
+    ctx->nccl = nullptr;
+    ctx->world = 1; ctx->rank = 0;
 }
 
 int comm_allreduce_ptr(tne_ctx* ctx, cplx* p, int64_t n) {
@@ -100,6 +111,7 @@ int comm_reduce_scatter_blocks(tne_ctx* ctx, cplx* p, int64_t block, int64_t nbl
 int comm_all_gather_blocks(tne_ctx* ctx, cplx* p, int64_t block, int64_t nblocks) { return comm_blocks(ctx, p, block, nblocks, true); }
 
 extern "C" int tne_allreduce_sum(tne_ctx* ctx, int n, const tne_buf* bufs) {
+    TNE_ENTER(ctx);
     if (ctx->world <= 1) return TNE_OK;
     if (!ctx->nccl) return tne_fail(ctx, TNE_ERR_NCCL, "tne_comm_init has not been called");
     const int NCCL_DOUBLE = 8, NCCL_SUM = 0;

@@ -384,8 +384,29 @@ int gett_fast_run(tne_ctx* ctx, const ContractPlan&, const cplx*, const cplx*, c
 // ---------------------------------------------------------------------------------------
 // C ABI: einsum
 // ---------------------------------------------------------------------------------------
-extern "C" int tne_einsum(tne_ctx* ctx, int n_in, const int32_t* labels_flat, const int32_t* ranks, const tne_buf* in,
-                          const int32_t* conj_flags, const int32_t* out_labels, int out_rank, tne_buf* out) {
+// Repeated labels inside one operand (OMEinsum's trace / diagonal unary rules, e.g. ein"ii->"): the operand is read
+// through its diagonal view -- one leg per distinct label whose stride is the sum of the strides of its occurrences.
+static int diagonal_view(tne_ctx* ctx, TensorRef& t, const char* what) {
+    std::vector<int64_t> st;
+    default_strides(t, st);
+    TensorRef v;
+    v.ptr = t.ptr; v.conj = t.conj;
+    for (size_t q = 0; q < t.labels.size(); ++q) {
+        int at = find_label(v.labels, t.labels[q]);
+        if (at < 0) { v.labels.push_back(t.labels[q]); v.dims.push_back(t.dims[q]); v.strides.push_back(st[q]); continue; }
+        if (v.dims[at] != t.dims[q])
+            return tne_fail(ctx, TNE_ERR_INVALID, "einsum: label %d repeats inside %s with sizes %lld and %lld", (int)t.labels[q], what,
+                            (long long)v.dims[at], (long long)t.dims[q]);
+        v.strides[at] += st[q];
+    }
+    if (v.labels.size() != t.labels.size()) t = v;
+    return TNE_OK;
+}
+
+extern "C" int tne_einsum_sized(tne_ctx* ctx, int n_in, const int32_t* labels_flat, const int32_t* ranks, const tne_buf* in,
+                                const int32_t* conj_flags, const int32_t* out_labels, int out_rank, int n_sizes,
+                                const int32_t* size_labels, const int64_t* size_values, tne_buf* out) {
+    TNE_ENTER(ctx);
     if (n_in != 1 && n_in != 2) return tne_fail(ctx, TNE_ERR_UNSUPPORTED, "einsum takes 1 or 2 tensors (got %d); use tne_contract_tree", n_in);
     TensorRef T[2];
     int pos = 0;
@@ -399,23 +420,44 @@ extern "C" int tne_einsum(tne_ctx* ctx, int n_in, const int32_t* labels_flat, co
         T[i].labels.assign(labels_flat + pos, labels_flat + pos + ranks[i]);
         T[i].conj = conj_flags ? conj_flags[i] != 0 : false;
         pos += ranks[i];
+        TNE_TRY(diagonal_view(ctx, T[i], "an operand"));
     }
     if (n_in == 1) {  // unary: permutation / summation == contraction with the constant 1
         T[1].ptr = ctx->one_dev;
     }
-    TensorRef C;
+    TensorRef C;   // the output as allocated: one leg per entry of out_labels, repeats included
     C.labels.assign(out_labels, out_labels + out_rank);
     for (int i = 0; i < out_rank; ++i) {
         int32_t l = out_labels[i];
         int ia = find_label(T[0].labels, l), ib = find_label(T[1].labels, l);
-        if (ia < 0 && ib < 0) return tne_fail(ctx, TNE_ERR_UNSUPPORTED, "einsum: output label %d not in the inputs", (int)l);
+        if (ia < 0 && ib < 0) {
+            // a label that only the output carries (OMEinsum's repeat rule; the pullback of a sum / trace): its size comes
+            // from the size dictionary and the first operand is broadcast along it (a leg of stride 0)
+            int64_t sz = -1;
+            for (int q = 0; q < n_sizes; ++q) if (size_labels[q] == l) sz = size_values[q];
+            if (sz < 0) return tne_fail(ctx, TNE_ERR_UNSUPPORTED, "einsum: output label %d is not in the inputs and has no size", (int)l);
+            std::vector<int64_t> st;
+            default_strides(T[0], st);
+            T[0].strides = st;
+            T[0].labels.push_back(l); T[0].dims.push_back(sz); T[0].strides.push_back(0);
+            ia = (int)T[0].labels.size() - 1;
+        }
         C.dims.push_back(ia >= 0 ? T[0].dims[ia] : T[1].dims[ib]);
     }
     tne_buf h;
     TNE_TRY(buf_new(ctx, C.dims, &h));
     C.ptr = buf_get(ctx, h)->ptr();
-    int rc = contract_launch(ctx, T[0], T[1], C, false, 1.0, 0.0);
+    TensorRef Cv = C;
+    int rc = diagonal_view(ctx, Cv, "the output");
+    if (rc == TNE_OK && Cv.labels.size() != C.labels.size())   // ein"i->ii": only the diagonal is written
+        rc = launch_fill_zero(ctx, C.ptr, buf_get(ctx, h)->nelem);
+    if (rc == TNE_OK) rc = contract_launch(ctx, T[0], T[1], Cv, false, 1.0, 0.0);
     if (rc != TNE_OK) { tne_free(ctx, h); return rc; }
     *out = h;
     return TNE_OK;
+}
+
+extern "C" int tne_einsum(tne_ctx* ctx, int n_in, const int32_t* labels_flat, const int32_t* ranks, const tne_buf* in,
+                          const int32_t* conj_flags, const int32_t* out_labels, int out_rank, tne_buf* out) {
+    return tne_einsum_sized(ctx, n_in, labels_flat, ranks, in, conj_flags, out_labels, out_rank, 0, nullptr, nullptr, out);
 }

@@ -799,11 +799,7 @@ void sort_legs_by(LegSet& L, int which) {  // insertion sort of the legs by stri
 
 template <int KS, int MTW, int MINB, bool ROWS>
 int launch_absorb(tne_ctx* ctx, const ContractPlan& plan, const cplx* A, const cplx* B, cplx* C) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(gett_absorb<KS, MTW, MINB, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-        attr_set = true;
-    }
+    ensure_smem_attr(ctx, gett_absorb<KS, MTW, MINB, ROWS>, 100 * 1024);
     unsigned gx = (unsigned)std::min<long long>((long long)plan.gx / 2 * MINB, ((plan.d.Msz + 8 * MTW - 1) / (8 * MTW) + 7) / 8);
     TNE_CUDA(ctx, launch_pdl(gett_absorb<KS, MTW, MINB, ROWS>, gx, (unsigned)plan.threads, plan.smem + (ROWS ? (size_t)8 * (2 * KS) * 34 * sizeof(cplx) + 16 : 0), ctx->stream, !ctx->opt_no_pdl, plan.d, A, B, C, plan.aux[1]));
     TNE_LAUNCH_CHECK(ctx);
@@ -812,11 +808,7 @@ int launch_absorb(tne_ctx* ctx, const ContractPlan& plan, const cplx* A, const c
 
 template <int KS, int NT>
 int launch_absorb_multi(tne_ctx* ctx, const ContractPlan& plan, const AbsorbMulti& ops, cplx* C) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(gett_absorb_multi<KS, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 75 * 1024);
-        attr_set = true;
-    }
+    ensure_smem_attr(ctx, gett_absorb_multi<KS, NT>, 75 * 1024);
     const int Np = plan.aux[1];
     const size_t smem = (size_t)ops.T * (2 * Np) * (4 * KS + 4) * sizeof(double) + (size_t)(2 * KS + Np) * sizeof(long long);
     unsigned gx = (unsigned)std::min<long long>((long long)plan.gx / 2 * 3, ((plan.d.Msz + 7) / 8 + 7) / 8);
@@ -827,11 +819,7 @@ int launch_absorb_multi(tne_ctx* ctx, const ContractPlan& plan, const AbsorbMult
 
 template <int KS, int MTW>
 int launch_absorb_tma(tne_ctx* ctx, const ContractPlan& plan, const cplx* A, const cplx* B, cplx* C) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(gett_absorb_tma<KS, MTW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
-        attr_set = true;
-    }
+    ensure_smem_attr(ctx, gett_absorb_tma<KS, MTW>, 110 * 1024);
     TmaGeom g;
     g.kf = plan.aux[4]; g.nplanes = plan.aux[5]; g.plane_stride = plan.aux[6]; g.Np = plan.aux[1]; g.tpc = plan.aux[2];
     gett_absorb_tma<KS, MTW><<<plan.gx, 32 * (TMA_CONSUMERS + 1), plan.smem, ctx->stream>>>(plan.d, A, B, C, g);
@@ -841,11 +829,7 @@ int launch_absorb_tma(tne_ctx* ctx, const ContractPlan& plan, const cplx* A, con
 
 template <int MT, int NT>
 int launch_reduce_tma(tne_ctx* ctx, const ContractPlan& plan, const RedGeom& g, const cplx* A, const cplx* B, cplx* C) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(gett_reduce_tma<MT, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-        attr_set = true;
-    }
+    ensure_smem_attr(ctx, gett_reduce_tma<MT, NT>, 220 * 1024);
     gett_reduce_tma<MT, NT><<<plan.gx, 32 * (RED_CONSUMERS + 1), plan.smem, ctx->stream>>>(plan.d, A, B, C, g);
     TNE_LAUNCH_CHECK(ctx);
     return TNE_OK;

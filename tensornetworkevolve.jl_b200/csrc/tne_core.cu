@@ -202,6 +202,7 @@ extern "C" int tne_ctx_destroy(tne_ctx* ctx) {
     }
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    comm_destroy(ctx);
     for (auto& kv : ctx->bufs) if (kv.second.block) kv.second.block->ctx = nullptr;  // freed below
     std::vector<void*> ptrs;
     for (auto& kv : ctx->bufs) if (kv.second.block && kv.second.block->ptr) ptrs.push_back(kv.second.block->ptr);
@@ -220,17 +221,20 @@ extern "C" int tne_ctx_destroy(tne_ctx* ctx) {
 extern "C" const char* tne_last_error(tne_ctx* ctx) { return ctx ? ctx->err.c_str() : g_noctx_err.c_str(); }
 
 extern "C" int tne_sync(tne_ctx* ctx) {
+    TNE_ENTER(ctx);
     TNE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return TNE_OK;
 }
 
 extern "C" int tne_set_mem_limit(tne_ctx* ctx, int64_t bytes) {
+    TNE_ENTER(ctx);
     if (bytes <= 0) return tne_fail(ctx, TNE_ERR_INVALID, "memory limit must be positive");
     ctx->mem_limit = bytes;
     return TNE_OK;
 }
 
 extern "C" int tne_mem_info(tne_ctx* ctx, int64_t* in_use, int64_t* peak, int64_t* workspace) {
+    TNE_ENTER(ctx);
     if (in_use) *in_use = ctx->in_use;
     if (peak) *peak = ctx->peak;
     if (workspace) *workspace = ctx->ws_bytes;
@@ -241,11 +245,13 @@ extern "C" void* tne_stream(tne_ctx* ctx) { return (void*)ctx->stream; }
 extern "C" int64_t tne_launch_count(tne_ctx* ctx) { return ctx->launches; }
 
 extern "C" int tne_last_program_stats(tne_ctx* ctx, double* s) {
+    TNE_ENTER(ctx);
     for (int i = 0; i < 6; ++i) s[i] = ctx->stats[i];
     return TNE_OK;
 }
 
 extern "C" int tne_profile_collect(tne_ctx* ctx, double* out) {
+    TNE_ENTER(ctx);
     for (int i = 0; i < 4 * TNE_PROFILE_CLASSES; ++i) out[i] = 0.0;
     TNE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     for (auto& r : ctx->prof) {
@@ -261,6 +267,7 @@ extern "C" int tne_profile_collect(tne_ctx* ctx, double* out) {
 }
 
 extern "C" int tne_set_option(tne_ctx* ctx, const char* key, int64_t value) {
+    TNE_ENTER(ctx);
     std::string k(key ? key : "");
     if (k == "force_generic_kernel") ctx->opt_force_generic = value;
     else if (k == "debug") ctx->opt_debug = value;
@@ -281,12 +288,14 @@ extern "C" int tne_set_option(tne_ctx* ctx, const char* key, int64_t value) {
 // C ABI: tensors
 // ---------------------------------------------------------------------------------------
 extern "C" int tne_alloc(tne_ctx* ctx, int rank, const int64_t* dims, tne_buf* out) {
+    TNE_ENTER(ctx);
     if (rank < 0 || rank > TNE_MAX_RANK) return tne_fail(ctx, TNE_ERR_INVALID, "bad rank %d", rank);
     std::vector<int64_t> d(dims, dims + rank);
     return buf_new(ctx, d, out);
 }
 
 extern "C" int tne_free(tne_ctx* ctx, tne_buf h) {
+    TNE_ENTER(ctx);
     if (h == 0) return TNE_OK;
     auto it = ctx->bufs.find(h);
     if (it == ctx->bufs.end()) return tne_fail(ctx, TNE_ERR_INVALID, "free of unknown handle %lld", (long long)h);
@@ -295,6 +304,7 @@ extern "C" int tne_free(tne_ctx* ctx, tne_buf h) {
 }
 
 extern "C" int tne_shape(tne_ctx* ctx, tne_buf h, int* rank, int64_t* dims) {
+    TNE_ENTER(ctx);
     Buf* b = buf_get(ctx, h);
     if (!b) return TNE_ERR_INVALID;
     *rank = (int)b->dims.size();
@@ -303,6 +313,7 @@ extern "C" int tne_shape(tne_ctx* ctx, tne_buf h, int* rank, int64_t* dims) {
 }
 
 extern "C" int tne_upload(tne_ctx* ctx, tne_buf h, const void* host) {
+    TNE_ENTER(ctx);
     Buf* b = buf_get(ctx, h);
     if (!b) return TNE_ERR_INVALID;
     TNE_CUDA(ctx, cudaMemcpyAsync(b->ptr(), host, b->nelem * sizeof(cplx), cudaMemcpyHostToDevice, ctx->stream));
@@ -312,6 +323,7 @@ extern "C" int tne_upload(tne_ctx* ctx, tne_buf h, const void* host) {
 }
 
 extern "C" int tne_download(tne_ctx* ctx, tne_buf h, void* host) {
+    TNE_ENTER(ctx);
     Buf* b = buf_get(ctx, h);
     if (!b) return TNE_ERR_INVALID;
     if (ctx->plan_only) return tne_fail(ctx, TNE_ERR_UNSUPPORTED, "planner context (TNE_PLAN_ONLY): nothing was computed, nothing to download");
@@ -321,6 +333,7 @@ extern "C" int tne_download(tne_ctx* ctx, tne_buf h, void* host) {
 }
 
 extern "C" void* tne_device_ptr(tne_ctx* ctx, tne_buf h) {
+    TNE_ENTER(ctx);
     Buf* b = buf_get(ctx, h);
     return b ? (void*)b->ptr() : nullptr;
 }
@@ -460,6 +473,7 @@ int launch_axpy_dev(tne_ctx* ctx, cplx* y, const cplx* x, int64_t n, const cplx*
 }
 
 extern "C" int tne_map(tne_ctx* ctx, int op, tne_buf in, double sre, double sim, tne_buf* out) {
+    TNE_ENTER(ctx);
     Buf* a = buf_get(ctx, in);
     if (!a) return TNE_ERR_INVALID;
     std::vector<int64_t> dims = a->dims;
@@ -476,6 +490,7 @@ extern "C" int tne_map(tne_ctx* ctx, int op, tne_buf in, double sre, double sim,
 }
 
 extern "C" int tne_map2(tne_ctx* ctx, int op, tne_buf ha, tne_buf hb, tne_buf* out) {
+    TNE_ENTER(ctx);
     Buf* a = buf_get(ctx, ha);
     Buf* b = buf_get(ctx, hb);
     if (!a || !b) return TNE_ERR_INVALID;
@@ -497,6 +512,7 @@ extern "C" int tne_map2(tne_ctx* ctx, int op, tne_buf ha, tne_buf hb, tne_buf* o
 }
 
 extern "C" int tne_reduce_sum(tne_ctx* ctx, tne_buf in, tne_buf* out) {
+    TNE_ENTER(ctx);
     Buf* a = buf_get(ctx, in);
     if (!a) return TNE_ERR_INVALID;
     int64_t n = a->nelem;
@@ -515,6 +531,7 @@ extern "C" int tne_reduce_sum(tne_ctx* ctx, tne_buf in, tne_buf* out) {
 }
 
 extern "C" int tne_fill(tne_ctx* ctx, tne_buf scalar0, int rank, const int64_t* dims, tne_buf* out) {
+    TNE_ENTER(ctx);
     Buf* s = buf_get(ctx, scalar0);
     if (!s) return TNE_ERR_INVALID;
     if (s->nelem != 1) return tne_fail(ctx, TNE_ERR_INVALID, "fill: source must have one element");
@@ -531,6 +548,7 @@ extern "C" int tne_fill(tne_ctx* ctx, tne_buf scalar0, int rank, const int64_t* 
 }
 
 extern "C" int tne_slice(tne_ctx* ctx, tne_buf in, int64_t lo, int64_t count, tne_buf* out) {
+    TNE_ENTER(ctx);
     Buf* a = buf_get(ctx, in);
     if (!a) return TNE_ERR_INVALID;
     if (lo < 0 || count < 0 || lo + count > a->nelem) return tne_fail(ctx, TNE_ERR_INVALID, "slice [%lld, %lld) out of range (%lld)", (long long)lo, (long long)(lo + count), (long long)a->nelem);
@@ -539,6 +557,7 @@ extern "C" int tne_slice(tne_ctx* ctx, tne_buf in, int64_t lo, int64_t count, tn
 }
 
 extern "C" int tne_embed(tne_ctx* ctx, tne_buf y, int64_t lo, int64_t total, tne_buf* out) {
+    TNE_ENTER(ctx);
     Buf* a = buf_get(ctx, y);
     if (!a) return TNE_ERR_INVALID;
     if (lo < 0 || lo + a->nelem > total) return tne_fail(ctx, TNE_ERR_INVALID, "embed range out of bounds");
@@ -554,6 +573,7 @@ extern "C" int tne_embed(tne_ctx* ctx, tne_buf y, int64_t lo, int64_t total, tne
 }
 
 extern "C" int tne_reshape(tne_ctx* ctx, tne_buf in, int rank, const int64_t* dims, tne_buf* out) {
+    TNE_ENTER(ctx);
     Buf* a = buf_get(ctx, in);
     if (!a) return TNE_ERR_INVALID;
     std::vector<int64_t> d(dims, dims + rank);
@@ -565,6 +585,7 @@ extern "C" int tne_reshape(tne_ctx* ctx, tne_buf in, int rank, const int64_t* di
 }
 
 extern "C" int tne_concat(tne_ctx* ctx, int n, const tne_buf* in, tne_buf* out) {
+    TNE_ENTER(ctx);
     int64_t total = 0;
     for (int i = 0; i < n; ++i) {
         Buf* b = buf_get(ctx, in[i]);

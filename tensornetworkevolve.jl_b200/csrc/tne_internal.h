@@ -7,6 +7,7 @@
 #include <map>
 #include <memory>
 #include <string>
+#include <set>
 #include <unordered_map>
 #include <vector>
 
@@ -68,7 +69,24 @@ struct tne_ctx {
     // planner context (TNE_PLAN_ONLY=1 and no device): programs are built, costed and dumped, nothing is ever
     // computed -- tne_expect_terms / tne_contract_tree return TNE_ERR_UNSUPPORTED after planning (tools/plan_dump.py)
     bool plan_only = false;
+    // kernels whose dynamic shared-memory opt-in has been set on THIS context's device (the attribute is per device)
+    std::set<const void*> smem_attr_done;
 };
+
+// every entry point binds the calling thread to the context's device first (a host program may switch devices or call
+// from another thread between two calls)
+#define TNE_ENTER(ctx)                                                      \
+    do {                                                                    \
+        if ((ctx) && !(ctx)->plan_only) cudaSetDevice((ctx)->device);       \
+    } while (0)
+
+template <typename K>
+inline void ensure_smem_attr(tne_ctx* ctx, K kernel, int bytes) {
+    const void* key = reinterpret_cast<const void*>(kernel);
+    if (ctx->smem_attr_done.count(key)) return;
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    ctx->smem_attr_done.insert(key);
+}
 
 // ---- error helpers ---------------------------------------------------------------------
 int tne_fail(tne_ctx* ctx, int code, const char* fmt, ...);
@@ -184,6 +202,7 @@ int comm_allreduce_ptr(tne_ctx* ctx, cplx* p, int64_t n);
 // all-gather: every rank contributes the blocks it owns, on return all blocks are complete everywhere.
 int comm_reduce_scatter_blocks(tne_ctx* ctx, cplx* p, int64_t block, int64_t nblocks);
 int comm_all_gather_blocks(tne_ctx* ctx, cplx* p, int64_t block, int64_t nblocks);
+void comm_destroy(tne_ctx* ctx);   // ncclCommDestroy of the context's communicator, if any
 
 // ---- elementwise helpers used across units ---------------------------------------------
 int launch_fill_zero(tne_ctx* ctx, cplx* p, int64_t n);

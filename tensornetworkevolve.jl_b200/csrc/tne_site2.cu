@@ -268,11 +268,7 @@ bool site2_plan(tne_ctx* ctx, const TensorRef& A, const TensorRef& B1, const Ten
 }
 
 int site2_run(tne_ctx* ctx, const Site2Desc& d, const cplx* A, const cplx* B1, const cplx* B2, cplx* C) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(gett_site2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)site2_smem());
-        attr_set = true;
-    }
+    ensure_smem_attr(ctx, gett_site2, (int)site2_smem());
     const unsigned gx = (unsigned)std::min<long long>(d.g.Msz / S2_TB, (long long)ctx->sm_count * 2);
     gett_site2<<<gx, 256, site2_smem(), ctx->stream>>>(d, A, B1, B2, C);
     TNE_LAUNCH_CHECK(ctx);

@@ -973,6 +973,7 @@ struct Exec {
 extern "C" int tne_expect_terms(tne_ctx* ctx, const tne_tree* tree, const tne_buf* leaves, const int32_t* leaf_conj,
                                 int n_terms, const tne_term* terms, int n_grad, const int32_t* grad_leaves,
                                 double seed_re, double seed_im, tne_buf* value_out, tne_buf* grads_out) {
+    TNE_ENTER(ctx);
     if (!tree || !leaves || !value_out) return tne_fail(ctx, TNE_ERR_INVALID, "null argument");
     if (n_grad > 0 && !grads_out) return tne_fail(ctx, TNE_ERR_INVALID, "grads_out is null");
     Program P;

@@ -33,12 +33,12 @@ class EinCode:
         return einsum(self.ixs, list(xs), self.iy)
 
 
-def einsum(ixs, xs, iy, conj=None):
-    """The single dispatch point (``OMEinsum.einsum``)."""
+def einsum(ixs, xs, iy, conj=None, size_dict=None):
+    """The single dispatch point (``OMEinsum.einsum(code, xs, size_dict)``)."""
     if _DIFF_HOOK is not None and all(_DIFF_HOOK["is"](x) for x in xs):
-        return _DIFF_HOOK["einsum"](ixs, xs, iy)
+        return _DIFF_HOOK["einsum"](ixs, xs, iy, size_dict)
     xs = [x if isinstance(x, B200Array) else B200Array.from_numpy(np.asarray(x)) for x in xs]
-    return einsum_device(ixs, xs, iy, conj)
+    return einsum_device(ixs, xs, iy, conj, size_dict)
 
 
 class NestedEinsum:

@@ -624,7 +624,11 @@ def expect(op, pa, pb, shard=(0, 1)):  # src/peps.jl:469-477
         fused = es.FUSED_TREES and len(pa.alltensors()) == len(pb.alltensors())
         cache = {}
         terms = [_term_replacements(pb, t, cache) for t in op.blocks] if fused else None
-        if fused and all(t is not None for t in terms) and all(_isdiff(t) for t in pa.alltensors()) == any(_isdiff(t) for t in pa.alltensors()):
+        # the fused programme returns pullbacks for the bra leaves only: a ket that requires gradients (the reference
+        # tapes apply -> inner_product for both arguments, src/peps.jl:474-477) takes the term-by-term taped path
+        ket_grad = any(_isdiff(t) and ad.requires_grad(t) for t in pb.alltensors())
+        if fused and not ket_grad and all(t is not None for t in terms) and \
+                all(_isdiff(t) for t in pa.alltensors()) == any(_isdiff(t) for t in pa.alltensors()):
             return _expect_fused(terms, pa, pb, shard)
         out = None
         for k, term in enumerate(op.blocks):
@@ -632,9 +636,17 @@ def expect(op, pa, pb, shard=(0, 1)):  # src/peps.jl:469-477
                 continue
             e = expect(term, pa, pb)
             out = e if out is None else out + e
-        return out
+        return _zero_scalar(pa) if out is None else out
     opb = apply_block(pb, op)
     return inner_product(pa, opb)
+
+
+def _zero_scalar(pa):
+    """The value of an empty sum of terms (a rank whose share of the Hamiltonian is empty): an explicit 0-dim zero
+    that carries no gradient -- NOT the plain overlap <pa|pb> that ``tne_expect_terms`` evaluates for ``n_terms == 0``."""
+    t0 = pa.alltensors()[0]
+    z = B200Array.from_numpy(np.zeros((), dtype=np.complex128), _dev(t0).ctx)
+    return DiffTensor(z, requires_grad=False) if _isdiff(t0) else z
 
 
 def _expect_fused(terms, pa, pb, shard):
@@ -650,6 +662,8 @@ def _expect_fused(terms, pa, pb, shard):
         if k % shard[1] != shard[0]:
             continue
         tlist.append((coef, [(nt + site - 1, t) for site, t in sorted(repl.items())]))
+    if not tlist:
+        return _zero_scalar(pa)
     if not diff:
         val, _ = es.expect_terms_device(code, leaves, cj, tlist)
         return val

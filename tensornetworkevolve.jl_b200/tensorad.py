@@ -146,6 +146,30 @@ def gradient(f, *args, **kwargs):  # TensorAD.jl:131-140
     return getgrad(storage, tuple(args))
 
 
+def jacobian(f, x):  # TensorAD.jl:170-185
+    """``transpose(cat(slices...; dims=2))``: row ``i`` is the gradient of ``y[i]`` (one backward pass per output element
+    over the same tape, seeded with a device unit vector).  Returns a device matrix (a ``DiffTensor``, as the reference)."""
+    GLOBAL_TAPE.instructs.clear()
+    slices = []
+    y = f(x)
+    n = y.data.size
+    for i in range(n):
+        storage = {}
+        e = np.zeros(n, dtype=np.float64 if y.data.is_real else np.complex128)
+        e[i] = 1
+        gy = DiffTensor(B200Array.from_numpy(e.reshape(y.data.shape, order="F"), y.data.ctx), requires_grad=False)
+        accumulate_gradient_(storage, getid(y), gy)
+        storage["_keep"] = [y, gy]
+        back_(GLOBAL_TAPE, storage)
+        g = getgrad(storage, x)
+        slices.append(reshape(g, (g.data.size,)))
+    return transpose(hcat(*slices))
+
+
+def hessian(f, x):  # TensorAD.jl:166-168
+    return jacobian(lambda z: gradient(f, z)[0], x)
+
+
 def init_storage_(y, requires_grad=False):  # TensorAD.jl:142-146
     storage = {}
     ones = B200Array.from_numpy(np.ones(y.data.shape, dtype=np.float64 if y.data.is_real else np.complex128), y.data.ctx)
@@ -196,9 +220,13 @@ def _project_eltype(x, y):  # rules.jl:165-166
     return real(y) if _is_real(x) else bcomplex(y)
 
 
-def _einsum_rule(ixs, xs, iy):  # rules.jl:1-8
+def _einsum_rule(ixs, xs, iy, size_dict=None):  # rules.jl:1-8
     xs = list(xs)
-    y = _arr.einsum_device(ixs, [x.data for x in xs], iy)
+    y = _arr.einsum_device(ixs, [x.data for x in xs], iy, None, size_dict)
+    sd = dict(size_dict or {})   # get_size_dict: the pullbacks may need the size of a label the cotangent lacks
+    for ix, x in zip(ixs, xs):
+        for l, s in zip(ix, x.shape):
+            sd[l] = s
 
     def mk(i):
         def back(dy):  # OMEinsum.einsum_grad(ixs, xs, iy, size_dict, conj(dy), i)
@@ -206,7 +234,7 @@ def _einsum_rule(ixs, xs, iy):  # rules.jl:1-8
             nxs = list(xs)
             nixs[i] = list(iy)
             nxs[i] = conj(dy)
-            return _project_eltype(xs[i], conj(_es.einsum(nixs, nxs, list(ixs[i]))))
+            return _project_eltype(xs[i], conj(_es.einsum(nixs, nxs, list(ixs[i]), size_dict=sd)))
         return back
     return difftensor(y, "einsum", *[(xs[i], mk(i)) for i in range(len(xs))])
 
@@ -356,14 +384,44 @@ def bcos(a):
     return difftensor(a.data.cos(), "cos.", (a, lambda dy: bmul(neg(dy), conj(bsin(a)))))
 
 
-def vcat(*tensors):  # rules.jl:110-123 for vectors
+def cat(tensors, dims):  # rules.jl:110-123 (``dims`` 1-based like Julia)
+    """``cat(a, B...; dims)``.  Column-major storage makes concatenation along the LAST axis a plain concatenation of the
+    flattened operands; any other axis is first rotated to the end with a (taped) permutation einsum.  The pullback of
+    operand ``i`` is the matching slice of the cotangent, ``getindex(dy, ..., lo:hi, ...)`` in the reference."""
     tensors = list(tensors)
-    ends = np.cumsum([t.shape[0] for t in tensors])
+    nd = max(tensors[0].ndim, dims)
+    ax = dims - 1
+    shapes = [tuple(t.shape) + (1,) * (nd - t.ndim) for t in tensors]
+    for sh in shapes:
+        if any(sh[k] != shapes[0][k] for k in range(nd) if k != ax):
+            raise ValueError("cat: mismatch in dimension sizes")
+    if ax != nd - 1:   # rotate ``ax`` to the end, concatenate there, rotate back
+        labs = list(range(1, nd + 1))
+        moved = [l for l in labs if l != dims] + [dims]
+        rot = [_es.einsum([labs], [reshape(t, sh)], moved) for t, sh in zip(tensors, shapes)]
+        return _es.einsum([moved], [cat(rot, nd)], labs)
+    lead = int(np.prod(shapes[0][:-1], dtype=np.int64))
+    ends = np.cumsum([sh[-1] for sh in shapes])
+    out_shape = shapes[0][:-1] + (int(ends[-1]),)
 
     def mk(i):
         lo = 0 if i == 0 else int(ends[i - 1])
-        return lambda dy: getindex(dy, slice(lo, int(ends[i])))
-    return difftensor(_arr.concat([t.data for t in tensors]), "cat", *[(tensors[i], mk(i)) for i in range(len(tensors))])
+        hi = int(ends[i])
+
+        def back(dy):
+            flat = reshape(dy, (lead * int(ends[-1]),))
+            return reshape(getindex(flat, slice(lead * lo, lead * hi)), tuple(tensors[i].shape))
+        return back
+    data = _arr.concat([t.data for t in tensors]).reshape(out_shape)
+    return difftensor(data, "cat", *[(tensors[i], mk(i)) for i in range(len(tensors))])
+
+
+def vcat(*tensors):
+    return cat(tensors, 1)
+
+
+def hcat(*tensors):
+    return cat(tensors, 2)
 
 
 def real(x):

@@ -31,6 +31,30 @@ def test_library_builds_loads_and_exports_every_symbol():
     assert tne_b200._lib.lib().tne_version() >= 100
 
 
+def test_julia_shim_matches_the_header():
+    """julia/TensorNetworkEvolveB200.jl cannot be executed here (no Julia runtime): every ccall signature and struct
+    mirror is diffed mechanically against include/tne.h, and the PEPS dispatch uses the reference's three type parameters."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import check_julia_ccalls as chk
+    assert chk.problems() == []
+    jl = open(os.path.join(ROOT, "julia", "TensorNetworkEvolveB200.jl")).read()
+    assert len(chk.julia_ccalls(jl)) >= 15
+    assert not re.search(r"PEPS\{[^}]*,[^}]*,[^}]*,[^}]*\}", jl)      # abstract type PEPS{T,NF,LT}: src/peps.jl:4
+    bad = jl.replace("(Ptr{Cvoid}, Int64, Ptr{Int64}), CTX[], x.handle, h))", "(Ptr{Cvoid}, Cint, Ptr{Int64}), CTX[], x.handle, h))", 1)
+    assert bad != jl                                                   # the checker does catch a wrong argument type
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        os.makedirs(os.path.join(d, "julia")); os.makedirs(os.path.join(d, "include"))
+        open(os.path.join(d, "julia", "TensorNetworkEvolveB200.jl"), "w").write(bad)
+        open(os.path.join(d, "include", "tne.h"), "w").write(open(os.path.join(ROOT, "include", "tne.h")).read())
+        root, chk.ROOT = chk.ROOT, d
+        try:
+            assert len(chk.problems()) == 1
+        finally:
+            chk.ROOT = root
+
+
 def test_no_cpu_fallback_without_a_device():
     import torch
     import tne_b200

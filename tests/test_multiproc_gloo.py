@@ -90,3 +90,81 @@ def test_wavefronts_and_shard_deal_are_partitions():
         items = list(range(16))
         deal = [[i for i in items if i % world == r] for r in range(world)]
         assert sorted(sum(deal, [])) == items
+
+
+def _product_worker(rank, world, port, outdir):
+    """PRODUCT host code under the planner context (TNE_PLAN_ONLY=1: everything is planned, nothing computed)."""
+    os.environ["TNE_PLAN_ONLY"] = "1"
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    sys.path.insert(0, ROOT)
+    log = os.path.join(outdir, "plan_rank%d.log" % rank)
+    fd = os.open(log, os.O_WRONLY | os.O_CREAT | os.O_TRUNC)
+    os.dup2(fd, 2)                                    # the planner dumps to the C stderr
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import tne_b200 as T
+    from tne_b200 import einsum as es, peps as P
+    ctx = T.context()
+    L, D = 4, 2
+    g = T.grid([L, L])
+    order, segs = T.sweep_plan(g, L)
+    p = T.rand_simplepeps(g, D, np.random.default_rng(7), optimizer=order, segments=segs)
+    h = T.rydberg_hamiltonian(g, 10.0, 0.2, 0.3)
+    # (1) Hamiltonian-term sharding of peps.expect(..., shard=(rank, world)): record what each rank would hand to the device
+    seen = []
+    real = es.expect_terms_device
+
+    def recorder(code, xs, conj, terms, grad_leaves=(), seed=1.0 + 0j, shard=(0, 1)):
+        seen.append([(complex(c), tuple((leaf, t.handle) for leaf, t in repl)) for c, repl in terms])
+        return T.B200Array.from_numpy(np.zeros(())), []
+    es.expect_terms_device = recorder
+    try:
+        T.expect(h, p, p, shard=(rank, world))
+        mine = [(c, tuple(leaf for leaf, _ in repl)) for c, repl in seen[-1]]
+        T.expect(h, p, p, shard=(0, 1))
+        full = [(c, tuple(leaf for leaf, _ in repl)) for c, repl in seen[-1]]
+        # a rank with no terms must not evaluate the bare overlap (tne_expect_terms with n_terms == 0 would)
+        n0 = len(seen)
+        z = T.expect(T.yao.Add(*h.blocks[:1]), p, p, shard=(1, 2))
+        empty_ok = len(seen) == n0 and z.shape == ()
+    finally:
+        es.expect_terms_device = real
+    gathered = [None] * world
+    dist.all_gather_object(gathered, mine)
+    # (2) segment-local slices dealt to the ranks: every rank must plan the SAME collectives in the same order
+    p.code_inner_product.seg_shard = True
+    ctx.set_option("debug", 2)
+    ctx.set_option("rs_comm", world)
+    leaves = [P._dev(t) for t in p.alltensors()] * 2
+    n = len(p.alltensors())
+    try:
+        es.expect_terms_device(p.code_inner_product, leaves, [1] * n + [0] * n, [], list(range(n)), 1.0 + 0j)
+        refused = False
+    except T.TneError:
+        refused = True
+    os.fsync(2)
+    plan = [l for l in open(log).read().splitlines() if l.startswith("[tne-plan]")]
+    plans = [None] * world
+    dist.all_gather_object(plans, plan)
+    if rank == 0:
+        import json
+        json.dump(dict(gathered=[[list(map(str, t)) for t in r] for r in gathered], full=[list(map(str, t)) for t in full],
+                       empty_ok=empty_ok, refused=refused, plans=plans), open(os.path.join(outdir, "res.json"), "w"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_product_sharding_logic_under_the_planner_context(tmp_path):
+    """World 2 over gloo, product code only: peps.expect deals the Hamiltonian terms k % world == rank into disjoint lists
+    whose union is the full list; an empty share yields an explicit zero; the planner gives both ranks identical
+    collective schedules for the slice-sharded programme (reduce-scatter / all-gather classification of checkpoints)."""
+    import json
+    port = 29950 + (os.getpid() % 40)
+    mp.spawn(_product_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    res = json.load(open(tmp_path / "res.json"))
+    full = [tuple(t) for t in res["full"]]
+    parts = [[tuple(t) for t in r] for r in res["gathered"]]
+    assert sorted(parts[0] + parts[1]) == sorted(full) and len(full) == 40
+    assert parts[0] == full[0::2] and parts[1] == full[1::2]
+    assert res["empty_ok"] and res["refused"]
+    assert res["plans"][0] == res["plans"][1] and any("reduce-scatter" in l for l in res["plans"][0])
