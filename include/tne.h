@@ -70,6 +70,10 @@ int tne_set_option(tne_ctx* ctx, const char* key, int64_t value);
 #define TNE_PROFILE_CLASSES 48   /* class = 8 * kernel + log2(k-steps) bucket (0 for kernels without one) */
 int tne_profile_collect(tne_ctx* ctx, double* out);
 
+/* roofline denominators of the context's device, measured now (a few ms): issue peaks of FP64 DMMA (mma.sync.m8n8k4, the
+ * tensor-pipe primitive of every dense contraction step here) and of DFMA, in TFLOP/s */
+int tne_measure_fp64_peak(tne_ctx* ctx, double* dmma_tflops, double* dfma_tflops);
+
 /* ---- device tensors: Array{ComplexF64,N} as used at src/peps.jl:41,132 ---------------- */
 int tne_alloc(tne_ctx* ctx, int rank, const int64_t* dims, tne_buf* out);
 int tne_free(tne_ctx* ctx, tne_buf buf);

@@ -77,6 +77,12 @@ class Context:
                 res.setdefault(n, dict(launches=0, ms=0.0, flops=0.0, bytes=0.0))
         return res
 
+    def measure_fp64_peak(self):
+        """FP64 DMMA / DFMA issue peaks of this device right now, in TFLOP/s (``tne_measure_fp64_peak``)."""
+        a, b = C.c_double(), C.c_double()
+        self.check(self.L.tne_measure_fp64_peak(self.h, C.byref(a), C.byref(b)))
+        return dict(dmma_tflops=a.value, dfma_tflops=b.value)
+
     def mem_info(self):
         a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
         self.check(self.L.tne_mem_info(self.h, C.byref(a), C.byref(b), C.byref(c)))

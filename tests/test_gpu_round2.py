@@ -1,0 +1,281 @@
+"""Round-2 parity additions (all through the C ABI): the block types of ``expect`` the reference tests at
+test/peps.jl:94-110, the rest of the TensorAD surface (trace / diag / repeat einsums, ``jacobian`` / ``hessian`` / ``cat``:
+test/TensorAD/TensorAD.jl:22-39, test/TensorAD/rules.jl:13), a converged ``sr_step``, the error status of the bond
+kernel, and the benchmark-size golden vectors of tests/golden/make_golden_big.py at 1e-10 through the BENCHMARK's plan
+(boundary sweep, one checkpointed segment per column, segment-local slices, fused kernels on)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import einsum as OE, graphs as OG, peps as OP, tebd as OT, tensorad as OAD, timeevolve as OTE, yao as OY
+from helpers import device_peps_like, oracle_peps, rel, seed_for, sweep_order, to_device_hamiltonian
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def crand(rng, shape):
+    return rng.standard_normal(shape) + 1j * rng.standard_normal(shape)
+
+
+# -- expect with two-site put / control terms (test/peps.jl:88-110) ------------------------------------------------
+def test_expect_put2_kron_control_terms(tne):
+    g = OG.test_graph()
+    n = 5
+    rng = np.random.default_rng(31)
+    blocks = []
+    for (i, j) in g.edges():      # test/peps.jl:94: rand() * put(n, (i, j) => kron(Y, Y)) / kron / control, alternating
+        c = rng.random()
+        kind = len(blocks) % 3
+        if kind == 0:
+            blocks.append(c * OY.put(n, (i, j), OY.kron_mat(OY.Y, OY.Y)))
+        elif kind == 1:
+            blocks.append(c * OY.kron(n, (i, OY.Y), (j, OY.Y)))
+        else:
+            blocks.append(c * OY.control(n, i, j, OY.Y))
+    for i in g.vertices():
+        blocks.append(OY.put(n, i, rng.random() * OY.X))
+    h = OY.Add(*blocks)
+    for kind in ("simple", "vidal"):
+        op1, op2 = oracle_peps(g, 2, 41, kind, Dmax=4), oracle_peps(g, 2, 42, kind, Dmax=4)
+        dp1, dp2 = device_peps_like(tne, op1, g, 2, Dmax=4), device_peps_like(tne, op2, g, 2, Dmax=4)
+        ref = OP.expect(h, op1, op2)
+        got = tne.expect(to_device_hamiltonian(tne, h), dp1, dp2).to_numpy()
+        assert rel(got, ref) < 1e-9, kind             # two-site terms go through apply! + SVD (src/peps.jl:456-460)
+        # ... and against the dense state vector, like the reference does (test/peps.jl:109-110)
+        from helpers import dense_apply
+        dense = np.vdot(OP.vec(op1), dense_apply(h, OP.vec(op2)))
+        assert abs(complex(got) - dense) < 1e-8 * abs(dense)
+
+
+def test_expect_gradient_wrt_ket_is_not_dropped(tne):
+    """<psi| H |psi(x)> differentiated w.r.t. the KET: the fused programme only has bra pullbacks, so this must take the
+    term-by-term taped path (src/peps.jl:474-477 tapes apply -> inner_product for both arguments)."""
+    g = OG.test_graph()
+    h = OT.rydberg_hamiltonian(g, 10.0, 0.2, 0.3)
+    hd = to_device_hamiltonian(tne, h)
+    op1 = oracle_peps(g, 2, 11, Dmax=4)
+    dp1 = device_peps_like(tne, op1, g, 2, Dmax=4)
+    v = OP.variables(op1)
+    obra = OP.replace_tensors(op1, [OAD.DiffTensor(t, requires_grad=False) for t in op1.alltensors()])
+    dbra = tne.replace_tensors(dp1, [tne.DiffTensor(t, requires_grad=False) for t in dp1.alltensors()])
+    ref = OAD.gradient(lambda x: OAD.real(OP.expect(h, obra, OP.load_variables(op1, x))), OAD.DiffTensor(v.copy()))[0].data
+    got = tne.gradient(lambda x: tne.tensorad.real(tne.expect(hd, dbra, tne.load_variables(dp1, x))), tne.DiffTensor(v.copy()))[0].to_numpy()
+    assert np.abs(ref).max() > 0 and rel(got, ref) < TOL
+
+
+def test_term_sharding_with_an_empty_share(tne):
+    g = OG.test_graph()
+    op1 = oracle_peps(g, 2, 11, Dmax=4)
+    dp1 = device_peps_like(tne, op1, g, 2, Dmax=4)
+    h = OY.Add(OY.put(5, 2, OY.X))
+    hd = to_device_hamiltonian(tne, h)
+    parts = [tne.expect(hd, dp1, dp1, shard=(r, 3)).to_numpy() for r in range(3)]
+    assert parts[1] == 0 and parts[2] == 0            # NOT the bare overlap <p|p>
+    assert rel(sum(parts), OP.expect(h, op1, op1)) < TOL
+
+
+# -- OMEinsum unary rules with repeated labels and output-only labels ----------------------------------------------
+def test_einsum_trace_diag_repeat(tne):
+    rng = np.random.default_rng(2)
+    a = crand(rng, (6, 6))
+    b = crand(rng, (4, 5, 4))
+    v = crand(rng, (5,))
+    dev = tne.B200Array.from_numpy
+    E = tne.einsum.einsum
+    assert rel(E([[1, 1]], [dev(a)], []).to_numpy(), np.trace(a)) < 1e-14                        # ein"ii->"
+    assert rel(E([[1, 1]], [dev(a)], [1]).to_numpy(), np.diag(a)) < 1e-15                        # ein"ii->i"
+    assert rel(E([[1, 2, 1]], [dev(b)], [2]).to_numpy(), np.einsum("iji->j", b)) < 1e-14         # partial trace
+    assert rel(E([[1]], [dev(v)], [1, 1]).to_numpy(), np.diag(v)) < 1e-15                        # ein"i->ii" (zeros off the diagonal)
+    assert rel(E([[1, 2, 1], [2]], [dev(b), dev(v)], []).to_numpy(), np.einsum("iji,j->", b, v)) < 1e-14
+    s = crand(rng, ())
+    got = E([[]], [dev(s)], [3, 3], size_dict={3: 4}).to_numpy()                                 # ein"->ii": pullback of a trace
+    assert rel(got, s * np.eye(4)) < 1e-15
+    got = E([[1]], [dev(v)], [1, 7], size_dict={7: 3}).to_numpy()                                # repeat along a new label
+    assert rel(got, np.repeat(v[:, None], 3, axis=1)) < 1e-15
+    with pytest.raises(ValueError):
+        E([[1]], [dev(v)], [1, 7])
+
+
+# -- TensorAD: jacobian / hessian / cat (test/TensorAD/TensorAD.jl:22-39, test/TensorAD/rules.jl:13) ------------------
+def _both(tne):
+    """(module, einsum, DiffTensor) pairs for the oracle and the device so that one test body defines f once."""
+    class O:
+        ad = OAD
+        ein = staticmethod(lambda ixs, xs, iy: OE.einsum(ixs, xs, iy))
+        wrap = staticmethod(lambda a: OAD.DiffTensor(np.array(a)))
+        out = staticmethod(lambda t: np.asarray(t.data if hasattr(t, "data") else t))
+
+    class Dv:
+        ad = tne.tensorad
+        ein = staticmethod(lambda ixs, xs, iy: tne.einsum.einsum(ixs, xs, iy))
+        wrap = staticmethod(lambda a: tne.DiffTensor(np.array(a)))
+        out = staticmethod(lambda t: t.to_numpy())
+    return O, Dv
+
+
+@pytest.mark.parametrize("dtype", ["real", "complex"])
+def test_hessians_match_the_oracle(tne, dtype):
+    rng = np.random.default_rng(8)
+    O, Dv = _both(tne)
+    mk = (lambda *s: rng.standard_normal(s)) if dtype == "real" else (lambda *s: crand(rng, s))
+
+    def f1(M):      # ein"ii->"(ein"ij,jk->ik"(x, y)) on the halves of one flat vector (ADTest.jl builds the same wrapper)
+        return lambda xy: M.ein([[1, 1]], [M.ein([[1, 2], [2, 3]], [M.ad.reshape(xy[0:25], (5, 5)), M.ad.reshape(xy[25:50], (5, 5))], [1, 3])], [])
+
+    def f2(M):      # sin.(sin.(sin.(xy))) on a 0-dim tensor
+        return lambda xy: M.ad.bsin(M.ad.bsin(M.ad.bsin(xy)))
+
+    def f3(M):      # ein"i->"((x .* y) .* z) with x = y = z = xy[1:1]
+        return lambda xy: M.ein([[1]], [M.ad.bmul(M.ad.bmul(xy[0:1], xy[0:1]), xy[0:1])], [])
+    for f, x0 in ((f1, mk(50)), (f2, np.asarray(mk())), (f3, mk(3))):
+        if dtype == "complex" and f is f2:
+            x0 = np.asarray(0.5 + 0.2j)
+        ref = O.out(O.ad.hessian(f(O), O.wrap(x0)))
+        got = Dv.out(Dv.ad.hessian(f(Dv), Dv.wrap(x0)))
+        assert got.shape == ref.shape and rel(got, ref) < 1e-12, f.__name__
+
+
+def test_jacobian_of_cat_and_hcat(tne):
+    rng = np.random.default_rng(9)
+    O, Dv = _both(tne)
+    x0 = crand(rng, (24,))
+
+    def f(M):   # cat(reshape(x[1:16], 4, 4), reshape(x[17:24], 4, 2); dims = 2), then a contraction that mixes the columns
+        def g(x):
+            c = M.ad.cat([M.ad.reshape(x[0:16], (4, 4)), M.ad.reshape(x[16:24], (4, 2))], 2)
+            return M.ein([[1, 2], [3, 2]], [c, c], [1, 3])
+        return g
+    ref = O.out(O.ad.jacobian(f(O), O.wrap(x0)))
+    got = Dv.out(Dv.ad.jacobian(f(Dv), Dv.wrap(x0)))
+    assert rel(got, ref) < 1e-12
+    # cat along the FIRST axis of matrices (the rotated path) and hcat / vcat of vectors
+    def f_rows(M):
+        return lambda x: M.ad.cat([M.ad.reshape(x[0:8], (2, 4)), M.ad.reshape(x[8:24], (4, 4))], 1)
+    assert rel(Dv.out(f_rows(Dv)(Dv.wrap(x0))), np.concatenate([x0[:8].reshape(2, 4, order="F"), x0[8:].reshape(4, 4, order="F")], 0)) < 1e-15
+    assert rel(Dv.out(Dv.ad.jacobian(f_rows(Dv), Dv.wrap(x0))), O.out(O.ad.jacobian(f_rows(O), O.wrap(x0)))) < 1e-12
+    h = Dv.ad.hcat(Dv.wrap(x0[:6]), Dv.wrap(x0[6:12]))
+    assert h.shape == (6, 2) and rel(h.to_numpy(), np.stack([x0[:6], x0[6:12]], 1)) < 1e-15
+    assert rel(Dv.ad.vcat(Dv.wrap(x0[:6]), Dv.wrap(x0[6:9])).to_numpy(), x0[:9]) < 1e-15
+
+
+# -- a converged TDVP step (src/timeevolve.jl:1-4) on a grid ---------------------------------------------------------
+def test_sr_step_converged_on_a_grid(tne):
+    L, D = 3, 2
+    g = OG.grid([L, L])
+    order, segs = tne.sweep_plan(tne.grid([L, L]), L)
+    op = oracle_peps(g, D, seed_for(L, D), optimizer=sweep_order(L * L))
+    dp = device_peps_like(tne, op, g, D, optimizer=order, segments=segs)
+    h = OT.rydberg_hamiltonian(g, 10.0, 0.2, 0.3)
+    ref = OTE.sr_step(op, h, tol=1e-12, maxiter=40)
+    got = tne.sr_step(dp, to_device_hamiltonian(tne, h), tol=1e-12, maxiter=40)
+    assert rel(tne.variables(got).to_numpy(), OP.variables(ref)) < 1e-8
+
+
+# -- bond kernel: non-finite input is an error status, not a fault ----------------------------------------------------
+def test_bond_update_reports_non_finite_input(tne):
+    g = OG.test_graph()
+    op = oracle_peps(g, 2, 5, Dmax=4)
+    bad = [np.array(t) for t in op.alltensors()]
+    bad[0][(0,) * bad[0].ndim] = np.nan
+    dp = tne.peps.from_numpy_tensors(device_peps_like(tne, op, g, 2, Dmax=4), bad)
+    gate = OY.time_evolve(OT.bond_hamiltonian(10.0, 0.2, 0.3, 2, 3), 0.03).reshape(2, 2, 2, 2, order="F")
+    with pytest.raises(tne.TneError, match="non-finite"):
+        tne.apply_onbond_(dp, 1, 2, gate)
+    # the context is still alive and correct afterwards
+    dq = device_peps_like(tne, op, g, 2, Dmax=4)
+    tne.apply_onbond_(dq, 1, 2, gate)
+    OP.apply_onbond_(op, 1, 2, gate)
+    assert rel(tne.vec(dq), OP.vec(op)) < 1e-10
+
+
+# -- benchmark-size golden vectors ------------------------------------------------------------------------------------
+def _gold(name):
+    path = os.path.join(GOLD, name)
+    if not os.path.exists(path):
+        pytest.skip("%s not generated (tests/golden/make_golden_big.py)" % name)
+    return np.load(path)
+
+
+def _bench_peps(tne, L, D):
+    """The benchmark's PEPS and plan for an L x L lattice (bench.py): same seed rule, sweep_plan segments."""
+    g = tne.grid([L, L])
+    order, segs = tne.sweep_plan(g, L)
+    p = tne.rand_simplepeps(g, D, np.random.default_rng(seed_for(L, D)), optimizer=order, segments=segs)
+    return g, p
+
+
+@pytest.mark.parametrize("L,D", [(4, 4), (5, 4), (6, 3)])
+def test_full_energy_and_force_golden(tne, L, D):
+    gold = _gold("grid_%dx%d_D%d.npz" % (L, L, D))
+    if "fvec" not in gold:
+        pytest.skip("force not generated yet")
+    g, p = _bench_peps(tne, L, D)
+    h = tne.rydberg_hamiltonian(g, 10.0, 0.2, 0.3)
+    assert rel(tne.variables(p).to_numpy(), gold["variables"]) == 0.0
+    assert rel(tne.inner_product(p, p).to_numpy(), gold["inner"]) < TOL
+    assert rel(tne.expect(h, p, p).to_numpy(), gold["energy"]) < TOL
+    y, f = tne.energy_and_gradient(p, h)
+    assert rel(y.to_numpy(), gold["iloss2"]) < TOL
+    assert rel(f.to_numpy(), gold["fvec"]) < TOL
+    assert rel(tne.fvec(p, h).to_numpy(), gold["fvec"]) < TOL
+
+
+@pytest.mark.parametrize("L,D", [(4, 4), (5, 4)])
+def test_smatrix_golden(tne, L, D):
+    gold = _gold("grid_%dx%d_D%d.npz" % (L, L, D))
+    if "smatrix_x" not in gold:
+        pytest.skip("S.x not generated yet")
+    g, p = _bench_peps(tne, L, D)
+    v = gold["variables"]
+    sx = tne.apply_smatrix(p, tne.DiffTensor(v.copy()), tne.DiffTensor(v.copy()), tne.DiffTensor(gold["x"], requires_grad=False)).to_numpy()
+    # "tape": the oracle's literal reverse-over-reverse; "fd": Richardson central differences of the oracle gradient
+    tol = 1e-9 if str(gold["smatrix_method"]) == "tape" else 2e-8
+    assert rel(sx, gold["smatrix_x"]) < tol
+
+
+def test_6x6_d4_against_the_oracle(tne):
+    """The headline configuration itself.  Oracle values (forward only: one 6x6 D=4 tree is 2.4e12 flop on the CPU): the norm,
+    a structurally representative subset of the 96 terms -- energies <psi|h_k|psi> and iloss2's cores psi^T h_k psi -- and
+    directional derivatives of iloss2 restricted to that subset along one-site directions, all through the benchmark's
+    plan with the same term-DP / segments / slices / fused kernels."""
+    gold = _gold("grid_6x6_D4_partial.npz")
+    L, D = 6, 4
+    g, p = _bench_peps(tne, L, D)
+    assert rel(tne.variables(p).to_numpy(), gold["variables"]) == 0.0
+    h = tne.rydberg_hamiltonian(g, 10.0, 0.2, 0.3)
+    inner = complex(tne.inner_product(p, p).to_numpy())
+    assert abs(inner - complex(gold["inner"])) < TOL * abs(complex(gold["inner"]))
+    ks = [int(k) for k in gold["term_index"]]
+    nE = len(gold["energy_terms"])
+    if nE == 0:
+        pytest.skip("no term energies generated yet")
+    sub = tne.yao.Add(*[h.blocks[k] for k in ks[:nE]])
+    e_sub = complex(tne.expect(sub, p, p).to_numpy())
+    ref = complex(np.sum(gold["energy_terms"]))
+    assert abs(e_sub - ref) < TOL * np.sum(np.abs(gold["energy_terms"]))
+    for k, want in zip(ks[:nE], gold["energy_terms"]):      # every term alone as well (different DP patterns)
+        got = complex(tne.expect(tne.yao.Add(h.blocks[k]), p, p).to_numpy())
+        assert abs(got - complex(want)) < TOL * abs(complex(want)), k
+    # iloss2 = Re sum_k core_k / <psi|psi> at x = variables(psi)   (src/timeevolve.jl:55-60)
+    y, f = tne.energy_and_gradient(p, sub)
+    n2 = abs(complex(gold["inner"]))
+    want_y = float(np.real(np.sum(gold["iloss_core_terms"][:nE]))) / n2
+    assert abs(float(np.real(y.to_numpy())) - want_y) < TOL * np.sum(np.abs(gold["iloss_core_terms"][:nE])) / n2
+    # directional derivatives: dL = dG / n2 - G <dN> / (2 n2^2),  G = Re sum core, dN = 2 Re <psi[s -> V]|psi>
+    if nE < len(ks):
+        return
+    grad = 1j * f.to_numpy()                                 # fvec = -i grad
+    sizes = [t.size for t in p.alltensors()]
+    offs = np.concatenate([[0], np.cumsum(sizes)])
+    G = float(np.real(np.sum(gold["iloss_core_terms"])))
+    for s in [int(s) for s in gold["dir_sites"]]:
+        V = gold["dir_V_s%02d" % s]
+        dG = float(np.real(np.sum(gold["dir_dcore_s%02d" % s])))
+        dN = 2.0 * float(np.real(complex(gold["dir_dinner_s%02d" % s])))
+        want = dG / n2 - G * dN / (2.0 * n2 * n2)
+        got = float(np.real(np.vdot(grad[offs[s - 1]:offs[s]], V)))
+        scale = np.linalg.norm(grad[offs[s - 1]:offs[s]]) * np.linalg.norm(V)
+        assert abs(got - want) < 1e-9 * scale, (s, got, want)
