@@ -34,7 +34,36 @@ def seed_for(L, D):
     return 20260000 + 100 * L + D
 
 
-def peaks():
+def workload_string(L, D):
+    """The same ``config.workload`` in both arms (the driver compares them)."""
+    n, K = L * L, 2 * L * (L - 1) + L * L
+    bulk, edge, corner = max(L - 2, 0) ** 2, 4 * max(L - 2, 0), 4 if L > 1 else 1
+    nvars = 2 * (bulk * D ** 4 + edge * D ** 3 + corner * D ** 2) if L > 2 else None
+    return "%dx%d D=%d SimplePEPS, Rydberg H (%d terms), energy + full gradient (%s complex variables)" % (L, L, D, K, nvars if nvars else "?")
+
+
+def sweep_tree_flops(L, D):
+    """flops(tree) of SURVEY.md 8(d) for the boundary-sweep tree (bra then ket per site), from the host mirror of OMEinsum's
+    cost accounting; one reference-style <H>+grad evaluation is 3 (K + 2) of these."""
+    from oracle import einsum as OE, graphs as OG, peps as OP
+    g = OG.grid([L, L])
+    n = g.nv()
+    order = []
+    for i in range(n):
+        order += [i, n + i]
+    p = OP.zero_simplepeps(g, D, optimizer=order)
+    sizes = {}
+    for vl, t in zip(p.vertex_labels, p.vertex_tensors):
+        for l, s_ in zip(vl, t.shape):
+            sizes[l] = s_
+    for k, l in enumerate(p.virtual_labels):
+        sizes[p.max_index + k + 1] = sizes[l]
+    return OE.tree_cost(p.code_inner_product, sizes)[0]
+
+
+def peaks(ctx=None, device=0):
+    """Roofline denominators: HBM from the driver-written MEASURED_PEAKS.json; the FP64 DMMA issue peak is measured HERE, in
+    this process, by the library (tne_measure_fp64_peak) with its own clocks record."""
     out = {"hbm_gbs": 6650.0, "hbm_source": "fallback", "fp64_dmma_tflops": 37.18, "fp64_source": "profiles/fp64_peaks_r01.json"}
     try:
         m = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -46,6 +75,19 @@ def peaks():
         out["fp64_dmma_tflops"] = float(f["dmma_tflops"])
     except Exception:
         pass
+    if ctx is not None:
+        try:
+            clk = Clocks(device)
+            best = {"dmma_tflops": 0.0, "dfma_tflops": 0.0}
+            for _ in range(8):          # ~0.3 s under load so that the clocks sampler sees it
+                m = ctx.measure_fp64_peak()
+                best = {k: max(best[k], m[k]) for k in best}
+            out["fp64_dmma_tflops"] = best["dmma_tflops"]
+            out["fp64_dfma_tflops"] = best["dfma_tflops"]
+            out["fp64_source"] = "measured in this run: mma.sync.m8n8k4.f64 issue peak (tne_measure_fp64_peak)"
+            out["fp64_clocks"] = clk.stop()
+        except Exception as e:      # an old library: keep the committed number
+            out["fp64_error"] = str(e)
     return out
 
 
@@ -60,6 +102,13 @@ def cpu_sample(L, D, budget_s=15.0):
     energy terms + 2 norms; forward + 2 pullback contractions per node: src/peps.jl:470-476,
     src/TensorAD/rules.jl:1-8)."""
     from oracle import einsum as OE, graphs as OG, peps as OP, tebd as OT
+    cores = os.cpu_count() or 1
+    try:    # torchrun exports OMP_NUM_THREADS=1: pin the BLAS pool explicitly to every host core and say so
+        from threadpoolctl import threadpool_limits, threadpool_info
+        _limit = threadpool_limits(limits=cores)
+        blas_threads = max([int(i.get("num_threads", 1)) for i in threadpool_info()] or [1])
+    except Exception:
+        blas_threads = None
 
     def build(Lx):
         g = OG.grid([Lx, Lx])
@@ -94,9 +143,9 @@ def cpu_sample(L, D, budget_s=15.0):
     dt = time.perf_counter() - t0
     rate = reps * flops_s / dt
     eval_time = 3.0 * (K + 2) * flops_full / rate
-    cores = os.cpu_count() or 1
     return {
-        "value": 1.0 / eval_time, "unit": "evals/s", "cores": cores, "kind": "port",
+        "value": 1.0 / eval_time, "unit": "evals/s", "cores": cores, "blas_threads": blas_threads, "kind": "port",
+        "reference_style_flops_per_eval": 3.0 * (K + 2) * flops_full,
         "sample": "%d x one %dx%d D=%d norm tree (%.2e flop each) through the numpy TTGT restatement of OMEinsum in %.1f s = %.1f GFLOP/s; "
                   "scaled by flops to the %dx%d tree (%.2e flop) x 3*(K+2)=%d trees per eval, K=%d terms; Julia is not installed on the box"
                   % (reps, Ls, Ls, D, flops_s, dt, rate / 1e9, L, L, flops_full, 3 * (K + 2), K),
@@ -120,7 +169,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": "evals/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "c128 (f64)", "data": "synthetic",
-        "config": {"workload": "%dx%d D=%d SimplePEPS, Rydberg H, energy + full gradient" % (args.L, args.L, args.D)},
+        "config": {"workload": workload_string(args.L, args.D),
+                   "note": "CPU restatement of the reference's execution (numpy TTGT = OMEinsum's algorithm); each step is a bounded "
+                           "sample (whole 5x5 D=4 norm trees) scaled by algorithmic flops to 3 (K + 2) trees of the 6x6 network"},
         "cpu_baseline": base,
         "e2e": {"value": v, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -269,14 +320,25 @@ def run_gpu(args):
     ctx.profile_collect()
     barrier()
     pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # per-programme statistics of the same step (norm programme + energy programme): algorithmic vs recomputed flops
+    progs = []
+    real_etd = T.einsum.expect_terms_device
+
+    def spy(*a, **k):
+        r = real_etd(*a, **k)
+        progs.append(ctx.program_stats())
+        return r
+    T.einsum.expect_terms_device = spy
     pe0.record(stream)
     step_resident()
     pe1.record(stream)
+    T.einsum.expect_terms_device = real_etd
     prof = ctx.profile_collect()
     prof_ms = pe0.elapsed_time(pe1)
     ctx.set_option("profile", 0)
     tot_flops = sum(v["flops"] for v in prof.values())
-    pk = peaks()
+    recompute_flops = sum(q["recompute_flops"] for q in progs)
+    pk = peaks(ctx, local)
     dom = max(prof, key=lambda k: prof[k]["ms"])
     dv = prof[dom]
     roof = {
@@ -292,12 +354,47 @@ def run_gpu(args):
         "fp64_frac": (dv["flops"] / (dv["ms"] * 1e-3) / 1e12 / pk["fp64_dmma_tflops"]) if dv["ms"] else None,
         "note": "AI of the absorb step = 8*K*N/(16*(K+N)) = 5.33 flop/B, just under the ridge 37.2 TF / 6.46 TB/s = 5.75: HBM-bound",
     }
+    for tf in ("traffic_r02.json", "traffic_r01.json"):     # dram__bytes of one `ncu --set full` capture of the dominant kernel
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", tf)))
+            if dom in tr:
+                roof["traffic"] = tr[dom].get("dram_bytes_read_plus_write_per_launch")
+                roof["traffic_note"] = dict(tr[dom], source="profiles/" + tf + " (ncu capture, not measured in this run)")
+                break
+        except Exception:
+            pass
+
+    # parity carried by the bench line itself (every N): oracle golden values of THIS configuration, contracted through the
+    # same plan / sharding as the timed step (tests/golden/make_golden_big.py; tests/test_gpu_round2.py has the full test)
+    check = {"energy_re": energy.real, "force_max_abs": fmax}
     try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic_r01.json")))
-        roof["traffic"] = (tr.get(dom) or {}).get("dram_bytes_read_plus_write_per_launch")
-        roof["traffic_note"] = tr.get(dom)
-    except Exception:
-        pass
+        gpath = os.path.join(ROOT, "tests", "golden", "grid_%dx%d_D%d_partial.npz" % (L, L, D))
+        fpath = os.path.join(ROOT, "tests", "golden", "grid_%dx%d_D%d.npz" % (L, L, D))
+        if os.path.exists(gpath):
+            gold = np.load(gpath)
+            inner = complex(T.inner_product(p, p).to_numpy())
+            check["rel_err_inner_vs_golden"] = abs(inner - complex(gold["inner"])) / abs(complex(gold["inner"]))
+            nE = len(gold["energy_terms"])
+            if nE:
+                ks = [int(k) for k in gold["term_index"]][:nE]
+                sub = T.yao.Add(*[h.blocks[k] for k in ks])
+                e_sub = complex(T.expect(sub, p, p).to_numpy())
+                check["rel_err_vs_golden"] = abs(e_sub - complex(np.sum(gold["energy_terms"]))) / float(np.sum(np.abs(gold["energy_terms"])))
+                check["golden"] = "oracle values of <psi|psi> and of %d of the %d Hamiltonian terms (sum |e_k| scale), same plan and sharding as the timed step" % (nE, K)
+        elif os.path.exists(fpath):
+            gold = np.load(fpath)
+            check["rel_err_vs_golden"] = abs(energy.real - float(gold["iloss2"])) / abs(float(gold["iloss2"]))
+            check["force_rel_err_vs_golden"] = float(np.abs(f.to_numpy() - gold["fvec"]).max() / np.abs(gold["fvec"]).max())
+            check["golden"] = "oracle iloss2 and fvec of this configuration (all terms)"
+        dpath = os.path.join(ROOT, "tests", "golden", "device_%dx%d_D%d_n1.npz" % (L, L, D))
+        if os.path.exists(dpath):      # the 1-GPU result of this library (itself checked against the oracle as above)
+            dev1 = np.load(dpath)
+            check["force_max_abs_diff_vs_n1"] = float(np.abs(f.to_numpy() - dev1["fvec"]).max())
+            check["energy_rel_diff_vs_n1"] = abs(energy.real - float(dev1["iloss2"])) / abs(float(dev1["iloss2"]))
+        elif world == 1 and rank == 0 and os.environ.get("TNE_WRITE_N1"):
+            np.savez_compressed(dpath, fvec=f.to_numpy(), iloss2=np.asarray(energy.real))
+    except Exception as e:
+        check["golden_error"] = repr(e)
 
     # end-to-end arm
     for _ in range(min(args.warmup, 1)):
@@ -308,6 +405,32 @@ def run_gpu(args):
     # secondary measurements of the same path (not part of the metric): the metric-vector product of the TDVP
     # step (src/timeevolve.jl:15-52) on the same PEPS and one TEBD sweep of an 8x8, D=4 PEPS (BASELINE configs 3, 4)
     extras = {}
+    if not args.no_extras:
+        # one TDVP step (src/timeevolve.jl:1-4) at a FIXED Krylov size on N GPUs: fvec + `tdvp_matvecs` metric-vector products
+        # (each one tne_expect_terms programme + reverse pass over the slice-sharded tree) + the GMRES algebra on the host
+        import scipy.sparse.linalg as sla
+        nmv = args.tdvp_matvecs
+        vv = T.variables(p).to_numpy()
+        nn = vv.size
+        memo2, mv_ms = {}, []
+
+        def matvec(xr):
+            xc = xr[:nn] + 1j * xr[nn:]
+            t0 = time.perf_counter()
+            sx = T.apply_smatrix(p, T.DiffTensor(vv.copy()), T.DiffTensor(vv.copy()), T.DiffTensor(xc, requires_grad=False), memo=memo2).to_numpy()
+            mv_ms.append(1e3 * (time.perf_counter() - t0))
+            return np.concatenate([sx.real, sx.imag])
+
+        def tdvp_step():
+            b = -1j * T.fvec(p, h).to_numpy()
+            op = sla.LinearOperator((2 * nn, 2 * nn), matvec=matvec, dtype=np.float64)
+            sol, _ = sla.gmres(op, np.concatenate([b.real, b.imag]), x0=np.concatenate([vv.real, vv.imag]), rtol=1e-30, restart=nmv - 1, maxiter=1)
+            return sol
+        tms, _, _ = timed(tdvp_step, 1)
+        extras["tdvp_step"] = {"ms": tms, "matvecs": len(mv_ms), "ms_per_matvec_host_clock": float(np.median(mv_ms[1:])) if len(mv_ms) > 1 else None,
+                               "ms_first_matvec_host_clock": mv_ms[0] if mv_ms else None, "n_gpus": world,
+                               "note": "sr_step of the same %dx%d D=%d PEPS cut at %d S.x products (GMRES restart %d, one cycle): fvec + matvecs, "
+                                       "x-independent contractions memoised after the first product; slices dealt to the ranks like the headline step" % (L, L, D, nmv, nmv - 1)}
     if world == 1 and not args.no_extras:
         v = T.variables(p).to_numpy()
         xr = np.random.default_rng(seed_for(L, D) + 1)
@@ -351,7 +474,7 @@ def run_gpu(args):
             "metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "c128 (f64)", "data": "synthetic",
-            "config": {"workload": "%dx%d D=%d SimplePEPS, Rydberg H (%d terms), energy + full gradient (%d complex variables)" % (L, L, D, K, nvars),
+            "config": {"workload": workload_string(L, D),
                        "plan": "boundary sweep, one checkpointed segment per column, D^2 segment-local slices",
                        "parallelism": "1 GPU" if world == 1 else ("segment-local bond slices dealt to %d GPUs, NCCL %s of column checkpoints, all-reduce of the outputs"
                                                                        % (world, "reduce-scatter / all-gather" if rs_comm else "all-reduce")),
@@ -360,7 +483,11 @@ def run_gpu(args):
             "executed_tflops_per_gpu": tot_flops / (prof_ms * 1e-3) / 1e12 if prof_ms else None,
             "executed_flops_per_step_per_gpu": tot_flops,
             "fp64_peak_frac": (tot_flops / (prof_ms * 1e-3) / 1e12 / pk["fp64_dmma_tflops"]) if prof_ms else None,
-            "reference_style_flops_per_eval": None,
+            "recompute_flops_per_step_per_gpu": recompute_flops,
+            "fp64_frac_excluding_recompute": ((tot_flops - recompute_flops) / (prof_ms * 1e-3) / 1e12 / pk["fp64_dmma_tflops"]) if prof_ms else None,
+            "fp64_peak": {k: pk.get(k) for k in ("fp64_dmma_tflops", "fp64_dfma_tflops", "fp64_source", "fp64_clocks", "fp64_error") if k in pk},
+            "reference_style_flops_per_eval": 3.0 * (K + 2) * sweep_tree_flops(L, D),
+            "algorithmic_speedup_vs_reference_style": 3.0 * (K + 2) * sweep_tree_flops(L, D) / max(1.0, (tot_flops - recompute_flops) * world),
             "roofline": roof,
             "kernels": {k: v for k, v in prof.items() if v["launches"]},
             "cpu_baseline": cpu,
@@ -368,7 +495,7 @@ def run_gpu(args):
                     "ms_per_step": ems / args.steps},
             "gpu_launches": launches,
             "clocks": clk,
-            "check": {"energy_re": energy.real, "force_max_abs": fmax},
+            "check": check,
             "extras": extras,
         }
         print(json.dumps(line))
@@ -388,6 +515,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--tdvp-matvecs", type=int, default=3)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -61,8 +61,8 @@ class Context:
     def profile_collect(self, fine=False):
         """Per kernel: launches, device ms, algorithmic flops and bytes since the last call.  ``fine``: keyed by
         (kernel, bucket) where the bucket of an absorb kernel is log2(padded K / 2) (5, 6: fused launches)."""
-        names = ["gett_generic", "gett_absorb", "gett_reduce", "gett_absorb_tma", "gett_reduce_tma", "gett_site2"]
-        ncls = 48
+        names = ["gett_generic", "gett_absorb", "gett_reduce", "gett_absorb_tma", "gett_reduce_tma", "gett_site2", "gett_site2_bwd", "gett_gemm"]
+        ncls = 64
         out = (C.c_double * (4 * ncls))()
         self.check(self.L.tne_profile_collect(self.h, out))
         res = {}

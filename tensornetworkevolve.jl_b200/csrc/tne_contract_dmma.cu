@@ -528,7 +528,7 @@ gett_absorb_tma(const __grid_constant__ GettDesc d, const cplx* __restrict__ A, 
 // MT x NT output tiles of 8 x 4 complex each; a warp owns a chunk of the reduction range.
 template <int MT, int NT>
 __global__ void __launch_bounds__(256, 2) gett_reduce(const __grid_constant__ GettDesc d, const cplx* __restrict__ A,
-                                                   const cplx* __restrict__ B, cplx* __restrict__ C, int chunk,
+                                                   const cplx* __restrict__ B, cplx* __restrict__ cta_part, int chunk,
                                                    long long nunits) {
     __shared__ double red[MT * NT * 2 * 32];
     for (int e = threadIdx.x; e < MT * NT * 2 * 32; e += blockDim.x) red[e] = 0.0;
@@ -609,26 +609,24 @@ __global__ void __launch_bounds__(256, 2) gett_reduce(const __grid_constant__ Ge
                 for (int nt = 0; nt < NT; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
         }
     }
-    // CTA reduction, then one atomic per element: lane holds complex (m = 8 mt + lrow, n = 4 nt + lcol)
+    // CTA reduction in a FIXED warp order (no floating-point atomics: bit-reproducible gradients), then one partial per CTA;
+    // lane holds complex (m = 8 mt + lrow, n = 4 nt + lcol)
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+        if (warp == w) {
 #pragma unroll
-    for (int mt = 0; mt < MT; ++mt)
+            for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt) {
-            atomicAdd(&red[((mt * NT + nt) * 2 + 0) * 32 + lane], acc[mt][nt][0]);
-            atomicAdd(&red[((mt * NT + nt) * 2 + 1) * 32 + lane], acc[mt][nt][1]);
+                for (int nt = 0; nt < NT; ++nt) {
+                    red[((mt * NT + nt) * 2 + 0) * 32 + lane] += acc[mt][nt][0];
+                    red[((mt * NT + nt) * 2 + 1) * 32 + lane] += acc[mt][nt][1];
+                }
         }
-    __syncthreads();
+        __syncthreads();
+    }
+    cplx* mine = cta_part + (long long)blockIdx.x * (MT * NT * 32);
     for (int e = tid; e < MT * NT * 32; e += blockDim.x) {
         const int tile = e >> 5, l = e & 31;
-        const double re = red[(tile * 2 + 0) * 32 + l], im = red[(tile * 2 + 1) * 32 + l];
-        const int mt = tile / NT, nt = tile - mt * NT;
-        const int m = 8 * mt + (l >> 2), n = 4 * nt + (l & 3);
-        if (m < d.Msz && n < d.Nsz) {
-            long long am, cm, bn, cn;
-            decomp2(d.M, m, am, cm);
-            decomp2(d.N, n, bn, cn);
-            atomic_add_c(C + cm + cn, d.alphaRe * re - d.alphaIm * im, d.alphaRe * im + d.alphaIm * re);
-        }
+        mine[e] = make_double2(red[(tile * 2 + 0) * 32 + l], red[(tile * 2 + 1) * 32 + l]);
     }
 }
 
@@ -656,7 +654,7 @@ constexpr int RED_CONSUMERS = 4;
 template <int MT, int NT>
 __global__ void __launch_bounds__(32 * (RED_CONSUMERS + 1), 1)
 gett_reduce_tma(const __grid_constant__ GettDesc d, const cplx* __restrict__ A, const cplx* __restrict__ B,
-                cplx* __restrict__ C, const RedGeom g) {
+                cplx* __restrict__ cta_part, const RedGeom g) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char* stages = smem_raw;
     long long* poffA = reinterpret_cast<long long*>(smem_raw + RED_STAGES * g.stage_bytes);   // [npA] global offset of plane
@@ -762,26 +760,54 @@ gett_reduce_tma(const __grid_constant__ GettDesc d, const cplx* __restrict__ A, 
         }
         if (++stage == RED_STAGES) { stage = 0; phase ^= 1; }
     }
+    // consumer warps add their accumulators in a FIXED order (no floating-point atomics), one partial per CTA
+    for (int w = 0; w < RED_CONSUMERS; ++w) {
+        if (warp == w) {
 #pragma unroll
-    for (int mt = 0; mt < MT; ++mt)
+            for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt) {
-            atomicAdd(&red[((mt * NT + nt) * 2 + 0) * 32 + lane], acc[mt][nt][0]);
-            atomicAdd(&red[((mt * NT + nt) * 2 + 1) * 32 + lane], acc[mt][nt][1]);
+                for (int nt = 0; nt < NT; ++nt) {
+                    red[((mt * NT + nt) * 2 + 0) * 32 + lane] += acc[mt][nt][0];
+                    red[((mt * NT + nt) * 2 + 1) * 32 + lane] += acc[mt][nt][1];
+                }
         }
-    asm volatile("bar.sync 1, %0;" ::"r"(32 * RED_CONSUMERS));   // consumers only (the producer warp has left)
+        asm volatile("bar.sync 1, %0;" ::"r"(32 * RED_CONSUMERS));   // consumers only (the producer warp has left)
+    }
+    cplx* mine = cta_part + (long long)blockIdx.x * (MT * NT * 32);
     for (int e = tid; e < MT * NT * 32; e += 32 * RED_CONSUMERS) {
         const int tile = e >> 5, l = e & 31;
-        const double re = red[(tile * 2 + 0) * 32 + l], im = red[(tile * 2 + 1) * 32 + l];
-        const int mt = tile / NT, nt = tile - mt * NT;
-        const int m = 8 * mt + (l >> 2), n = 4 * nt + (l & 3);
-        if (m < d.Msz && n < d.Nsz) {
-            long long am, cm, bn, cn;
-            decomp2(d.M, m, am, cm);
-            decomp2(d.N, n, bn, cn);
-            atomic_add_c(C + cm + cn, d.alphaRe * re - d.alphaIm * im, d.alphaRe * im + d.alphaIm * re);
-        }
+        mine[e] = make_double2(red[(tile * 2 + 0) * 32 + l], red[(tile * 2 + 1) * 32 + l]);
     }
+}
+
+// second pass of both reduce kernels: C[m, n] += alpha * sum of the CTA partials, in CTA order (deterministic)
+__global__ void __launch_bounds__(128) gett_reduce_final(const __grid_constant__ GettDesc d, const cplx* __restrict__ part, int nparts, int NT, int ntile_elems,
+                                                        cplx* __restrict__ C) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= ntile_elems) return;
+    double re = 0.0, im = 0.0;
+    for (int g = 0; g < nparts; ++g) { const cplx v = part[(long long)g * ntile_elems + e]; re += v.x; im += v.y; }
+    const int tile = e >> 5, l = e & 31;
+    const int mt = tile / NT, nt = tile - mt * NT;
+    const int m = 8 * mt + (l >> 2), n = 4 * nt + (l & 3);
+    if (m < d.Msz && n < d.Nsz) {
+        long long am, cm, bn, cn;
+        decomp2(d.M, m, am, cm);
+        decomp2(d.N, n, bn, cn);
+        cplx* p = C + cm + cn;
+        const cplx o = *p;
+        *p = make_double2(o.x + d.alphaRe * re - d.alphaIm * im, o.y + d.alphaRe * im + d.alphaIm * re);
+    }
+}
+
+// workspace of the CTA partials of the reduce kernels (stream-ordered: one launch uses it at a time)
+int reduce_part_reserve(tne_ctx* ctx, int64_t elems) {
+    if (ctx->plan_only || elems <= ctx->red_part_elems) return TNE_OK;
+    if (ctx->red_part) { TNE_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->red_part); ctx->red_part = nullptr; ctx->red_part_elems = 0; }
+    const int64_t want = std::max<int64_t>(elems, (int64_t)ctx->sm_count * 2 * 512);
+    TNE_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->red_part), (size_t)want * sizeof(cplx)));
+    ctx->red_part_elems = want;
+    return TNE_OK;
 }
 
 void sort_legs_by(LegSet& L, int which) {  // insertion sort of the legs by stride s0 / s1
@@ -830,7 +856,10 @@ int launch_absorb_tma(tne_ctx* ctx, const ContractPlan& plan, const cplx* A, con
 template <int MT, int NT>
 int launch_reduce_tma(tne_ctx* ctx, const ContractPlan& plan, const RedGeom& g, const cplx* A, const cplx* B, cplx* C) {
     ensure_smem_attr(ctx, gett_reduce_tma<MT, NT>, 220 * 1024);
-    gett_reduce_tma<MT, NT><<<plan.gx, 32 * (RED_CONSUMERS + 1), plan.smem, ctx->stream>>>(plan.d, A, B, C, g);
+    TNE_TRY(reduce_part_reserve(ctx, (int64_t)plan.gx * MT * NT * 32));
+    gett_reduce_tma<MT, NT><<<plan.gx, 32 * (RED_CONSUMERS + 1), plan.smem, ctx->stream>>>(plan.d, A, B, ctx->red_part, g);
+    TNE_LAUNCH_CHECK(ctx);
+    gett_reduce_final<<<(MT * NT * 32 + 127) / 128, 128, 0, ctx->stream>>>(plan.d, ctx->red_part, (int)plan.gx, NT, MT * NT * 32, C);
     TNE_LAUNCH_CHECK(ctx);
     return TNE_OK;
 }
@@ -838,7 +867,10 @@ int launch_reduce_tma(tne_ctx* ctx, const ContractPlan& plan, const RedGeom& g, 
 template <int MT, int NT>
 int launch_reduce(tne_ctx* ctx, const ContractPlan& plan, const cplx* A, const cplx* B, cplx* C) {
     long long nunits = ((long long)plan.aux[3] << 31) | (long long)plan.aux[2];
-    gett_reduce<MT, NT><<<plan.gx, plan.threads, 0, ctx->stream>>>(plan.d, A, B, C, plan.aux[1], nunits);
+    TNE_TRY(reduce_part_reserve(ctx, (int64_t)plan.gx * MT * NT * 32));
+    gett_reduce<MT, NT><<<plan.gx, plan.threads, 0, ctx->stream>>>(plan.d, A, B, ctx->red_part, plan.aux[1], nunits);
+    TNE_LAUNCH_CHECK(ctx);
+    gett_reduce_final<<<(MT * NT * 32 + 127) / 128, 128, 0, ctx->stream>>>(plan.d, ctx->red_part, (int)plan.gx, NT, MT * NT * 32, C);
     TNE_LAUNCH_CHECK(ctx);
     return TNE_OK;
 }

@@ -213,6 +213,8 @@ extern "C" int tne_ctx_destroy(tne_ctx* ctx) {
     for (auto& kv : ctx->free_blocks) cudaFree(kv.second);
     if (ctx->ws) cudaFree(ctx->ws);
     if (ctx->one_dev) cudaFree(ctx->one_dev);
+    if (ctx->s2b_part) cudaFree(ctx->s2b_part);
+    if (ctx->red_part) cudaFree(ctx->red_part);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return TNE_OK;
@@ -275,6 +277,7 @@ extern "C" int tne_set_option(tne_ctx* ctx, const char* key, int64_t value) {
     else if (k == "absorb_tma") ctx->opt_absorb_tma = value;
     else if (k == "no_fuse") ctx->opt_no_fuse = value;
     else if (k == "no_site2") ctx->opt_no_site2 = value;
+    else if (k == "no_site2b") ctx->opt_no_site2b = value;
     else if (k == "no_rows") ctx->opt_no_rows = value;
     else if (k == "no_pdl") ctx->opt_no_pdl = value;   // default 1: measured no gain from programmatic dependent launch
     else if (k == "no_reduce_tma") ctx->opt_no_reduce_tma = value;

@@ -56,6 +56,10 @@ struct tne_ctx {
     int64_t opt_no_pdl = 1;                // 1: no programmatic dependent launch of the absorb kernels
     int64_t opt_no_site2 = 0;              // 1: never fuse the bra and ket step of a site into one kernel
     int64_t opt_no_fuse = 0;               // 1: one launch per contribution (no gett_absorb_multi)
+    int64_t opt_no_site2b = 0;             // 1: never fuse the three reverse ops of a site into one kernel (tne_site2b.cu)
+    cplx* s2b_part = nullptr;              // CTA partials of the fused reverse kernel's leaf gradient
+    cplx* red_part = nullptr;              // CTA partials of the reduce kernels (deterministic two-pass reduction)
+    int64_t red_part_elems = 0;
     int64_t opt_absorb_tma = 0;            // 1: TMA-staged absorb kernel where applicable (default: register-fed)
     int64_t opt_no_reduce_tma = 0;         // 1: register-fed reduce kernel instead of the TMA-staged one
     int64_t opt_rs_comm = 0;               // 1: reduce-scatter / all-gather of column checkpoints instead of all-reduce (tne_tree.cu)
@@ -173,6 +177,26 @@ struct Site2Desc {
 bool site2_plan(tne_ctx* ctx, const TensorRef& A, const TensorRef& B1, const TensorRef& B2, const TensorRef& C, bool accumulate,
                 double a1re, double a1im, double a2re, double a2im, Site2Desc* out);
 int site2_run(tne_ctx* ctx, const Site2Desc& d, const cplx* A, const cplx* B1, const cplx* B2, cplx* C);
+
+// fused reverse pass of one PEPS site: dT = dC . B2^H (kept on the SM), dA = dT . B1^H, dB1 += A^H . dT (tne_site2b.cu)
+struct Site2BwdDesc {
+    LegSet M;                      // boundary rows: s0 A stride, s1 dC stride, s2 dA stride
+    long long Msz;
+    Legs4 K1, X, P, N1, N2;        // (A, B1), (A, B2), (B1, B2), (B1, dC), (B2, dC) strides
+    Legs4 K1d, Xd;                 // s0: dA strides
+    Legs4 K1g, Pg, N1g;            // s0: strides of the leaf gradient dB1
+    int conjC, conjB2;             // dT  = a1 f(dC) f(B2)
+    int conjT2, conjB1;            // dA  = a2 f(dT) f(B1)
+    int conjA, conjT3;             // dB1 += a3 f(A) f(dT)
+    int accumulate;                // dA += ...
+    int part_add;                  // add the CTA partials of the leaf gradient to the workspace instead of overwriting it
+    double a1re, a1im, a2re, a2im, a3re, a3im;
+};
+bool site2b_plan(tne_ctx* ctx, const TensorRef& dC, const TensorRef& B2, const TensorRef& B1, const TensorRef& A, const TensorRef& dA,
+                 const TensorRef& dB1, Site2BwdDesc* out);
+int64_t site2b_part_elems(tne_ctx* ctx);
+int site2b_run(tne_ctx* ctx, const Site2BwdDesc& d, const cplx* dC, const cplx* B2, const cplx* B1, const cplx* A, cplx* dA, cplx* dB1,
+               cplx* part, bool part_add, bool finalize);
 
 // several contributions into one output through the DMMA absorb kernel (see gett_absorb_multi)
 #define TNE_MULTI_MAX 3

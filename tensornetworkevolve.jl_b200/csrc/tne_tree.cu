@@ -406,6 +406,18 @@ struct PhaseOp {
     std::shared_ptr<Site2Desc> s2;
     int s2_a = -1, s2_b1 = -1, s2_b2 = -1;
     double s2_flops = 0, s2_bytes = 0;
+    // fused reverse pass of a site (tne_site2b.cu): this op is dA = dT . B1^H; the producer of dT and the leaf-gradient op
+    // dB1 += A^H . dT are folded in (op.out = dA)
+    std::shared_ptr<Site2BwdDesc> s2b;
+    int s2b_dC = -1, s2b_B2 = -1, s2b_B1 = -1, s2b_A = -1, s2b_dB1 = -1;
+    bool s2b_add = false, s2b_final = true;    // CTA partials of the leaf gradient: add to the workspace / reduce into dB1 afterwards
+    std::vector<int> inputs() const {
+        if (s2) return {s2_a, s2_b1, s2_b2};
+        if (s2b) return {s2b_dC, s2b_B2, s2b_B1, s2b_A};
+        std::vector<int> v = {op.a, op.b};
+        for (auto& ex : extra) { v.push_back(ex.a); v.push_back(ex.b); }
+        return v;
+    }
 };
 
 struct Phase {
@@ -638,6 +650,69 @@ struct Exec {
             for (auto& po : ph.ops) if (!po.dead) kept.push_back(std::move(po));
             ph.ops.swap(kept);
         }
+        // fuse the three reverse ops of a site -- dT = dC . B2^H (single writer), dA = dT . B1^H, dB1 += A^H . dT -- when dT has
+        // no other reader: dT then never exists in memory (tne_site2b.cu)
+        if (!ctx->opt_no_site2b) {
+            std::map<int, std::vector<int>> writers, readers;
+            for (int i = 0; i < (int)ph.ops.size(); ++i) {
+                for (int v : ph.ops[i].inputs()) if (v >= 0) readers[v].push_back(i);
+                writers[ph.ops[i].op.out].push_back(i);
+            }
+            auto plain_bwd = [&](const PhaseOp& po) {
+                return po.op.kind == OP_CONTRACT && po.op.backward && !po.s2 && !po.s2b && !po.dead && !po.first_slice_only && !po.plan.empty && po.extra.empty();
+            };
+            for (int j = 0; j < (int)ph.ops.size(); ++j) {
+                PhaseOp& pj = ph.ops[j];
+                if (!plain_bwd(pj)) continue;
+                for (int side = 0; side < 2 && !pj.s2b; ++side) {
+                    const int dT = side == 0 ? pj.op.a : pj.op.b, vB1 = side == 0 ? pj.op.b : pj.op.a;
+                    const bool cT2 = side == 0 ? pj.op.conj_a : pj.op.conj_b, cB1 = side == 0 ? pj.op.conj_b : pj.op.conj_a;
+                    if (dT < 0 || vB1 < 0 || !ph.views.at(dT).temp) continue;
+                    auto wi = writers.find(dT);
+                    auto ri = readers.find(dT);
+                    if (wi == writers.end() || wi->second.size() != 1 || ri == readers.end() || ri->second.size() != 2) continue;
+                    const int i = wi->second[0];
+                    const int k = ri->second[0] == j ? ri->second[1] : ri->second[0];
+                    if (i >= j || k == j || k <= i) continue;
+                    PhaseOp& pi = ph.ops[i];
+                    PhaseOp& pk = ph.ops[k];
+                    if (!plain_bwd(pi) || !plain_bwd(pk) || pi.op.acc) continue;
+                    // producer of dT: the big operand is the cotangent dC, the small one the ket tensor
+                    const bool a_big = ph.views.at(pi.op.a).nelem >= ph.views.at(pi.op.b).nelem;
+                    const int vdC = a_big ? pi.op.a : pi.op.b, vB2 = a_big ? pi.op.b : pi.op.a;
+                    const bool cC = a_big ? pi.op.conj_a : pi.op.conj_b, cB2 = a_big ? pi.op.conj_b : pi.op.conj_a;
+                    // leaf gradient: the operand that is not dT is the forward boundary A; the output must not be phase-local
+                    if (pk.op.a != dT && pk.op.b != dT) continue;
+                    const int vA = pk.op.a == dT ? pk.op.b : pk.op.a;
+                    const bool cA = pk.op.a == dT ? pk.op.conj_b : pk.op.conj_a, cT3 = pk.op.a == dT ? pk.op.conj_a : pk.op.conj_b;
+                    if (vA < 0 || vA == dT || ph.views.at(pk.op.out).temp) continue;
+                    TensorRef rdC = ref_of(ph, vdC, cC), rB2 = ref_of(ph, vB2, cB2), rB1 = ref_of(ph, vB1, cB1), rA = ref_of(ph, vA, cA);
+                    TensorRef rdA = ref_of(ph, pj.op.out, false), rdB1 = ref_of(ph, pk.op.out, false);
+                    Site2BwdDesc sd;
+                    if (!site2b_plan(ctx, rdC, rB2, rB1, rA, rdA, rdB1, &sd)) continue;
+                    sd.conjC = cC; sd.conjB2 = cB2; sd.conjT2 = cT2; sd.conjB1 = cB1; sd.conjA = cA; sd.conjT3 = cT3;
+                    sd.accumulate = pj.op.acc;
+                    sd.a1re = pi.op.are; sd.a1im = pi.op.aim; sd.a2re = pj.op.are; sd.a2im = pj.op.aim; sd.a3re = pk.op.are; sd.a3im = pk.op.aim;
+                    pj.s2b = std::make_shared<Site2BwdDesc>(sd);
+                    pj.s2b_dC = vdC; pj.s2b_B2 = vB2; pj.s2b_B1 = vB1; pj.s2b_A = vA; pj.s2b_dB1 = pk.op.out;
+                    pj.s2_flops = pi.plan.flops + pj.plan.flops + pk.plan.flops;
+                    pj.s2_bytes = 16.0 * ((double)ph.views.at(vdC).nelem + (double)ph.views.at(vA).nelem + (double)ph.views.at(pj.op.out).nelem);
+                    pi.dead = true; pk.dead = true;
+                }
+            }
+            std::vector<PhaseOp> kept;
+            for (auto& po : ph.ops) if (!po.dead) kept.push_back(std::move(po));
+            ph.ops.swap(kept);
+            // consecutive fused launches into one leaf gradient (the variants of a site) share the CTA-partial workspace: the
+            // first overwrites it, the others add, one reduction into dB1 after the last
+            for (size_t q = 0; q < ph.ops.size(); ++q) {
+                if (!ph.ops[q].s2b) continue;
+                size_t e = q;
+                while (e + 1 < ph.ops.size() && ph.ops[e + 1].s2b && ph.ops[e + 1].s2b_dB1 == ph.ops[q].s2b_dB1) ++e;
+                for (size_t z = q; z <= e; ++z) { ph.ops[z].s2b_add = z > q; ph.ops[z].s2b_final = z == e; }
+                q = e;
+            }
+        }
         // fuse consecutive writers of one output that run the absorb kernel with identical geometry: the group
         // moves to the position of its last member (all inputs are ready there), C is written once
         if (!ctx->opt_no_fuse) {
@@ -645,10 +720,9 @@ struct Exec {
             std::map<int, int> open;   // output value -> index in `merged` of a group that may still grow
             for (auto& po : ph.ops) {
                 const int out = po.op.out;
-                int ins[2] = {po.op.a, po.op.b};
-                for (int v : ins) if (v >= 0) open.erase(v);   // a reader closes the group of the value it reads
+                for (int v : po.inputs()) if (v >= 0) open.erase(v);   // a reader closes the group of the value it reads
                 auto it = open.find(out);
-                if (po.s2) { merged.push_back(po); open.erase(out); continue; }
+                if (po.s2 || po.s2b) { merged.push_back(po); open.erase(out); if (po.s2b) open.erase(po.s2b_dB1); continue; }
                 if (it != open.end() && po.op.kind == OP_CONTRACT && !po.plan.empty) {
                     PhaseOp& g = merged[it->second];
                     if ((int)g.extra.size() + 1 < TNE_MULTI_MAX && g.first_slice_only == po.first_slice_only &&
@@ -677,6 +751,7 @@ struct Exec {
             std::vector<int> ids = {op.out, op.a, op.b};
             for (auto& ex : ph.ops[i].extra) { ids.push_back(ex.a); ids.push_back(ex.b); }
             if (ph.ops[i].s2) { ids = {op.out, ph.ops[i].s2_a, ph.ops[i].s2_b1, ph.ops[i].s2_b2}; }
+            if (ph.ops[i].s2b) { ids = {op.out, ph.ops[i].s2b_dC, ph.ops[i].s2b_B2, ph.ops[i].s2b_B1, ph.ops[i].s2b_A, ph.ops[i].s2b_dB1}; }
             for (int v : ids) {
                 if (v < 0 || !ph.views.at(v).temp) continue;
                 auto it = slot.find(v);
@@ -842,6 +917,25 @@ struct Exec {
         return rc;
     }
 
+    int site2b_launch(const PhaseOp& po, const cplx* dC, const cplx* B2, const cplx* B1, const cplx* A, cplx* dA, cplx* dB1, bool skip_leaf) {
+        const bool fin = po.s2b_final && !skip_leaf;
+        if (!ctx->s2b_part && !ctx->plan_only)
+            TNE_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->s2b_part), (size_t)site2b_part_elems(ctx) * sizeof(cplx)));
+        if (!ctx->opt_profile) return site2b_run(ctx, *po.s2b, dC, B2, B1, A, dA, dB1, ctx->s2b_part, po.s2b_add, fin);
+        tne_ctx::ProfRec r;
+        cudaEvent_t* ev[2] = {&r.e0, &r.e1};
+        for (auto e : ev) {
+            if (!ctx->event_pool.empty()) { *e = ctx->event_pool.back(); ctx->event_pool.pop_back(); }
+            else TNE_CUDA(ctx, cudaEventCreate(e));
+        }
+        r.cls = 8 * 6; r.flops = po.s2_flops; r.bytes = po.s2_bytes;
+        TNE_CUDA(ctx, cudaEventRecord(r.e0, ctx->stream));
+        int rc = site2b_run(ctx, *po.s2b, dC, B2, B1, A, dA, dB1, ctx->s2b_part, po.s2b_add, fin);
+        TNE_CUDA(ctx, cudaEventRecord(r.e1, ctx->stream));
+        ctx->prof.push_back(r);
+        return rc;
+    }
+
     cplx* base_ptr(const Phase& ph, int v) const {
         const Val& val = P.vals[v];
         if (val.ext) return val.ext + val.slice_base;
@@ -857,7 +951,7 @@ struct Exec {
         for (auto& ph : phases)
             for (auto& po : ph.ops) {
                 const long long n = po.first_slice_only ? 1 : ph.nsl;
-                double fl = po.s2 ? po.s2_flops : po.plan.flops;
+                double fl = (po.s2 || po.s2b) ? po.s2_flops : po.plan.flops;
                 for (auto& ex : po.extra) fl += ex.plan.flops;
                 tot_flops += fl * (double)n;
                 tot_launches += n;
@@ -885,6 +979,7 @@ struct Exec {
                 double fl = po.plan.flops, by = po.plan.bytes;
                 const char* kind = po.plan.kernel == 0 ? "generic" : "dmma";
                 if (po.s2) { kind = "site2"; fl = po.s2_flops; by = po.s2_bytes; }
+                else if (po.s2b) { kind = "site2b"; fl = po.s2_flops; by = po.s2_bytes; }
                 else if (!po.extra.empty()) {
                     kind = "multi";
                     for (auto& ex : po.extra) { fl += ex.plan.flops; by += ex.plan.bytes - 16.0 * (double)ex.plan.c_nelem; }
@@ -898,6 +993,7 @@ struct Exec {
                     fprintf(stderr, " %s %d:%lld:%s", nm, v, (long long)w.nelem, w.temp ? "t" : (P.vals[v].ext ? "x" : "c"));
                 };
                 if (po.s2) { pv("A", po.s2_a); pv("B1", po.s2_b1); pv("B2", po.s2_b2); }
+                else if (po.s2b) { pv("dC", po.s2b_dC); pv("B2", po.s2b_B2); pv("B1", po.s2b_B1); pv("A", po.s2b_A); pv("dB1", po.s2b_dB1); }
                 else { pv("a", po.op.a); pv("b", po.op.b); for (auto& ex : po.extra) { pv("a", ex.a); pv("b", ex.b); } }
                 pv("o", po.op.out);
                 fprintf(stderr, "\n");
@@ -931,6 +1027,16 @@ struct Exec {
                     if (po.s2) {
                         TNE_TRY(site2_launch(po, ptr_of(po.s2_a), ptr_of(po.s2_b1), ptr_of(po.s2_b2), ptr_of(po.op.out)));
                         if (po.op.recompute) P.re_flops += po.s2_flops; else { P.flops += po.s2_flops; P.bytes += po.s2_bytes; }
+                        P.n_contract++;
+                        continue;
+                    }
+                    if (po.s2b) {
+                        // replicated segment on several ranks: only rank 0 may add to the (external) leaf gradient; the
+                        // others still need dA and simply never reduce their partials
+                        const bool skip_leaf = world > 1 && !sharded && rank != 0 && P.vals[po.s2b_dB1].ext;
+                        TNE_TRY(site2b_launch(po, ptr_of(po.s2b_dC), ptr_of(po.s2b_B2), ptr_of(po.s2b_B1), ptr_of(po.s2b_A), ptr_of(po.op.out),
+                                              ptr_of(po.s2b_dB1), skip_leaf));
+                        P.flops += po.s2_flops; P.bytes += po.s2_bytes;
                         P.n_contract++;
                         continue;
                     }

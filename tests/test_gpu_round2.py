@@ -279,3 +279,43 @@ def test_6x6_d4_against_the_oracle(tne):
         got = float(np.real(np.vdot(grad[offs[s - 1]:offs[s]], V)))
         scale = np.linalg.norm(grad[offs[s - 1]:offs[s]]) * np.linalg.norm(V)
         assert abs(got - want) < 1e-9 * scale, (s, got, want)
+
+
+# -- fused reverse pass of a site (tne_site2b.cu) -------------------------------------------------------------------------
+def test_fused_reverse_site_kernel(tne):
+    """D = 4 grid with the full Rydberg H: the three reverse ops of a bulk site run as ONE kernel.  Same energy and force as
+    the step-by-step reverse pass (option no_site2b) to rounding, the kernel did launch, and two runs agree bit for bit in
+    the leaf gradients it produced (fixed-order reduction, no floating-point atomics in this kernel)."""
+    ctx = tne.context()
+    L, D = 4, 4
+    g, p = _bench_peps(tne, L, D)
+    h = tne.rydberg_hamiltonian(g, 10.0, 0.2, 0.3)
+    ctx.set_option("profile", 1); ctx.profile_collect()
+    y1, f1 = tne.energy_and_gradient(p, h)
+    used = ctx.profile_collect()
+    ctx.set_option("profile", 0)
+    assert used["gett_site2_bwd"]["launches"] > 0, used
+    ctx.set_option("no_site2b", 1)
+    try:
+        y0, f0 = tne.energy_and_gradient(p, h)
+    finally:
+        ctx.set_option("no_site2b", 0)
+    assert rel(y1.to_numpy(), y0.to_numpy()) < 1e-13
+    assert rel(f1.to_numpy(), f0.to_numpy()) < 1e-12
+    # the norm programme (gradient of <psi|psi> w.r.t. every bra leaf) through the same kernel, against the oracle
+    op = oracle_peps(OG.grid([L, L]), D, seed_for(L, D), optimizer=sweep_order(L * L))
+    gref = OAD.gradient(lambda x: OP.norm(OP.load_variables(op, x)), OAD.DiffTensor(OP.variables(op)))[0].data
+    gdev = tne.gradient(lambda x: tne.norm(tne.load_variables(p, x)), tne.DiffTensor(tne.variables(p)))[0].to_numpy()
+    assert rel(gdev, gref) < TOL
+
+
+def test_gradients_are_bit_reproducible(tne):
+    """No floating-point atomics on the gradient path (fixed-order two-pass reductions in the reduce kernels and in the
+    fused reverse kernel): two evaluations of the same programme give bit-identical energies and forces."""
+    for L, D in ((4, 4), (4, 3)):
+        g, p = _bench_peps(tne, L, D)
+        h = tne.rydberg_hamiltonian(g, 10.0, 0.2, 0.3)
+        y1, f1 = tne.energy_and_gradient(p, h)
+        y2, f2 = tne.energy_and_gradient(p, h)
+        assert np.array_equal(y1.to_numpy(), y2.to_numpy())
+        assert np.array_equal(f1.to_numpy(), f2.to_numpy())

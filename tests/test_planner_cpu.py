@@ -22,8 +22,12 @@ def test_benchmark_programme_plan():
     flops = float(m.group(2))
     # energy programme: term-DP forward + per-column recompute + reverse pass (8.8e13 with the norm programme)
     assert abs(flops - 7.88e13) / 7.88e13 < 0.02, flops
-    rows = {l.split()[0]: l.split() for l in out.splitlines() if l and l.split()[0] in ("site2", "multi", "reduce", "generic")}
+    rows = {l.split()[0]: l.split() for l in out.splitlines() if l and l.split()[0] in ("site2", "site2b", "multi", "reduce", "generic")}
     assert int(rows["site2"][1]) == 3072          # fused bra+ket absorption of the bulk sites, every slice of every sliced column
+    # fused reverse pass (dT, dA, dB1 in one launch): 4 bulk sites x 6 single-contribution variants x 16 slices x 4 sliced columns
+    assert int(rows["site2b"][1]) == 1536
+    off = _plan("6", "4", "no_site2b=1")
+    assert "site2b" not in off and abs(float(re.search(r"total model time [0-9.]+ s, flops ([0-9.e+]+)", off).group(1)) - flops) < 1e-6 * flops
     assert int(rows["multi"][1]) > 0 and int(rows["reduce"][1]) > 0
     phases = [l for l in out.splitlines() if l.startswith("phase")]
     assert len(phases) == 11                      # 5 forward columns (the last one with its reverse ops) + 5 reverse columns ... 6 columns

@@ -45,7 +45,7 @@ def child(L, D, opts, what):
 
 
 RATES = {  # kind -> (TFLOP/s, TB/s)
-    "site2": (25.0, 99.0), "multi": (28.0, 5.0), "absorb": (23.5, 4.4), "reduce": (22.0, 4.6), "generic": (1.0, 1.0),
+    "site2": (25.0, 99.0), "site2b": (25.0, 99.0), "multi": (28.0, 5.0), "absorb": (23.5, 4.4), "reduce": (22.0, 4.6), "generic": (1.0, 1.0),
 }
 
 
@@ -65,7 +65,7 @@ def parse(text):
                 i += 1
                 continue
             v = tok[i + 1]
-            if k in ("a", "b", "A", "B1", "B2", "o"):
+            if k in ("a", "b", "A", "B1", "B2", "o", "dC", "dB1"):
                 vid, n, st = v.split(":")
                 refs.append((k, int(vid), int(n), st))
             elif k in ("seg", "phase", "nsl", "first_only", "kernel", "re", "bwdop", "acc", "M", "N", "K", "B", "out"):
@@ -81,7 +81,7 @@ def parse(text):
 
 
 def classify(d):
-    if d["kind"] in ("site2", "multi", "generic"):
+    if d["kind"] in ("site2", "site2b", "multi", "generic"):
         return d["kind"]
     # dmma kernels: absorb (big M) or reduce (big K)
     return "reduce" if d["K"] >= 8192 else "absorb"
