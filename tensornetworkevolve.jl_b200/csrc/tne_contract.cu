@@ -28,7 +28,7 @@
 // ---------------------------------------------------------------------------------------
 template <int TM, int TN, int TK>
 __global__ void __launch_bounds__(256) gett_generic(const __grid_constant__ GettDesc d, const cplx* __restrict__ A,
-                                                    const cplx* __restrict__ B, cplx* __restrict__ C) {
+                                                    const cplx* __restrict__ B, cplx* __restrict__ C, cplx* __restrict__ splitws) {
     constexpr int RM = TM / 16, RN = TN / 16;
     __shared__ long long offAm[TM], offCm[TM], offBn[TN], offCn[TN], offAk[TK], offBk[TK];
     __shared__ cplx As[TK][TM + 1];
@@ -112,10 +112,39 @@ __global__ void __launch_bounds__(256) gett_generic(const __grid_constant__ Gett
             cplx* p = C + oCb + offCm[mi] + offCn[nj];
             const double vr = d.alphaRe * accr[i][j] - d.alphaIm * acci[i][j];
             const double vi = d.alphaRe * acci[i][j] + d.alphaIm * accr[i][j];
-            if (d.nsplit > 1) atomic_add_c(p, vr, vi);
+            if (d.nsplit > 1) {
+                // split K: every split writes its tile to the workspace; gett_generic_final adds the splits in a fixed order
+                // (no floating-point atomics: bit-reproducible results)
+                const long long tile = ((long long)z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;   // z = bt * nsplit + split
+                splitws[tile * (TM * TN) + mi * TN + nj] = make_double2(vr, vi);
+            }
             else if (d.accumulate) { cplx o = *p; *p = make_double2(o.x + vr, o.y + vi); }
             else *p = make_double2(vr, vi);
         }
+    }
+}
+
+// second pass of a split-K launch: C (+)= sum over the splits, in split order
+template <int TM, int TN>
+__global__ void __launch_bounds__(256) gett_generic_final(const __grid_constant__ GettDesc d, const cplx* __restrict__ splitws, cplx* __restrict__ C) {
+    const long long m0 = (long long)blockIdx.x * TM, n0 = (long long)blockIdx.y * TN, bt = blockIdx.z;
+    long long oAb, oBb, oCb;
+    decomp3(d.Bt, bt, oAb, oBb, oCb);
+    for (int e = threadIdx.x; e < TM * TN; e += blockDim.x) {
+        const int mi = e / TN, nj = e - mi * TN;
+        if (m0 + mi >= d.Msz || n0 + nj >= d.Nsz) continue;
+        double re = 0.0, im = 0.0;
+        for (int sp = 0; sp < d.nsplit; ++sp) {
+            const long long tile = ((bt * d.nsplit + sp) * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+            const cplx v = splitws[tile * (TM * TN) + e];
+            re += v.x; im += v.y;
+        }
+        long long a_, cm, b_, cn;
+        decomp2(d.M, m0 + mi, a_, cm);
+        decomp2(d.N, n0 + nj, b_, cn);
+        cplx* p = C + oCb + cm + cn;
+        if (d.accumulate) { const cplx o = *p; re += o.x; im += o.y; }
+        *p = make_double2(re, im);
     }
 }
 
@@ -285,12 +314,19 @@ int contract_plan(tne_ctx* ctx, const TensorRef& A0, const TensorRef& B0, const 
         long long per = (d.Ksz + ns - 1) / ns;
         per = (per + TK - 1) / TK * TK;
         ns = (d.Ksz + per - 1) / per;
+        // the splits go through a workspace of nsplit x (tiles x TM x TN) elements: keep it below 64 MiB
+        while (ns > 1 && ns * tiles * TM * TN * (long long)sizeof(cplx) > (64LL << 20)) {
+            ns = (ns + 1) / 2;
+            per = (d.Ksz + ns - 1) / ns;
+            per = (per + TK - 1) / TK * TK;
+            ns = (d.Ksz + per - 1) / per;
+        }
         d.nsplit = (int)ns;
         d.kPerSplit = per;
     }
     if (gn > 65535 || d.Bsz * d.nsplit > 65535)
         return tne_fail(ctx, TNE_ERR_UNSUPPORTED, "contraction grid too large (N tiles %lld, batch*split %lld)", gn, d.Bsz * d.nsplit);
-    plan->zero_first = d.nsplit > 1 && !accumulate;  // atomics accumulate into C: clear it first (C is dense)
+    plan->zero_first = false;   // split K is reduced by a second pass (gett_generic_final), which also honours `accumulate`
     plan->gx = (unsigned)gm; plan->gy = (unsigned)gn; plan->gz = (unsigned)(d.Bsz * d.nsplit);
     return TNE_OK;
 }
@@ -320,8 +356,14 @@ static int contract_run_inner(tne_ctx* ctx, const ContractPlan& plan, const cplx
     if (plan.kernel != 0) return gett_fast_run(ctx, plan, A, B, C);
     if (plan.zero_first) TNE_TRY(launch_fill_zero(ctx, C, plan.c_nelem));
     dim3 grid(plan.gx, plan.gy, plan.gz);
-    gett_generic<64, 32, 16><<<grid, 256, 0, ctx->stream>>>(plan.d, A, B, C);
+    if (plan.d.nsplit > 1) TNE_TRY(reduce_part_reserve(ctx, (int64_t)plan.gx * plan.gy * plan.gz * 64 * 32));
+    gett_generic<64, 32, 16><<<grid, 256, 0, ctx->stream>>>(plan.d, A, B, C, ctx->red_part);
     TNE_LAUNCH_CHECK(ctx);
+    if (plan.d.nsplit > 1) {
+        dim3 g2(plan.gx, plan.gy, (unsigned)plan.d.Bsz);
+        gett_generic_final<64, 32><<<g2, 256, 0, ctx->stream>>>(plan.d, ctx->red_part, C);
+        TNE_LAUNCH_CHECK(ctx);
+    }
     return TNE_OK;
 }
 

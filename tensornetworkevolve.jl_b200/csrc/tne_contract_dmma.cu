@@ -21,6 +21,17 @@
 
 #include "tne_gett.cuh"
 
+// workspace of the CTA partials of the reduce kernels (stream-ordered: one launch uses it at a time)
+int reduce_part_reserve(tne_ctx* ctx, int64_t elems) {
+    if (ctx->plan_only || elems <= ctx->red_part_elems) return TNE_OK;
+    if (ctx->red_part) { TNE_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->red_part); ctx->red_part = nullptr; ctx->red_part_elems = 0; }
+    const int64_t want = std::max<int64_t>(elems, (int64_t)ctx->sm_count * 2 * 512);
+    TNE_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->red_part), (size_t)want * sizeof(cplx)));
+    ctx->red_part_elems = want;
+    return TNE_OK;
+}
+
+
 namespace {
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
@@ -780,13 +791,20 @@ gett_reduce_tma(const __grid_constant__ GettDesc d, const cplx* __restrict__ A, 
     }
 }
 
-// second pass of both reduce kernels: C[m, n] += alpha * sum of the CTA partials, in CTA order (deterministic)
-__global__ void __launch_bounds__(128) gett_reduce_final(const __grid_constant__ GettDesc d, const cplx* __restrict__ part, int nparts, int NT, int ntile_elems,
+// second pass of both reduce kernels: C[m, n] += alpha * sum of the CTA partials.  Eight lanes share one element (lane s adds
+// the partials g = s, s + 8, ... in order; fixed shuffle tree): the same association order in every run (deterministic).
+__global__ void __launch_bounds__(256) gett_reduce_final(const __grid_constant__ GettDesc d, const cplx* __restrict__ part, int nparts, int NT, int ntile_elems,
                                                         cplx* __restrict__ C) {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= ntile_elems) return;
+    const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 3, sub = threadIdx.x & 7;
     double re = 0.0, im = 0.0;
-    for (int g = 0; g < nparts; ++g) { const cplx v = part[(long long)g * ntile_elems + e]; re += v.x; im += v.y; }
+    if (e < ntile_elems)
+        for (int g = sub; g < nparts; g += 8) { const cplx v = part[(long long)g * ntile_elems + e]; re += v.x; im += v.y; }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+        re += __shfl_down_sync(0xffffffffu, re, o, 8);
+        im += __shfl_down_sync(0xffffffffu, im, o, 8);
+    }
+    if (e >= ntile_elems || sub != 0) return;
     const int tile = e >> 5, l = e & 31;
     const int mt = tile / NT, nt = tile - mt * NT;
     const int m = 8 * mt + (l >> 2), n = 4 * nt + (l & 3);
@@ -798,16 +816,6 @@ __global__ void __launch_bounds__(128) gett_reduce_final(const __grid_constant__
         const cplx o = *p;
         *p = make_double2(o.x + d.alphaRe * re - d.alphaIm * im, o.y + d.alphaRe * im + d.alphaIm * re);
     }
-}
-
-// workspace of the CTA partials of the reduce kernels (stream-ordered: one launch uses it at a time)
-int reduce_part_reserve(tne_ctx* ctx, int64_t elems) {
-    if (ctx->plan_only || elems <= ctx->red_part_elems) return TNE_OK;
-    if (ctx->red_part) { TNE_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->red_part); ctx->red_part = nullptr; ctx->red_part_elems = 0; }
-    const int64_t want = std::max<int64_t>(elems, (int64_t)ctx->sm_count * 2 * 512);
-    TNE_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->red_part), (size_t)want * sizeof(cplx)));
-    ctx->red_part_elems = want;
-    return TNE_OK;
 }
 
 void sort_legs_by(LegSet& L, int which) {  // insertion sort of the legs by stride s0 / s1
@@ -859,7 +867,7 @@ int launch_reduce_tma(tne_ctx* ctx, const ContractPlan& plan, const RedGeom& g, 
     TNE_TRY(reduce_part_reserve(ctx, (int64_t)plan.gx * MT * NT * 32));
     gett_reduce_tma<MT, NT><<<plan.gx, 32 * (RED_CONSUMERS + 1), plan.smem, ctx->stream>>>(plan.d, A, B, ctx->red_part, g);
     TNE_LAUNCH_CHECK(ctx);
-    gett_reduce_final<<<(MT * NT * 32 + 127) / 128, 128, 0, ctx->stream>>>(plan.d, ctx->red_part, (int)plan.gx, NT, MT * NT * 32, C);
+    gett_reduce_final<<<(MT * NT * 32 * 8 + 255) / 256, 256, 0, ctx->stream>>>(plan.d, ctx->red_part, (int)plan.gx, NT, MT * NT * 32, C);
     TNE_LAUNCH_CHECK(ctx);
     return TNE_OK;
 }
@@ -870,7 +878,7 @@ int launch_reduce(tne_ctx* ctx, const ContractPlan& plan, const cplx* A, const c
     TNE_TRY(reduce_part_reserve(ctx, (int64_t)plan.gx * MT * NT * 32));
     gett_reduce<MT, NT><<<plan.gx, plan.threads, 0, ctx->stream>>>(plan.d, A, B, ctx->red_part, plan.aux[1], nunits);
     TNE_LAUNCH_CHECK(ctx);
-    gett_reduce_final<<<(MT * NT * 32 + 127) / 128, 128, 0, ctx->stream>>>(plan.d, ctx->red_part, (int)plan.gx, NT, MT * NT * 32, C);
+    gett_reduce_final<<<(MT * NT * 32 * 8 + 255) / 256, 256, 0, ctx->stream>>>(plan.d, ctx->red_part, (int)plan.gx, NT, MT * NT * 32, C);
     TNE_LAUNCH_CHECK(ctx);
     return TNE_OK;
 }

@@ -216,6 +216,8 @@ int contract_run(tne_ctx* ctx, const ContractPlan& plan, const cplx* A, const cp
 // C (+)= A * B over the labels; C's layout is given by its labels/strides.
 int contract_launch(tne_ctx* ctx, const TensorRef& A, const TensorRef& B, const TensorRef& C, bool accumulate,
                     double alpha_re = 1.0, double alpha_im = 0.0);
+// workspace of CTA / split partials of the two-pass (deterministic) reductions; grows on demand (tne_contract_dmma.cu)
+int reduce_part_reserve(tne_ctx* ctx, int64_t elems);
 // algorithmic cost of one contraction (SURVEY.md 8(d) accounting)
 void contract_cost(const TensorRef& A, const TensorRef& B, const TensorRef& C, double* flops, double* bytes);
 

@@ -39,7 +39,7 @@ constexpr int SB_WARPS = 4, SB_XW = SB_X / SB_WARPS;        // 4 x values per wa
 constexpr int SB_STRB1 = 2 * SB_P * SB_N1 + 4;              // doubles per B1' row (64 reals of (p, n1) + pad)
 constexpr int SB_NOUT = SB_K1 * SB_P * SB_N1;               // 512 elements of dB1
 
-__device__ __forceinline__ long long legs4_off(const Legs4& L, int idx, int which) {
+__device__ __noinline__ long long legs4_off(const Legs4& L, int idx, int which) {
     long long o = 0;
     for (int i = 0; i < L.n; ++i) {
         int r = idx % L.size[i];
@@ -54,18 +54,28 @@ __device__ __forceinline__ int scr_idx(int n1, int mrow, int c) {
     return ((n1 * SB_TB + mrow) << 3) + (c ^ ((mrow & 1) << 2) ^ ((n1 & 1) << 1));
 }
 
+__device__ __forceinline__ double flip_sign(double x, int mask) {   // x * (+-1) on the integer pipe (the FP64 pipe belongs to DMMA)
+    return __hiloint2double(__double2hiint(x) ^ mask, __double2loint(x));
+}
+
 __global__ void __launch_bounds__(32 * SB_WARPS, 2)
 gett_site2_bwd(const __grid_constant__ Site2BwdDesc d, const cplx* __restrict__ dC, const cplx* __restrict__ B2,
                const cplx* __restrict__ B1, const cplx* __restrict__ A, cplx* __restrict__ dA, cplx* __restrict__ part) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* B1s = reinterpret_cast<double*>(smem_raw);                                   // [2 K1 = 32][SB_STRB1]
-    cplx* scratch = reinterpret_cast<cplx*>(B1s + 2 * SB_K1 * SB_STRB1);                   // [SB_WARPS][128 * 8]
-    long long* offC_n1 = reinterpret_cast<long long*>(scratch + SB_WARPS * SB_N1 * SB_TB * 8);   // [16]
+    double* B2f = B1s + 2 * SB_K1 * SB_STRB1;                                              // [SB_WARPS][2 j][8 ks][32 lanes]: B2' fragments
+    cplx* scratch = reinterpret_cast<cplx*>(B2f + SB_WARPS * 2 * 8 * 32);                  // [SB_WARPS][128 * 8]
+    long long* offC_n1 = reinterpret_cast<long long*>(scratch + SB_WARPS * SB_N1 * SB_TB * 8);   // [16] each
     long long* offC_n2 = offC_n1 + 16;
     long long* offA_k1 = offC_n2 + 16;
     long long* offA_x = offA_k1 + 16;
     long long* offD_k1 = offA_x + 16;     // dA
     long long* offD_x = offD_k1 + 16;
+    long long* offB1_k1 = offD_x + 16;    // small operands
+    long long* offB1_n1 = offB1_k1 + 16;
+    long long* offB2_x = offB1_n1 + 16;
+    long long* offB2_n2 = offB2_x + 16;
+    long long* offP = offB2_n2 + 16;      // [0..1]: B1 stride of p, [2..3]: B2 stride of p
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int lrow = lane >> 2, lcol = lane & 3;
     if (tid < 16) {
@@ -75,14 +85,20 @@ gett_site2_bwd(const __grid_constant__ Site2BwdDesc d, const cplx* __restrict__ 
         offA_x[tid] = legs4_off(d.X, tid, 0);
         offD_k1[tid] = legs4_off(d.K1d, tid, 0);
         offD_x[tid] = legs4_off(d.Xd, tid, 0);
+        offB1_k1[tid] = legs4_off(d.K1, tid, 1);
+        offB1_n1[tid] = legs4_off(d.N1, tid, 0);
+        offB2_x[tid] = legs4_off(d.X, tid, 1);
+        offB2_n2[tid] = legs4_off(d.N2, tid, 0);
+        if (tid < 2) { offP[tid] = legs4_off(d.P, tid, 0); offP[2 + tid] = legs4_off(d.P, tid, 1); }
     }
+    __syncthreads();
     // B1'[(k1, t)][real index of k = p + 2 n1]:  dA = a2 * f(dT) * f(B1), contraction over (p, n1)
     {
         const double sT = d.conjT2 ? -1.0 : 1.0;
         for (int e = tid; e < SB_K1 * SB_P * SB_N1; e += blockDim.x) {
             const int k = e % (SB_P * SB_N1), k1 = e / (SB_P * SB_N1);
             const int p = k & 1, n1 = k >> 1;
-            cplx v = B1[legs4_off(d.K1, k1, 1) + legs4_off(d.P, p, 0) + legs4_off(d.N1, n1, 0)];
+            cplx v = B1[offB1_k1[k1] + offP[p] + offB1_n1[n1]];
             if (d.conjB1) v.y = -v.y;
             const double br = d.a2re * v.x - d.a2im * v.y, bi = d.a2re * v.y + d.a2im * v.x;
             const int jre = 8 * (k >> 2) + (k & 3), jim = jre + 4;
@@ -92,23 +108,21 @@ gett_site2_bwd(const __grid_constant__ Site2BwdDesc d, const cplx* __restrict__ 
             r1[jre] = bi; r1[jim] = sT * br;
         }
     }
-    // B2' fragments of this warp's 8 columns c = 2 xi + p (x = 4 warp + xi), kept in registers:
-    // b2r[j][ks] = B2'[real column 8 j + lrow][real k = 4 ks + lcol], dT = a1 * f(dC) * f(B2), contraction over n2
-    double b2r[2][8];
+    // B2' fragments of this warp's 8 columns c = 2 xi + p (x = 4 warp + xi), one double per (j, ks, lane):
+    // B2'[real column 8 j + lrow][real k = 4 ks + lcol], dT = a1 * f(dC) * f(B2), contraction over n2
+    double* b2w = B2f + warp * (2 * 8 * 32) + lane;
     {
         const double sC = d.conjC ? -1.0 : 1.0;
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
+#pragma unroll 1
+        for (int e = 0; e < 16; ++e) {
+            const int j = e >> 3, ks = e & 7;
             const int c = 4 * j + (lrow >> 1), t = lrow & 1;
             const int x = SB_XW * warp + (c >> 1), p = c & 1;
-#pragma unroll
-            for (int ks = 0; ks < 8; ++ks) {
-                const int n2 = 4 * (ks >> 1) + lcol, prt = ks & 1;
-                cplx v = B2[legs4_off(d.X, x, 1) + legs4_off(d.P, p, 1) + legs4_off(d.N2, n2, 0)];
-                if (d.conjB2) v.y = -v.y;
-                const double br = d.a1re * v.x - d.a1im * v.y, bi = d.a1re * v.y + d.a1im * v.x;
-                b2r[j][ks] = t == 0 ? (prt == 0 ? br : -sC * bi) : (prt == 0 ? bi : sC * br);
-            }
+            const int n2 = 4 * (ks >> 1) + lcol, prt = ks & 1;
+            cplx v = B2[offB2_x[x] + offP[2 + p] + offB2_n2[n2]];
+            if (d.conjB2) v.y = -v.y;
+            const double br = d.a1re * v.x - d.a1im * v.y, bi = d.a1re * v.y + d.a1im * v.x;
+            b2w[e * 32] = t == 0 ? (prt == 0 ? br : -sC * bi) : (prt == 0 ? bi : sC * br);
         }
     }
     __syncthreads();
@@ -119,6 +133,7 @@ gett_site2_bwd(const __grid_constant__ Site2BwdDesc d, const cplx* __restrict__ 
     const double sx = d.conjA ? -1.0 : 1.0, sy = d.conjT3 ? -1.0 : 1.0;
     const int ysel = (t3 == 0) ? prt3 : 1 - prt3;
     const double ysgn = (t3 == 0) ? (prt3 == 0 ? 1.0 : -sx * sy) : (prt3 == 0 ? sy : sx);
+    const int ymask = ysgn < 0.0 ? (int)0x80000000 : 0;
     double acc3[2][8][2];
 #pragma unroll
     for (int i = 0; i < 2; ++i)
@@ -127,16 +142,54 @@ gett_site2_bwd(const __grid_constant__ Site2BwdDesc d, const cplx* __restrict__ 
 
     const long long ntiles = d.Msz / SB_TB;
     const long long sA0 = d.M.s0[0], sC0 = d.M.s1[0], sD0 = d.M.s2[0];
+
+    // dC fragments of two consecutive n1 (rows m'' = lrow, k = n2): 8 x 128-bit loads per lane
+    auto load_pair = [&](double (&a)[2][8], const cplx* row, int n1) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const cplx v = __ldg(row + offC_n1[n1 + u] + offC_n2[4 * q + lcol]);
+                a[u][2 * q] = v.x; a[u][2 * q + 1] = v.y;
+            }
+    };
+    // stage 1 for two n1: 4 accumulator chains, results to the scratch tile
+    auto mma_pair = [&](const double (&a)[2][8], int n1) {
+        double c[2][2][2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) { c[u][j][0] = 0.0; c[u][j][1] = 0.0; }
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+            const double b0 = b2w[ks * 32], b1 = b2w[(8 + ks) * 32];
+            dmma884(c[0][0][0], c[0][0][1], a[0][ks], b0);
+            dmma884(c[1][0][0], c[1][0][1], a[1][ks], b0);
+            dmma884(c[0][1][0], c[0][1][1], a[0][ks], b1);
+            dmma884(c[1][1][0], c[1][1][1], a[1][ks], b1);
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) scr[scr_idx(n1 + u, lrow, 4 * j + lcol)] = make_double2(c[u][j][0], c[u][j][1]);
+    };
+
+    double aA[2][8], aB[2][8];
+    long long bA = 0, bC = 0, bD = 0;
+    if ((long long)blockIdx.x < ntiles) {
+        decomp3(d.M, (long long)blockIdx.x * SB_TB, bA, bC, bD);
+        load_pair(aA, dC + bC + lrow * sC0, 0);
+    }
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        // offsets of boundary row 8 tile (the 8 rows of a tile share everything above M leg 0)
-        long long bA, bC, bD;
-        decomp3(d.M, tile * SB_TB, bA, bC, bD);
         __syncthreads();   // keeps the four warps on the same tile: they all read the same dC rows (L1 reuse)
         const cplx* dCrow = dC + bC + lrow * sC0;
-        if (tile + gridDim.x < ntiles) {
+        const long long dArow = bD + lrow * sD0;
+        const double* Ad = reinterpret_cast<const double*>(A + bA) + prt3;
+        const bool more = tile + gridDim.x < ntiles;
+        long long nA = 0, nC = 0, nD = 0;
+        if (more) {
             // pull the NEXT tile into L2 while this one computes: its dC rows (256 lines of 128 B, 64 per warp) and this
             // warp's share of its A rows (4 x values x 16 k1 x 8 rows)
-            long long nA, nC, nD;
             decomp3(d.M, (tile + gridDim.x) * SB_TB, nA, nC, nD);
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
@@ -146,38 +199,17 @@ gett_site2_bwd(const __grid_constant__ Site2BwdDesc d, const cplx* __restrict__ 
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(A + nA + offA_x[SB_XW * warp + (ak >> 4)] + offA_k1[4 * ((ak >> 2) & 3)] + 2 * (ak & 3) * sA0));
             }
         }
-        // ---- stage 1: dT[m'', n1, c] for all n1, two n1 at a time (4 independent accumulator chains) ----
-#pragma unroll 2
-        for (int n1 = 0; n1 < SB_N1; n1 += 2) {
-            double a[2][8];
+        // ---- stage 1: dT[m'', n1, c] for all n1; the fragments of the next pair of n1 are in flight under the DMMAs ----
 #pragma unroll
-            for (int u = 0; u < 2; ++u)
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const cplx v = __ldg(dCrow + offC_n1[n1 + u] + offC_n2[4 * q + lcol]);
-                    a[u][2 * q] = v.x; a[u][2 * q + 1] = v.y;
-                }
-            double c[2][2][2];
-#pragma unroll
-            for (int u = 0; u < 2; ++u)
-#pragma unroll
-                for (int j = 0; j < 2; ++j) { c[u][j][0] = 0.0; c[u][j][1] = 0.0; }
-#pragma unroll
-            for (int ks = 0; ks < 8; ++ks)
-#pragma unroll
-                for (int u = 0; u < 2; ++u)
-#pragma unroll
-                    for (int j = 0; j < 2; ++j) dmma884(c[u][j][0], c[u][j][1], a[u][ks], b2r[j][ks]);
-#pragma unroll
-            for (int u = 0; u < 2; ++u)
-#pragma unroll
-                for (int j = 0; j < 2; ++j) scr[scr_idx(n1 + u, lrow, 4 * j + lcol)] = make_double2(c[u][j][0], c[u][j][1]);
+        for (int pr = 0; pr < 8; pr += 2) {
+            load_pair(aB, dCrow, 2 * (pr + 1));
+            mma_pair(aA, 2 * pr);
+            if (pr + 2 < 8) load_pair(aA, dCrow, 2 * (pr + 2));
+            mma_pair(aB, 2 * (pr + 1));
         }
         __syncwarp();
         // ---- stages 2 and 3, two x values at a time.  The A fragments of stage 3 (the only consumer of A: every load is an
         // HBM / L2 access) are requested BEFORE the 128 DMMAs of stage 2, which hide their latency ----
-        const long long dArow = bD + lrow * sD0;
-        const double* Ad = reinterpret_cast<const double*>(A + bA) + prt3;
 #pragma unroll 1
         for (int xi0 = 0; xi0 < SB_XW; xi0 += 2) {
             double af[2][4][2];
@@ -190,6 +222,8 @@ gett_site2_bwd(const __grid_constant__ Site2BwdDesc d, const cplx* __restrict__ 
                     for (int mt = 0; mt < 2; ++mt)
                         af[u][jj][mt] = __ldg(Ad + 2 * ((2 * jj + kin) * sA0 + ox + offA_k1[8 * mt + lrow]));
             }
+            // the first dC fragments of the next tile travel under the last 256 DMMAs of this one
+            if (xi0 + 2 >= SB_XW && more) load_pair(aA, dC + nC + lrow * sC0, 0);
             // stage 2: dA[m'', k1, x] = sum over (p, n1): 8 accumulator chains, one B1' fragment feeds both x values
             double c2[2][4][2];
 #pragma unroll
@@ -220,9 +254,14 @@ gett_site2_bwd(const __grid_constant__ Site2BwdDesc d, const cplx* __restrict__ 
 #pragma unroll
                 for (int nt = 0; nt < 4; ++nt) {
                     cplx* pd = dA + dArow + ox + offD_k1[4 * nt + lcol];
-                    cplx v = make_double2(c2[u][nt][0], c2[u][nt][1]);
-                    if (d.accumulate) { const cplx o = *pd; v.x += o.x; v.y += o.y; }
-                    __stcs(pd, v);
+                    if (d.accumulate) {
+                        // every element of dA belongs to exactly one thread of one launch and launches are ordered on the
+                        // stream: these fire-and-forget reductions are deterministic and do not stall on the old value
+                        atomicAdd(&pd->x, c2[u][nt][0]);
+                        atomicAdd(&pd->y, c2[u][nt][1]);
+                    } else {
+                        __stcs(pd, make_double2(c2[u][nt][0], c2[u][nt][1]));
+                    }
                 }
             }
             // stage 3: dB1[k1, (p, n1)] += sum over (xi, m'') of fA(A) fT(dT); one k-step = rows m'' = 2 jj + kin
@@ -235,7 +274,7 @@ gett_site2_bwd(const __grid_constant__ Site2BwdDesc d, const cplx* __restrict__ 
 #pragma unroll
                     for (int nt = 0; nt < 8; ++nt) {
                         const int np = 4 * nt + (lrow >> 1), p = np & 1, n1 = np >> 1;
-                        bf[nt] = ysgn * reinterpret_cast<const double*>(scr + scr_idx(n1, mrow, 2 * (xi0 + u) + p))[ysel];
+                        bf[nt] = flip_sign(reinterpret_cast<const double*>(scr + scr_idx(n1, mrow, 2 * (xi0 + u) + p))[ysel], ymask);
                     }
 #pragma unroll
                     for (int nt = 0; nt < 8; ++nt) {
@@ -245,6 +284,7 @@ gett_site2_bwd(const __grid_constant__ Site2BwdDesc d, const cplx* __restrict__ 
                 }
         }
         __syncwarp();   // the scratch tile is rewritten by stage 1 of the next tile
+        bA = nA; bC = nC; bD = nD;
     }
 
     // ---- leaf gradient: warps summed in a fixed order through shared memory, one partial per CTA ----
@@ -269,13 +309,20 @@ gett_site2_bwd(const __grid_constant__ Site2BwdDesc d, const cplx* __restrict__ 
     }
 }
 
-// dB1[k1, p, n1] += a3 * sum over the CTA partials, in CTA order (deterministic)
-__global__ void __launch_bounds__(128) site2_bwd_reduce(const __grid_constant__ Site2BwdDesc d, const cplx* __restrict__ part, int nparts,
+// dB1[k1, p, n1] += a3 * sum over the CTA partials.  Eight lanes share one element: lane s adds the partials g = s, s + 8, ...
+// in order, the eight sub-sums are combined by a fixed shuffle tree -- the same association order in every run (deterministic).
+__global__ void __launch_bounds__(256) site2_bwd_reduce(const __grid_constant__ Site2BwdDesc d, const cplx* __restrict__ part, int nparts,
                                                        cplx* __restrict__ dB1) {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= SB_NOUT) return;
+    const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 3, sub = threadIdx.x & 7;
     double re = 0.0, im = 0.0;
-    for (int g = 0; g < nparts; ++g) { const cplx v = part[(long long)g * SB_NOUT + e]; re += v.x; im += v.y; }
+    if (e < SB_NOUT)
+        for (int g = sub; g < nparts; g += 8) { const cplx v = part[(long long)g * SB_NOUT + e]; re += v.x; im += v.y; }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+        re += __shfl_down_sync(0xffffffffu, re, o, 8);
+        im += __shfl_down_sync(0xffffffffu, im, o, 8);
+    }
+    if (e >= SB_NOUT || sub != 0) return;
     const int k1 = e / (SB_P * SB_N1), np = e % (SB_P * SB_N1), p = np & 1, n1 = np >> 1;
     cplx* out = dB1 + legs4_off(d.K1g, k1, 0) + legs4_off(d.Pg, p, 0) + legs4_off(d.N1g, n1, 0);
     const cplx o = *out;
@@ -283,7 +330,8 @@ __global__ void __launch_bounds__(128) site2_bwd_reduce(const __grid_constant__ 
 }
 
 size_t site2b_smem() {
-    return (size_t)(2 * SB_K1 * SB_STRB1) * sizeof(double) + (size_t)SB_WARPS * SB_N1 * SB_TB * 8 * sizeof(cplx) + 6 * 16 * sizeof(long long) + 128;
+    return (size_t)(2 * SB_K1 * SB_STRB1 + SB_WARPS * 2 * 8 * 32) * sizeof(double) + (size_t)SB_WARPS * SB_N1 * SB_TB * 8 * sizeof(cplx) +
+           (10 * 16 + 4) * sizeof(long long) + 128;
 }
 
 struct HL { int32_t label; int64_t size, s[6]; };   // strides in dC, B2, B1, A, dA, dB1 (0: absent)
@@ -398,7 +446,7 @@ int site2b_run(tne_ctx* ctx, const Site2BwdDesc& d0, const cplx* dC, const cplx*
     gett_site2_bwd<<<gx, 32 * SB_WARPS, site2b_smem(), ctx->stream>>>(d, dC, B2, B1, A, dA, part);
     TNE_LAUNCH_CHECK(ctx);
     if (finalize) {
-        site2_bwd_reduce<<<SB_NOUT / 128, 128, 0, ctx->stream>>>(d, part, (int)gx, dB1);
+        site2_bwd_reduce<<<SB_NOUT * 8 / 256, 256, 0, ctx->stream>>>(d, part, (int)gx, dB1);
         TNE_LAUNCH_CHECK(ctx);
     }
     return TNE_OK;
