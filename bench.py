@@ -245,8 +245,8 @@ def run_gpu(args):
         ctx.set_option("absorb_tma", int(os.environ["TNE_VARIANT"]))
     if os.environ.get("TNE_NO_PDL"):
         ctx.set_option("no_pdl", 1)
-    rs_comm = world > 1 and os.environ.get("TNE_RS_COMM", "0") == "1"
-    if rs_comm:   # reduce-scatter / all-gather of the column checkpoints (validated at world 2; all-reduce is the default)
+    rs_comm = world > 1 and os.environ.get("TNE_RS_COMM", "1") == "1"
+    if rs_comm:   # reduce-scatter / all-gather of the column checkpoints (half the NVLink bytes of the all-reduce; TNE_RS_COMM=0 disables)
         ctx.set_option("rs_comm", 1)
     if world > 1:
         T.array.init_comm(ctx, dist, rank, world)
@@ -395,6 +395,30 @@ def run_gpu(args):
             np.savez_compressed(dpath, fvec=f.to_numpy(), iloss2=np.asarray(energy.real))
     except Exception as e:
         check["golden_error"] = repr(e)
+    if world > 1:
+        # multi-GPU parity inside the driver's own N-GPU run (tests/test_gpu_multi.py needs a multi-GPU lease): slice-sharded
+        # energy + force of the 4x4 D=3 golden configuration and the slice-sharded 10x10 D=2 exact norm (BASELINE configs[4]
+        # at its validation size), both against committed oracle values, with the same collectives as the timed step
+        try:
+            mg = {}
+            for (L2, D2, name) in ((4, 3, "grid_4x4_D3.npz"), (10, 2, "grid_10x10_D2_norm.npz")):
+                gp = os.path.join(ROOT, "tests", "golden", name)
+                if not os.path.exists(gp):
+                    continue
+                gold = np.load(gp)
+                g2 = T.grid([L2, L2])
+                o2, s2 = T.sweep_plan(g2, L2)
+                q2 = T.rand_simplepeps(g2, D2, np.random.default_rng(seed_for(L2, D2)), optimizer=o2, segments=s2)
+                q2.code_inner_product.seg_shard = True
+                ip = complex(T.inner_product(q2, q2).to_numpy())
+                mg["%dx%d_D%d_inner_rel_err" % (L2, L2, D2)] = abs(ip - complex(gold["inner"])) / abs(complex(gold["inner"]))
+                if "fvec" in gold:
+                    y2, f2 = T.energy_and_gradient(q2, T.rydberg_hamiltonian(g2, C_, DELTA_, OMEGA_))
+                    mg["%dx%d_D%d_iloss2_rel_err" % (L2, L2, D2)] = abs(float(np.real(y2.to_numpy())) - float(gold["iloss2"])) / abs(float(gold["iloss2"]))
+                    mg["%dx%d_D%d_force_rel_err" % (L2, L2, D2)] = float(np.abs(f2.to_numpy() - gold["fvec"]).max() / np.abs(gold["fvec"]).max())
+            check["multi_gpu_vs_oracle_golden"] = mg
+        except Exception as e:
+            check["multi_gpu_error"] = repr(e)
 
     # end-to-end arm
     for _ in range(min(args.warmup, 1)):

@@ -59,13 +59,13 @@ int tne_last_program_stats(tne_ctx* ctx, double* stats6);
 /* option knobs: "force_generic_kernel", "debug", "profile" (1: bracket every contraction launch with a
  * CUDA-event pair on the context's stream; read the totals with tne_profile_collect), "absorb_tma" (1: use the
  * TMA-staged absorb kernel where it applies), "no_reduce_tma" (1: register-fed reduce kernel), "pad",
- * "no_site2" / "no_site2b" / "no_fuse" (1: never fuse the two steps of a site / the contributions into one output: the step-by-step
+ * "no_permute" (1: unary permutations run on the FMA contraction kernel instead of the tiled transpose), "no_gemm" (1: general dense nodes run on the FMA kernel instead of the tiled DMMA GEMM), "no_site2" / "no_site2b" / "no_fuse" (1: never fuse the two steps of a site / the contributions into one output: the step-by-step
  * launch plan), "rs_comm" (1: multi-GPU checkpoints are combined by reduce-scatter / all-gather instead of all-reduce).
  * A context created with TNE_PLAN_ONLY=1 in the environment on a machine WITHOUT a device is a planner: tree programs are
  * built, costed and dumped to stderr, no kernel ever runs, tne_download and the tree entry points fail. */
 int tne_set_option(tne_ctx* ctx, const char* key, int64_t value);
 /* Per kernel class c = 8 * kernel + bucket (kernel: 0 generic FMA, 1 DMMA absorb, 2 DMMA reduce, 3 DMMA absorb with
- * TMA-staged operand, 4 DMMA reduce with TMA-staged operands, 5 fused two-stage site absorption, 6 fused reverse pass of a site; bucket: log2 of the padded K / 2 of absorb kernels): out[4c .. 4c+3] = launches, summed
+ * TMA-staged operand, 4 DMMA reduce with TMA-staged operands, 5 fused two-stage site absorption, 6 fused reverse pass of a site, 7 tiled DMMA GEMM of a general dense node; bucket: log2 of the padded K / 2 of absorb kernels): out[4c .. 4c+3] = launches, summed
  * device milliseconds, algorithmic real flops, algorithmic bytes since the last collect.  Synchronises. */
 #define TNE_PROFILE_CLASSES 64   /* class = 8 * kernel + log2(k-steps) bucket (0 for kernels without one) */
 int tne_profile_collect(tne_ctx* ctx, double* out);

@@ -487,7 +487,8 @@ struct BondBatch {
 };
 
 // builds the device descriptors and launches the bond kernel for `n_jobs` site-disjoint jobs; does not synchronise
-static int bond_enqueue(tne_ctx* ctx, int n_jobs, const tne_bond_job* in, BondBatch& bb, std::vector<tne_buf>* direct = nullptr) {
+// defer: only build the descriptors (bb.dev); the caller uploads and launches them later (tne_tebd_sweep: one upload per sweep)
+static int bond_enqueue(tne_ctx* ctx, int n_jobs, const tne_bond_job* in, BondBatch& bb, std::vector<tne_buf>* direct = nullptr, bool defer = false) {
     ensure_smem_attr(ctx, bond_kernel, (int)bond_smem_bytes());
     std::vector<BondDev>& dev = bb.dev;
     std::vector<HostJob>& hj = bb.hj;
@@ -559,6 +560,7 @@ static int bond_enqueue(tne_ctx* ctx, int n_jobs, const tne_bond_job* in, BondBa
         d.kept = reinterpret_cast<int*>(meta + 16 * (2 * k));
         d.trunc_err = reinterpret_cast<double*>(meta + 16 * (2 * k + 1));
     }
+    if (defer) return TNE_OK;
     tne_buf& hdev = bb.hdev;
     const int64_t dev_elems = ((int64_t)n_jobs * (int64_t)sizeof(BondDev) + 15) / 16;
     TNE_TRY(buf_new(ctx, {dev_elems}, &hdev));
@@ -586,8 +588,10 @@ static int bond_fetch(tne_ctx* ctx, BondBatch& bb, std::vector<int>& kept, std::
         }
         err[k] = *reinterpret_cast<double*>(hmeta_host.data() + 32 * k + 16);
     }
-    tne_free(ctx, hdev);
+    if (hdev) tne_free(ctx, hdev);
+    hdev = 0;
     tne_free(ctx, hmeta);
+    hmeta = 0;
     return TNE_OK;
 }
 
@@ -692,7 +696,7 @@ extern "C" int tne_tebd_sweep(tne_ctx* ctx, int n_sites, tne_buf* sites, int n_b
             }
             BondBatch& bb = batches[lv];
             std::vector<tne_buf> direct;
-            rc = bond_enqueue(ctx, (int)jobs.size(), jobs.data(), bb, speculative ? &direct : nullptr);
+            rc = bond_enqueue(ctx, (int)jobs.size(), jobs.data(), bb, speculative ? &direct : nullptr, speculative);
             for (auto h : direct) created.push_back(h);
             if (rc) break;
             std::vector<int> kept;
@@ -733,6 +737,28 @@ extern "C" int tne_tebd_sweep(tne_ctx* ctx, int n_sites, tne_buf* sites, int n_b
             for (size_t q = 0; q < err.size() && rc == TNE_OK; ++q)
                 if (std::isnan(err[q])) rc = tne_fail(ctx, TNE_ERR_INVALID, "tebd sweep gate %d: non-finite values in the site tensors", ids[q]);
         }
+        std::vector<BondDev> all_dev;      // alive until the first fetch has synchronised the stream
+        tne_buf hall = 0;
+        if (rc == TNE_OK && speculative) {
+            // ONE descriptor upload for the whole sweep, then the wavefront launches back to back: between two launches the
+            // host does nothing but the launch itself
+            std::vector<size_t> off(n_levels + 1, 0);
+            for (int lv = 0; lv < n_levels; ++lv) off[lv + 1] = off[lv] + batches[lv].dev.size();
+            all_dev.reserve(off[n_levels]);
+            for (int lv = 0; lv < n_levels; ++lv) all_dev.insert(all_dev.end(), batches[lv].dev.begin(), batches[lv].dev.end());
+            rc = buf_new(ctx, {(int64_t)((all_dev.size() * sizeof(BondDev) + 15) / 16)}, &hall);
+            if (rc == TNE_OK) {
+                BondDev* base = reinterpret_cast<BondDev*>(buf_get(ctx, hall)->ptr());
+                cudaError_t e = cudaMemcpyAsync(base, all_dev.data(), all_dev.size() * sizeof(BondDev), cudaMemcpyHostToDevice, ctx->stream);
+                if (e != cudaSuccess) rc = tne_fail(ctx, TNE_ERR_CUDA, "descriptor upload failed: %s", cudaGetErrorString(e));
+                for (int lv = 0; lv < n_levels && rc == TNE_OK; ++lv) {
+                    bond_kernel<<<(unsigned)batches[lv].dev.size(), BOND_THREADS, bond_smem_bytes(), ctx->stream>>>(base + off[lv]);
+                    ctx->launches++;
+                    e = cudaGetLastError();
+                    if (e != cudaSuccess) rc = tne_fail(ctx, TNE_ERR_CUDA, "bond kernel launch failed: %s", cudaGetErrorString(e));
+                }
+            }
+        }
         if (rc == TNE_OK && speculative) {   // one synchronisation for the whole sweep: were all the caps reached?
             for (int lv = 0; lv < n_levels && rc == TNE_OK; ++lv) {
                 std::vector<int> kept;
@@ -745,6 +771,7 @@ extern "C" int tne_tebd_sweep(tne_ctx* ctx, int n_sites, tne_buf* sites, int n_b
                 }
             }
         }
+        if (hall) { cudaStreamSynchronize(ctx->stream); tne_free(ctx, hall); }
         if (rc != TNE_OK) {
             for (auto& bb : batches) { if (bb.hmeta) tne_free(ctx, bb.hmeta); if (bb.hdev) tne_free(ctx, bb.hdev); }
             drop_created();

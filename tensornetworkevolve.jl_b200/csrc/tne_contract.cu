@@ -302,6 +302,7 @@ int contract_plan(tne_ctx* ctx, const TensorRef& A0, const TensorRef& B0, const 
     if (!ctx->opt_force_generic) {
         TNE_TRY(gett_fast_plan(ctx, plan));
         if (plan->kernel != 0) return TNE_OK;
+        if (gemm_plan(ctx, plan)) return TNE_OK;     // general dense node: tiled DMMA GEMM (tne_gemm.cu)
     }
     constexpr int TM = 64, TN = 32, TK = 16;
     long long gm = (d.Msz + TM - 1) / TM, gn = (d.Nsz + TN - 1) / TN;
@@ -353,6 +354,7 @@ int contract_run(tne_ctx* ctx, const ContractPlan& plan, const cplx* A, const cp
 
 static int contract_run_inner(tne_ctx* ctx, const ContractPlan& plan, const cplx* A, const cplx* B, cplx* C) {
     if (plan.swapped) std::swap(A, B);
+    if (plan.kernel == 7) return gemm_run(ctx, plan, A, B, C);
     if (plan.kernel != 0) return gett_fast_run(ctx, plan, A, B, C);
     if (plan.zero_first) TNE_TRY(launch_fill_zero(ctx, C, plan.c_nelem));
     dim3 grid(plan.gx, plan.gy, plan.gz);
@@ -493,7 +495,11 @@ extern "C" int tne_einsum_sized(tne_ctx* ctx, int n_in, const int32_t* labels_fl
     int rc = diagonal_view(ctx, Cv, "the output");
     if (rc == TNE_OK && Cv.labels.size() != C.labels.size())   // ein"i->ii": only the diagonal is written
         rc = launch_fill_zero(ctx, C.ptr, buf_get(ctx, h)->nelem);
-    if (rc == TNE_OK) rc = contract_launch(ctx, T[0], T[1], Cv, false, 1.0, 0.0);
+    if (rc == TNE_OK) {
+        // a pure permutation goes to the shared-memory tiled transpose kernel (tne_permute.cu), anything else is a contraction
+        if (n_in == 1 && !ctx->opt_force_generic && !ctx->opt_no_permute && permute_applicable(T[0], Cv)) rc = permute_launch(ctx, T[0], Cv);
+        else rc = contract_launch(ctx, T[0], T[1], Cv, false, 1.0, 0.0);
+    }
     if (rc != TNE_OK) { tne_free(ctx, h); return rc; }
     *out = h;
     return TNE_OK;

@@ -278,6 +278,8 @@ extern "C" int tne_set_option(tne_ctx* ctx, const char* key, int64_t value) {
     else if (k == "no_fuse") ctx->opt_no_fuse = value;
     else if (k == "no_site2") ctx->opt_no_site2 = value;
     else if (k == "no_site2b") ctx->opt_no_site2b = value;
+    else if (k == "no_gemm") ctx->opt_no_gemm = value;
+    else if (k == "no_permute") ctx->opt_no_permute = value;
     else if (k == "no_rows") ctx->opt_no_rows = value;
     else if (k == "no_pdl") ctx->opt_no_pdl = value;   // default 1: measured no gain from programmatic dependent launch
     else if (k == "no_reduce_tma") ctx->opt_no_reduce_tma = value;

@@ -56,6 +56,8 @@ struct tne_ctx {
     int64_t opt_no_pdl = 1;                // 1: no programmatic dependent launch of the absorb kernels
     int64_t opt_no_site2 = 0;              // 1: never fuse the bra and ket step of a site into one kernel
     int64_t opt_no_fuse = 0;               // 1: one launch per contribution (no gett_absorb_multi)
+    int64_t opt_no_permute = 0;            // 1: unary permutations run as contractions with the constant 1 (gett_generic)
+    int64_t opt_no_gemm = 0;               // 1: never use the tiled DMMA GEMM for general dense nodes (tne_gemm.cu)
     int64_t opt_no_site2b = 0;             // 1: never fuse the three reverse ops of a site into one kernel (tne_site2b.cu)
     cplx* s2b_part = nullptr;              // CTA partials of the fused reverse kernel's leaf gradient
     cplx* red_part = nullptr;              // CTA partials of the reduce kernels (deterministic two-pass reduction)
@@ -216,6 +218,12 @@ int contract_run(tne_ctx* ctx, const ContractPlan& plan, const cplx* A, const cp
 // C (+)= A * B over the labels; C's layout is given by its labels/strides.
 int contract_launch(tne_ctx* ctx, const TensorRef& A, const TensorRef& B, const TensorRef& C, bool accumulate,
                     double alpha_re = 1.0, double alpha_im = 0.0);
+// tiled complex128 DMMA GEMM for general dense nodes (tne_gemm.cu); plan->kernel = 7
+bool gemm_plan(tne_ctx* ctx, ContractPlan* plan);
+int gemm_run(tne_ctx* ctx, const ContractPlan& plan, const cplx* A, const cplx* B, cplx* C);
+// shared-memory tiled tensor permutation (tne_permute.cu)
+bool permute_applicable(const TensorRef& A, const TensorRef& C);
+int permute_launch(tne_ctx* ctx, const TensorRef& A, const TensorRef& C);
 // workspace of CTA / split partials of the two-pass (deterministic) reductions; grows on demand (tne_contract_dmma.cu)
 int reduce_part_reserve(tne_ctx* ctx, int64_t elems);
 // algorithmic cost of one contraction (SURVEY.md 8(d) accounting)

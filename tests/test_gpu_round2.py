@@ -319,3 +319,84 @@ def test_gradients_are_bit_reproducible(tne):
         y2, f2 = tne.energy_and_gradient(p, h)
         assert np.array_equal(y1.to_numpy(), y2.to_numpy())
         assert np.array_equal(f1.to_numpy(), f2.to_numpy())
+
+
+# -- general dense nodes: tiled complex128 DMMA GEMM (tne_gemm.cu) -----------------------------------------------------------
+def test_gemm_kernel_random_shapes(tne):
+    """Contractions with M, N and K all large and / or batch legs (greedy / TreeSA tree nodes, the paired boundary tree) run on
+    the tiled DMMA GEMM: random label orders, odd sizes, batch legs, conjugations, against numpy at 1e-13."""
+    ctx = tne.context()
+    rng = np.random.default_rng(17)
+    cases = [
+        ([[1, 2], [2, 3]], [(300, 70), (70, 50)], [1, 3]),                                         # plain, ragged tiles
+        ([[1, 2], [2, 3]], [(1024, 256), (256, 256)], [3, 1]),                                     # paired-tree shape, transposed output
+        ([[2, 1], [3, 2]], [(96, 200), (40, 96)], [1, 3]),                                         # both operands transposed
+        ([[1, 5, 2, 6], [6, 3, 5, 4]], [(16, 6, 9, 10), (10, 8, 6, 5)], [4, 1, 2, 3]),             # two K legs, split M / N, permuted output
+        ([[7, 1, 2], [2, 7, 3]], [(5, 64, 48), (48, 5, 33)], [1, 7, 3]),                           # batch leg 7 in the middle of the output
+        ([[1, 2, 3, 4], [4, 3, 5, 1]], [(6, 40, 9, 11), (11, 9, 36, 6)], [5, 2, 1]),               # batch label 1 slowest / fastest
+        ([[1, 2, 3, 4, 5], [3, 6, 5, 7]], [(4, 4, 4, 4, 4), (4, 4, 4, 4)], [1, 2, 4, 6, 7]),       # D = 4 legs only (M 64, N 16, K 16)
+        ([[1, 2, 3], [3, 4]], [(27, 27, 81), (81, 27)], [4, 2, 1]),                                # D = 3 powers
+    ]
+    ctx.set_option("profile", 1); ctx.profile_collect()
+    for ixs, shapes, iy in cases:
+        xs = [crand(rng, s) for s in shapes]
+        for conj in ([0, 0], [1, 0], [0, 1], [1, 1]):
+            want = OE.einsum_raw(ixs, [np.conj(x) if c else x for x, c in zip(xs, conj)], iy)
+            got = tne.einsum.einsum(ixs, [tne.B200Array.from_numpy(x) for x in xs], iy, conj=conj).to_numpy()
+            assert rel(got, want) < 1e-13, (ixs, iy, conj)
+    used = ctx.profile_collect()
+    ctx.set_option("profile", 0)
+    assert used["gett_gemm"]["launches"] >= 16, used       # the tiny cases may stay on the FMA kernel (latency-bound anyway)
+    # the same contractions on the FMA kernel (option no_gemm): the two kernels agree to rounding
+    ctx.set_option("no_gemm", 1)
+    try:
+        ixs, shapes, iy = cases[3]
+        xs = [crand(rng, s) for s in shapes]
+        ref = tne.einsum.einsum(ixs, [tne.B200Array.from_numpy(x) for x in xs], iy).to_numpy()
+    finally:
+        ctx.set_option("no_gemm", 0)
+    assert rel(tne.einsum.einsum(ixs, [tne.B200Array.from_numpy(x) for x in xs], iy).to_numpy(), ref) < 1e-13
+
+
+def test_greedy_and_paired_trees_run_on_dmma_kernels(tne):
+    """Trees other than the hand-built sweep on a 5x5 D=4 PEPS, against the ORACLE golden <psi|psi>:
+    * the reference's DEFAULT contraction order (GreedyMethod, src/peps.jl:244-245): 1.1e12 flop, nodes like
+      4096 x 65536 x 256 and 256 x 4096 x 65536;
+    * the fully paired boundary tree (bra . ket per site first, then N = K = 256 absorptions).
+    Both match at 1e-10 and the FMA kernel gets < 2 % of the time: the heavy nodes run on the DMMA GEMM / absorb / reduce kernels."""
+    gold = _gold("grid_5x5_D4.npz")
+    ctx = tne.context()
+    L, D = 5, 4
+    g = tne.grid([L, L])
+    n = L * L
+    base = tne.rand_simplepeps(g, D, np.random.default_rng(seed_for(L, D)), optimizer=sweep_order(n))
+    for name, opt in (("greedy", "greedy"), ("paired", [(i, n + i) for i in range(n)])):
+        p = tne.replace_tensors(tne.zero_simplepeps(g, D, optimizer=opt), base.alltensors())
+        tne.inner_product(p, p)                          # warm-up (workspace)
+        ctx.set_option("profile", 1); ctx.profile_collect()
+        got = tne.inner_product(p, p).to_numpy()
+        used = ctx.profile_collect()
+        ctx.set_option("profile", 0)
+        assert rel(got, gold["inner"]) < TOL, name
+        total = sum(v["ms"] for v in used.values())
+        shares = {k: (v["launches"], round(v["ms"], 2), round(v["flops"] / max(v["ms"], 1e-9) / 1e9, 1)) for k, v in used.items() if v["launches"]}
+        assert used["gett_gemm"]["launches"] > 0, (name, shares)
+        assert used["gett_generic"]["ms"] < 0.02 * total, (name, shares)
+
+
+# -- tensor permutation kernel (tne_permute.cu) -----------------------------------------------------------------------------
+def test_permutation_kernel(tne):
+    ctx = tne.context()
+    rng = np.random.default_rng(23)
+    cases = [((3, 4, 5), [3, 1, 2]), ((64, 64), [2, 1]), ((4,) * 8, [8, 3, 1, 6, 2, 7, 4, 5]), ((2, 4, 4, 4, 4, 4), [6, 5, 4, 3, 2, 1]),
+             ((3, 9, 27, 3), [2, 4, 1, 3]), ((100, 7, 33), [1, 3, 2]), ((81, 50), [2, 1]), ((5,), [1]), ((16384, 6), [2, 1]),
+             ((2, 3, 2, 3, 2, 3, 2), [7, 1, 6, 2, 5, 3, 4])]
+    l0 = ctx.launch_count()
+    for shape, perm in cases:
+        x = crand(rng, shape)
+        labels = list(range(1, len(shape) + 1))
+        for conj in (0, 1):
+            got = tne.einsum.einsum([labels], [tne.B200Array.from_numpy(x)], perm, conj=[conj]).to_numpy()
+            want = np.transpose(np.conj(x) if conj else x, [p - 1 for p in perm])
+            assert got.shape == want.shape and np.array_equal(got, want), (shape, perm)
+    assert ctx.launch_count() - l0 == 2 * len(cases)       # one launch each: no zero-fill, no contraction
