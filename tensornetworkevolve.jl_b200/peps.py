@@ -227,7 +227,7 @@ def load_variables(peps, variables):
 
 
 # -- factories, src/peps.jl:244-280 -----------------------------------------------------
-def sweep_plan(g, L, nbonds=1, pair_last_row=True):
+def sweep_plan(g, L, nbonds=1, pair_last_row=True, slice_first_row=False):
     """Boundary-sweep contraction plan for an ``L x L`` ``grid`` PEPS (vertex ``v = x + (y-1) L``): the leaf
     order ``bra_1, ket_1, bra_2, ...`` and checkpointed segments with segment-local slices.
 
@@ -239,7 +239,12 @@ def sweep_plan(g, L, nbonds=1, pair_last_row=True):
     ``nbonds = k > 1`` (bigger lattices): the bonds of the last ``k`` rows between columns ``y-1`` and ``y`` are all
     looped over (``D^(2k)`` slices).  The bond of row ``r`` closes at site ``(r, y)``, so the column is cut into
     ``k`` segments -- rows ``1..L-k+1``, then one row each -- and every segment only loops over the bonds that are
-    still open in it: again no flops are repeated."""
+    still open in it: again no flops are repeated.
+    ``slice_first_row`` (big lattices, forward only: the exact 8 x 8, D = 4 norm): every column also loops over the bond
+    that leaves its FIRST site towards column ``y+1``.  That leg is created by the column's very first absorption, so
+    every intermediate of the column carries one fixed value of it -- ``D^2`` times smaller again -- and nothing but the
+    first (tiny) bra step is repeated; the column's output is written slice by slice through a strided view of the
+    next boundary.  With both bonds looped over the workspace of 8 x 8, D = 4 is two 64 GiB boundaries plus 12 GiB."""
     n = g.nv()
     order = []
     for i in range(n):
@@ -254,6 +259,10 @@ def sweep_plan(g, L, nbonds=1, pair_last_row=True):
     site = lambda x, y: x + (y - 1) * L
     hbond = lambda x, y: emap[(site(x, y - 1), site(x, y))]    # bond between (x, y-1) and (x, y)
     k = max(1, min(int(nbonds), L - 1))
+    if slice_first_row:
+        if k != 1:
+            raise ValueError("slice_first_row needs nbonds = 1")
+        return order, [(site(1, y), ([hbond(L, y)] if y >= 2 else []) + ([hbond(1, y + 1)] if y < L else [])) for y in range(1, L + 1)]
     segments = [(1, [])]
     for y in range(2, L + 1):
         # segment 0 of the column: rows 1 .. L-k+1, all k bonds open; then one segment per remaining row

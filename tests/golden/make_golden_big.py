@@ -4,6 +4,7 @@
     python tests/golden/make_golden_big.py full 6 3 --procs 4     -> tests/golden/grid_6x6_D3.npz
     python tests/golden/make_golden_big.py smatrix 5 4            -> adds x / smatrix_x to grid_5x5_D4.npz
     python tests/golden/make_golden_big.py part66                 -> tests/golden/grid_6x6_D4_partial.npz
+    python tests/golden/make_golden_big.py norm 8 3               -> tests/golden/grid_8x8_D3_norm.npz  (also 8 2, 10 2)
 
 The oracle executes the reference's algorithm literally: one full contraction per Hamiltonian term
 (``src/peps.jl:469-477``) and one TensorAD tape holding every intermediate (``src/TensorAD/TensorAD.jl:131-164``).
@@ -169,6 +170,18 @@ def make_part66(memgb):
         _write66(out, en, il, dirs, dG, dN)
 
 
+def make_norm(L, D, memgb):
+    """<psi|psi> of the seeded L x L PEPS through the oracle's inner_product (src/peps.jl:106-110), forward only: the
+    validation sizes of BASELINE configs[3] (8x8) and configs[4] (10x10) whose D = 4 boundary does not fit a CPU."""
+    _limit_memory(memgb)
+    g, p, h = setup(L, D)
+    t = time.time()
+    inner = np.asarray(OP.inner_product(p, p))
+    path = os.path.join(ROOT, "tests", "golden", "grid_%dx%d_D%d_norm.npz" % (L, L, D))
+    np.savez_compressed(path, variables=OP.variables(p), inner=inner, norm=np.sqrt(np.abs(inner)))
+    print("[golden] wrote %s (%.1f s): inner = %r" % (path, time.time() - t, complex(inner)), flush=True)
+
+
 def _write66(out, en, il, dirs, dG, dN):
     o = dict(out)
     o["energy_terms"] = np.array([complex(x) for x in en])
@@ -183,7 +196,7 @@ def _write66(out, en, il, dirs, dG, dN):
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("what", choices=["full", "smatrix", "part66"])
+    ap.add_argument("what", choices=["full", "smatrix", "part66", "norm"])
     ap.add_argument("L", type=int, nargs="?", default=5)
     ap.add_argument("D", type=int, nargs="?", default=4)
     ap.add_argument("--procs", type=int, default=1)
@@ -194,5 +207,7 @@ if __name__ == "__main__":
         make_full(a.L, a.D, a.procs, a.memgb)
     elif a.what == "smatrix":
         make_smatrix(a.L, a.D, a.method, a.memgb)
+    elif a.what == "norm":
+        make_norm(a.L, a.D, a.memgb)
     else:
         make_part66(a.memgb)

@@ -1,0 +1,87 @@
+"""Exact <psi|psi> of big square-lattice PEPS with the two-bond sliced sweep (sweep_plan(slice_first_row=True)):
+golden checks at the validation sizes, then a timed run.  One rank or under torchrun (slices dealt to the ranks).
+
+    python tools/norm_big.py check                 # 4x4 D=3, 5x5 D=4, 8x8 D=2, 8x8 D=3, 10x10 D=2 against the oracle goldens
+    python tools/norm_big.py time 8 4 [reps]       # BASELINE configs[3]: exact 8x8 D=4 norm (64 GiB boundary)
+"""
+import json, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np
+import tne_b200 as T
+from helpers import seed_for
+
+world = int(os.environ.get("WORLD_SIZE", "1"))
+rank = int(os.environ.get("RANK", "0"))
+dist = None
+if world > 1:
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+    dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])))
+ctx = T.context()
+for kv in os.environ.get("TNE_OPTS", "").split(","):
+    if "=" in kv:
+        ctx.set_option(kv.split("=")[0], int(kv.split("=")[1]))
+if world > 1:
+    T.array.init_comm(ctx, dist, rank, world)
+
+
+def big_peps(L, D):
+    g = T.grid([L, L])
+    order, segs = T.sweep_plan(g, L, slice_first_row=True)
+    p = T.rand_simplepeps(g, D, np.random.default_rng(seed_for(L, D)), optimizer=order, segments=segs)
+    if world > 1:
+        p.code_inner_product.seg_shard = True
+    return p
+
+
+def say(*a):
+    if rank == 0:
+        print(*a, flush=True)
+
+
+what = sys.argv[1]
+if what == "check":
+    worst = 0.0
+    for L, D, name in ((4, 3, "grid_4x4_D3.npz"), (5, 4, "grid_5x5_D4.npz"), (8, 2, "grid_8x8_D2_norm.npz"), (8, 3, "grid_8x8_D3_norm.npz"),
+                       (10, 2, "grid_10x10_D2_norm.npz")):
+        path = os.path.join(ROOT, "tests", "golden", name)
+        if not os.path.exists(path):
+            say("missing", name)
+            continue
+        gold = np.load(path)
+        p = big_peps(L, D)
+        assert np.array_equal(T.variables(p).to_numpy(), gold["variables"])
+        t0 = time.time()
+        ip = complex(T.inner_product(p, p).to_numpy())
+        err = abs(ip - complex(gold["inner"])) / abs(complex(gold["inner"]))
+        worst = max(worst, err)
+        st = ctx.program_stats()
+        say("%dx%d D=%d  <psi|psi> rel err vs oracle %.2e  (%.3e flop, workspace %.2f GiB, %.2f s, world %d)" % (L, L, D, err, st["flops"], st["workspace_bytes"] / 2 ** 30, time.time() - t0, world))
+    assert worst < 1e-10, worst
+    say("NORM CHECK OK")
+else:
+    L, D = int(sys.argv[2]), int(sys.argv[3])
+    reps = int(sys.argv[4]) if len(sys.argv) > 4 else 1
+    p = big_peps(L, D)
+    out = []
+    for r in range(reps + 1):
+        ctx.sync()
+        if dist is not None:
+            dist.barrier()
+        t0 = time.time()
+        v = T.inner_product(p, p)
+        ctx.sync()
+        if dist is not None:
+            dist.barrier()
+        dt = time.time() - t0
+        st = ctx.program_stats()
+        out.append(dt)
+        say("%dx%d D=%d exact norm: run %d  %.3f s  %.3e flop on this rank -> %.2f TFLOP/s per GPU, log10 <psi|psi> = %.12f, workspace %.1f GiB"
+            % (L, L, D, r, dt, st["flops"], st["flops"] / dt / 1e12, np.log10(abs(complex(v.to_numpy()))), st["workspace_bytes"] / 2 ** 30))
+    say(json.dumps({"workload": "%dx%d D=%d exact norm" % (L, L, D), "world": world, "seconds": out, "flops_per_rank": st["flops"]}))
+if dist is not None:
+    dist.barrier()
+    dist.destroy_process_group()
