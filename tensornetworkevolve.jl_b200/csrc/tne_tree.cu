@@ -847,18 +847,26 @@ struct Exec {
         return TNE_OK;
     }
 
-    // the slices of value v, as phase ph loops over them, are `nsl` contiguous blocks in iteration order
-    bool contiguous_slices(const Phase& ph, int v, int64_t* block) const {
+    // The slices of value v, as phase ph loops over them, are contiguous blocks in iteration order.  The sliced labels of
+    // the phase that v carries must be the FIRST ones of the phase's list (the fastest digits of the iteration counter, so
+    // that block j is touched by the iterations it = j mod nblocks only); `whole`: v must carry all of them.
+    bool contiguous_slices(const Phase& ph, int v, int64_t* block, int64_t* nblocks, bool whole) const {
         auto it = ph.views.find(v);
         if (it == ph.views.end() || ph.nsl <= 1) return false;
         const PView& pv = it->second;
+        size_t q = 0;
+        int64_t nb = 1;
+        while (q < ph.ssz.size() && pv.sl_stride[q] != 0) { nb *= ph.ssz[q]; ++q; }
+        for (size_t z = q; z < ph.ssz.size(); ++z) if (pv.sl_stride[z] != 0) return false;
+        if (q == 0 || (whole && q != ph.ssz.size())) return false;
         const int64_t ext = extent_of(P.vals[v]);
-        if (ext % ph.nsl != 0) return false;
-        int64_t want = ext / ph.nsl;
+        if (ext % nb != 0) return false;
+        int64_t want = ext / nb;
         *block = want;
-        for (size_t q = 0; q < ph.ssz.size(); ++q) {
-            if (pv.sl_stride[q] != want) return false;
-            want *= ph.ssz[q];
+        *nblocks = nb;
+        for (size_t z = 0; z < q; ++z) {
+            if (pv.sl_stride[z] != want) return false;
+            want *= ph.ssz[z];
         }
         return true;
     }
@@ -876,23 +884,25 @@ struct Exec {
             for (int v : ph.zero_at_start) {
                 Phase::Comm c;
                 const PView& pv = ph.views.at(v);
-                bool all_sliced = !pv.sl_stride.empty(), none_sliced = true;
-                for (auto st : pv.sl_stride) { if (st == 0) all_sliced = false; else none_sliced = false; }
-                int64_t block = 0;
-                if (all_sliced && ph.nsl % world == 0 && contiguous_slices(ph, v, &block)) {
+                bool all_sliced = !pv.sl_stride.empty();
+                for (auto st : pv.sl_stride) if (st == 0) all_sliced = false;
+                int64_t block = 0, nb = 0;
+                if (all_sliced && ph.nsl % world == 0 && contiguous_slices(ph, v, &block, &nb, true)) {
                     c.kind = 2; c.block = block; c.nblocks = ph.nsl;
-                } else if (none_sliced) {
+                }
+                if (c.kind == 0) {
+                    // every rank holds a partial sum of the WHOLE tensor (whatever it did not write is zero): the ranks only
+                    // need the blocks they will read
                     bool ok = true, any = false;
-                    int64_t nb = 0;
                     for (size_t pj = 0; pj < phases.size() && ok; ++pj) {
                         if (pj == pi || !phases[pj].views.count(v)) continue;
                         const Phase& cons = phases[pj];
-                        int64_t b2 = 0;
-                        if (cons.nsl % world != 0 || !contiguous_slices(cons, v, &b2)) { ok = false; break; }
+                        int64_t b2 = 0, n2 = 0;
+                        if (!contiguous_slices(cons, v, &b2, &n2, false) || n2 % world != 0) { ok = false; break; }
                         for (int z : cons.zero_at_start) if (z == v) ok = false;          // a second writer
                         for (auto& po : cons.ops) if (po.op.out == v) ok = false;
-                        if (any && (b2 != block || cons.nsl != nb)) ok = false;
-                        block = b2; nb = cons.nsl; any = true;
+                        if (any && (b2 != block || n2 != nb)) ok = false;
+                        block = b2; nb = n2; any = true;
                     }
                     if (ok && any) { c.kind = 1; c.block = block; c.nblocks = nb; }
                 }

@@ -21,8 +21,8 @@ for r in range(reps):
     y, f = T.energy_and_gradient(p, h)
     yv = y.to_numpy()
     dt = time.time() - t
-    prof = ctx.profile_collect(); ctx.set_option("profile", 0)
+    prof = ctx.profile_collect(fine=bool(os.environ.get("TNE_FINE"))); ctx.set_option("profile", 0)
     print("step %.3f s  y = %r" % (dt, yv))
     for k, v in prof.items():
         if v["launches"]:
-            print("  %-16s %6d launches %9.1f ms  %6.2f TFLOP/s  %7.1f GB/s" % (k, v["launches"], v["ms"], v["flops"] / v["ms"] / 1e9, v["bytes"] / v["ms"] / 1e6))
+            print("  %-22s %6d launches %9.1f ms  %6.2f TFLOP/s  %7.1f GB/s" % (str(k), v["launches"], v["ms"], v["flops"] / v["ms"] / 1e9, v["bytes"] / v["ms"] / 1e6))
