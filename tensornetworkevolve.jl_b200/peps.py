@@ -355,6 +355,51 @@ def inner_product(p1, p2):  # src/peps.jl:106-110
     return p1.code_inner_product(*p1c.alltensors(), *p2.alltensors())
 
 
+def slice_bonds(peps, bonds, index, host=None):
+    """One term of a SlicedEinsum over virtual bonds (the reference's ``TreeSA(nslices = k)`` codes, test/peps.jl:9, loop
+    over the values of the sliced labels): the PEPS with bond ``bonds[k]`` fixed at ``index[k]`` (0-based), kept as a leg of
+    dimension 1 so that labels, contraction order and segments stay valid.  ``host``: cached numpy copies of the tensors."""
+    host = host if host is not None else [t.to_numpy() for t in peps.alltensors()]
+    fix = dict(zip(bonds, index))
+    out = []
+    for vl, a in zip(peps.vertex_labels, host):
+        if any(l in fix for l in vl):
+            a = a[tuple(slice(fix[l], fix[l] + 1) if l in fix else slice(None) for l in vl)]
+            out.append(B200Array.from_numpy(np.asfortranarray(a)))
+        else:
+            out.append(None)
+    tens = [o if o is not None else t for o, t in zip(out, peps.alltensors())]
+    return replace_tensors(peps, tens)
+
+
+def inner_product_sliced(p1, p2, bonds, subset=None, shard=(0, 1)):
+    """``<p1|p2>`` as the sum over the values of the sliced ``bonds`` (bra and ket copy of each bond are sliced
+    independently: ``D^(2 len(bonds))`` terms) -- BASELINE configs[4]: every term is an ordinary contraction with
+    dimension-1 legs, the terms are dealt round-robin to the ranks (``shard = (rank, world)``) and the caller all-reduces
+    the partial sums.  ``subset``: a list of ``(bra index tuple, ket index tuple)`` to evaluate instead of all of them
+    (timing a fixed subset of the slices).  Returns ``(partial sum as a Python complex, number of terms evaluated)``."""
+    import itertools
+    dims = []
+    for b in bonds:
+        for vl, t in zip(p1.vertex_labels, p1.vertex_tensors):
+            if b in vl:
+                dims.append(t.shape[vl.index(b)])
+                break
+    if subset is None:
+        one = list(itertools.product(*[range(d) for d in dims]))
+        subset = [(a, b) for a in one for b in one]
+    h1 = [t.to_numpy() for t in p1.alltensors()]
+    h2 = h1 if p2 is p1 else [t.to_numpy() for t in p2.alltensors()]
+    total, n = 0.0 + 0.0j, 0
+    rank, world = shard
+    for k, (ia, ib) in enumerate(subset):
+        if k % world != rank:
+            continue
+        total += complex(inner_product(slice_bonds(p1, bonds, ia, h1), slice_bonds(p2, bonds, ib, h2)).to_numpy())
+        n += 1
+    return total, n
+
+
 def norm(peps):  # src/peps.jl:302
     ip = inner_product(peps, peps)
     if _isdiff(ip):

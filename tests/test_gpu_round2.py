@@ -400,3 +400,46 @@ def test_permutation_kernel(tne):
             want = np.transpose(np.conj(x) if conj else x, [p - 1 for p in perm])
             assert got.shape == want.shape and np.array_equal(got, want), (shape, perm)
     assert ctx.launch_count() - l0 == 2 * len(cases)       # one launch each: no zero-fill, no contraction
+
+
+# -- big lattices: two-bond sliced sweep (BASELINE configs[3], the exact 8x8 D=4 norm) and globally sliced sums (configs[4]) -----
+def _row_bonds(tne, L, rows):
+    g = tne.grid([L, L])
+    n = L * L
+    emap = {e: n + 1 + k for k, e in enumerate(g.edges())}
+    return [emap[(r + (y - 2) * L, r + (y - 1) * L)] for r in rows for y in range(2, L + 1)]
+
+
+@pytest.mark.parametrize("L,D,name", [(4, 3, "grid_4x4_D3.npz"), (5, 4, "grid_5x5_D4.npz"), (8, 2, "grid_8x8_D2_norm.npz"),
+                                      (8, 3, "grid_8x8_D3_norm.npz"), (10, 2, "grid_10x10_D2_norm.npz")])
+def test_two_bond_sliced_sweep_norm_golden(tne, L, D, name):
+    """sweep_plan(slice_first_row=True) -- the plan that fits the exact 8x8 D=4 norm (64 GiB boundaries) into one B200 --
+    against the oracle's <psi|psi> at the validation sizes: every column loops over the bond entering its last site AND the
+    bond leaving its first site; the next boundary is written slice by slice through strided views."""
+    gold = _gold(name)
+    g = tne.grid([L, L])
+    order, segs = tne.sweep_plan(g, L, slice_first_row=True)
+    p = tne.rand_simplepeps(g, D, np.random.default_rng(seed_for(L, D)), optimizer=order, segments=segs)
+    assert np.array_equal(tne.variables(p).to_numpy(), gold["variables"])
+    assert rel(tne.inner_product(p, p).to_numpy(), gold["inner"]) < TOL
+
+
+def test_globally_sliced_inner_product_sums_to_the_golden(tne):
+    """inner_product_sliced (BASELINE configs[4]: sliced bond indices, partial sums per rank): the sum over ALL values of the
+    horizontal bonds of one lattice row equals the oracle's <psi|psi>; dealing the terms to 3 'ranks' partitions the sum."""
+    gold = _gold("grid_3x3_D2.npz")
+    L, D = 3, 2
+    g = tne.grid([L, L])
+    order, segs = tne.sweep_plan(g, L)
+    p = tne.rand_simplepeps(g, D, np.random.default_rng(seed_for(L, D)), optimizer=order, segments=segs)
+    want = complex(tne.inner_product(p, p).to_numpy())
+    if "inner" in gold:
+        assert rel(want, gold["inner"]) < TOL
+    bonds = _row_bonds(tne, L, [2])
+    total, n = tne.inner_product_sliced(p, p, bonds)
+    assert n == (D * D) ** len(bonds) and rel(total, want) < TOL
+    parts = [tne.inner_product_sliced(p, p, bonds, shard=(r, 3)) for r in range(3)]
+    assert sum(q[1] for q in parts) == n and rel(sum(q[0] for q in parts), want) < TOL
+    # a slice is a PEPS with dimension-1 legs; two different bra / ket slices give one off-diagonal term
+    one = tne.slice_bonds(p, bonds, (1, 0))
+    assert sum(1 in t.shape for t in one.vertex_tensors) == L
