@@ -226,8 +226,8 @@ class Clocks:
 # GPU arm
 # ---------------------------------------------------------------------------------------------
 def run_gpu(args):
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-        os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the one JSON line
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ.pop("NCCL_DEBUG")        # keep stdout to the one JSON line (NCCL prints its version banner there)
     import torch
     import tne_b200 as T
     rank = int(os.environ.get("RANK", "0"))
@@ -492,6 +492,68 @@ def run_gpu(args):
         st = ctx.program_stats()
         extras["norm_7x7_D4"] = {"ms": nms, "flops": st["flops"], "tflops": st["flops"] / (nms * 1e-3) / 1e12, "log10_norm": float(np.log10(abs(nv.item()))),
                                  "note": "exact <psi|psi> of a 7x7 D=4 PEPS (one contraction, forward only)"}
+    if not args.no_extras and (world > 1 or os.environ.get("TNE_BENCH_BIG") == "1"):
+        # BASELINE configs[3] / configs[4] on N GPUs: exact norms of big lattices with the two-bond sliced sweep
+        # (sweep_plan(slice_first_row=True)): every column loops over the bond entering its last site and the bond leaving
+        # its first site, the D^4 (column, slice) units are dealt to the ranks, the 64 GiB boundaries are combined with
+        # ncclReduceScatter (each rank only needs the slices it will read); one un-warmed run each (they take seconds)
+        def big_norm(Lb, Db):
+            gb = T.grid([Lb, Lb])
+            ob, sb = T.sweep_plan(gb, Lb, slice_first_row=True)
+            pb = T.rand_simplepeps(gb, Db, np.random.default_rng(seed_for(Lb, Db)), optimizer=ob, segments=sb)
+            pb.code_inner_product.seg_shard = world > 1
+            bms, _, val = timed(lambda: T.inner_product(pb, pb), 1)
+            st = ctx.program_stats()
+            return pb, {"ms": bms, "n_gpus": world, "flops_per_gpu": st["flops"], "tflops_per_gpu": st["flops"] / (bms * 1e-3) / 1e12,
+                        "workspace_gib_per_gpu": st["workspace_bytes"] / 2 ** 30, "log10_inner": float(np.log10(abs(complex(val.to_numpy()))))}
+        try:
+            for (Lb, Db, name) in ((8, 3, "grid_8x8_D3_norm.npz"), (10, 2, "grid_10x10_D2_norm.npz")):   # parity of this very path first
+                gp = os.path.join(ROOT, "tests", "golden", name)
+                if os.path.exists(gp):
+                    gold = np.load(gp)
+                    pb, rec = big_norm(Lb, Db)
+                    ip = complex(T.inner_product(pb, pb).to_numpy())
+                    check["two_bond_sweep_%dx%d_D%d_inner_rel_err_vs_oracle" % (Lb, Lb, Db)] = abs(ip - complex(gold["inner"])) / abs(complex(gold["inner"]))
+            _, rec = big_norm(8, 4)
+            rec["note"] = ("exact <psi|psi> of an 8x8 D=4 PEPS (BASELINE configs[3]): 1.37e15 flop, two 64 GiB boundaries + 12 GiB per GPU; "
+                           "one B200 alone: 72.6 s (tools/norm_big.py)")
+            extras["norm_8x8_D4"] = rec
+            if world >= 4 or os.environ.get("TNE_BENCH_BIG") == "1":
+                _, rec = big_norm(10, 3)
+                rec["note"] = "exact <psi|psi> of a 10x10 D=3 PEPS (BASELINE configs[4] at the largest bond dimension whose 52 GiB boundary fits): 6.2e14 flop; one B200 alone: 82.5 s"
+                extras["norm_10x10_D3"] = rec
+            # configs[4] at D=4 cannot be contracted exactly (16 TiB boundary): a fixed subset of a globally sliced sum, timed
+            Lb, Db, rows, per_rank = 10, 4, [4, 5, 6], 1
+            gb = T.grid([Lb, Lb])
+            ob, sb = T.sweep_plan(gb, Lb, slice_first_row=True)
+            pb = T.rand_simplepeps(gb, Db, np.random.default_rng(seed_for(Lb, Db)), optimizer=ob, segments=sb)
+            nb = Lb * Lb
+            emap = {e: nb + 1 + k for k, e in enumerate(gb.edges())}
+            bonds = [emap[(r + (yy - 2) * Lb, r + (yy - 1) * Lb)] for r in rows for yy in range(2, Lb + 1)]
+            srng = np.random.default_rng(7)
+            subset = [(tuple(srng.integers(0, Db, len(bonds))), tuple(srng.integers(0, Db, len(bonds)))) for _ in range(per_rank * world)]
+            part = []
+
+            def slice_job():
+                sv, cnt = T.inner_product_sliced(pb, pb, bonds, subset, shard=(rank, world))
+                acc = T.B200Array.from_numpy(np.asarray(sv))
+                if world > 1:
+                    T.array.allreduce_sum(ctx, [acc])      # NCCL all-reduce of the slice sums
+                part.append(complex(acc.to_numpy()))
+            sms, _, _ = timed(slice_job, 1)
+            st = ctx.program_stats()
+            nsl = float(Db) ** (2 * len(bonds))
+            extras["slices_10x10_D4"] = {"ms": sms, "slices": len(subset), "slices_per_s": len(subset) / (sms * 1e-3), "flops_per_slice": st["flops"],
+                                         "tflops_per_gpu": st["flops"] * per_rank / (sms * 1e-3) / 1e12, "total_slices": nsl,
+                                         "extrapolated_seconds_all_slices": nsl / (len(subset) / (sms * 1e-3)), "unsliced_flops": 6.13e17,
+                                         "unsliced_seconds_at_this_rate_if_memory_allowed": 6.13e17 / (world * st["flops"] * per_rank / (sms * 1e-3)),
+                                         "partial_sum": [part[-1].real, part[-1].imag],
+                                         "note": "10x10 D=4 (BASELINE configs[4]): the 27 horizontal bonds of lattice rows 4-6 sliced globally, bra and ket copies "
+                                                 "independently (16^27 terms, each a contraction with dimension-1 legs, 8.75 GiB, 1.1e14 flop); one term per GPU timed, "
+                                                 "partial sums all-reduced with NCCL; the exact contraction needs a 16 TiB boundary and is out of reach of 8 x 180 GB "
+                                                 "by any slicing -- the extrapolation is printed, not claimed"}
+        except Exception as e:
+            extras["big_lattice_error"] = repr(e)
     if rank == 0:
         cpu, _ = cpu_sample(L, D, budget_s=args.cpu_seconds) if world == 1 and not args.no_cpu else (None, None)
         line = {

@@ -88,6 +88,7 @@ SYMBOLS = {
     "tne_stream": (C.c_void_p, [C.c_void_p]),
     "tne_launch_count": (C.c_int64, [C.c_void_p]),
     "tne_last_program_stats": (C.c_int, [C.c_void_p, _P(C.c_double)]),
+    "tne_plan_cache_info": (C.c_int, [C.c_void_p, _P(C.c_int64), _P(C.c_int64)]),
     "tne_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
     "tne_profile_collect": (C.c_int, [C.c_void_p, _P(C.c_double)]),
     "tne_measure_fp64_peak": (C.c_int, [C.c_void_p, _P(C.c_double), _P(C.c_double)]),

@@ -58,6 +58,12 @@ class Context:
         return dict(flops=s[0], bytes=s[1], contractions=int(s[2]), workspace_bytes=int(s[3]),
                     recompute_flops=s[4], values=int(s[5]))
 
+    def plan_cache_info(self):
+        """(programs held, calls served from the cache) of the tree entry points (``tne_plan_cache_info``)."""
+        a, b = C.c_int64(), C.c_int64()
+        self.check(self.L.tne_plan_cache_info(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def profile_collect(self, fine=False):
         """Per kernel: launches, device ms, algorithmic flops and bytes since the last call.  ``fine``: keyed by
         (kernel, bucket) where the bucket of an absorb kernel is log2(padded K / 2) (5, 6: fused launches)."""

@@ -85,6 +85,18 @@ int comm_allreduce_ptr(tne_ctx* ctx, cplx* p, int64_t n) {
     return TNE_OK;
 }
 
+int comm_allreduce_many(tne_ctx* ctx, int n, cplx* const* ptrs, const int64_t* counts) {
+    if (ctx->world <= 1 || n <= 0) return TNE_OK;
+    if (!ctx->nccl) return tne_fail(ctx, TNE_ERR_NCCL, "tne_comm_init has not been called");
+    const int NCCL_DOUBLE = 8, NCCL_SUM = 0;
+    int rc = g_nccl.group_start();
+    for (int i = 0; i < n && rc == 0; ++i)
+        if (counts[i] > 0) rc = g_nccl.allreduce(ptrs[i], ptrs[i], (size_t)(2 * counts[i]), NCCL_DOUBLE, NCCL_SUM, ctx->nccl, ctx->stream);
+    int rc2 = g_nccl.group_end();
+    if (rc != 0 || rc2 != 0) return tne_fail(ctx, TNE_ERR_NCCL, "ncclAllReduce failed: %s", g_nccl.errstr ? g_nccl.errstr(rc ? rc : rc2) : "?");
+    return TNE_OK;
+}
+
 // Blocks dealt round-robin to the ranks (block b belongs to rank b % world), `world` consecutive blocks per NCCL call,
 // in place (recvbuff = sendbuff + rank * count for the reduce-scatter, sendbuff = recvbuff + rank * count for the
 // all-gather: the in-place forms NCCL documents).

@@ -246,6 +246,12 @@ extern "C" int tne_mem_info(tne_ctx* ctx, int64_t* in_use, int64_t* peak, int64_
 extern "C" void* tne_stream(tne_ctx* ctx) { return (void*)ctx->stream; }
 extern "C" int64_t tne_launch_count(tne_ctx* ctx) { return ctx->launches; }
 
+extern "C" int tne_plan_cache_info(tne_ctx* ctx, int64_t* entries, int64_t* hits) {
+    if (entries) *entries = (int64_t)ctx->plan_cache.size();
+    if (hits) *hits = ctx->plan_cache_hits;
+    return TNE_OK;
+}
+
 extern "C" int tne_last_program_stats(tne_ctx* ctx, double* s) {
     TNE_ENTER(ctx);
     for (int i = 0; i < 6; ++i) s[i] = ctx->stats[i];
@@ -279,6 +285,7 @@ extern "C" int tne_set_option(tne_ctx* ctx, const char* key, int64_t value) {
     else if (k == "no_site2") ctx->opt_no_site2 = value;
     else if (k == "no_site2b") ctx->opt_no_site2b = value;
     else if (k == "no_gemm") ctx->opt_no_gemm = value;
+    else if (k == "no_plan_cache") { ctx->opt_no_plan_cache = value; if (value) ctx->plan_cache.clear(); }
     else if (k == "no_permute") ctx->opt_no_permute = value;
     else if (k == "no_rows") ctx->opt_no_rows = value;
     else if (k == "no_pdl") ctx->opt_no_pdl = value;   // default 1: measured no gain from programmatic dependent launch
@@ -436,6 +443,11 @@ __global__ void fill_from_kernel(cplx* p, int64_t n, const cplx* s) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = v;
 }
 
+__global__ void fill_value_kernel(cplx* p, int64_t n, double re, double im) {
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = make_double2(re, im);
+}
+
 // block-wise tree reduction; second pass over <= 1024 partials
 __global__ void reduce_sum_kernel(const cplx* __restrict__ in, int64_t n, cplx* __restrict__ out) {
     __shared__ double sre[256], sim[256];
@@ -460,6 +472,13 @@ static int grid_for(tne_ctx* ctx, int64_t n) {
 int launch_fill_zero(tne_ctx* ctx, cplx* p, int64_t n) {
     if (n <= 0) return TNE_OK;
     TNE_CUDA(ctx, cudaMemsetAsync(p, 0, n * sizeof(cplx), ctx->stream));
+    return TNE_OK;
+}
+
+int launch_fill_value(tne_ctx* ctx, cplx* p, int64_t n, double re, double im) {
+    if (n <= 0) return TNE_OK;
+    fill_value_kernel<<<grid_for(ctx, n), 256, 0, ctx->stream>>>(p, n, re, im);
+    TNE_LAUNCH_CHECK(ctx);
     return TNE_OK;
 }
 

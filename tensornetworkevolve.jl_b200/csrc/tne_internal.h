@@ -4,6 +4,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <list>
 #include <map>
 #include <memory>
 #include <string>
@@ -59,6 +60,9 @@ struct tne_ctx {
     int64_t opt_no_permute = 0;            // 1: unary permutations run as contractions with the constant 1 (gett_generic)
     int64_t opt_no_gemm = 0;               // 1: never use the tiled DMMA GEMM for general dense nodes (tne_gemm.cu)
     int64_t opt_no_site2b = 0;             // 1: never fuse the three reverse ops of a site into one kernel (tne_site2b.cu)
+    int64_t opt_no_plan_cache = 0;         // 1: tne_expect_terms re-plans every call (default: compiled programs are cached, tne_tree.cu)
+    std::list<std::pair<std::string, std::shared_ptr<void>>> plan_cache;   // key bytes -> compiled program, most recently used first
+    int64_t plan_cache_hits = 0;
     cplx* s2b_part = nullptr;              // CTA partials of the fused reverse kernel's leaf gradient
     cplx* red_part = nullptr;              // CTA partials of the reduce kernels (deterministic two-pass reduction)
     int64_t red_part_elems = 0;
@@ -231,6 +235,7 @@ void contract_cost(const TensorRef& A, const TensorRef& B, const TensorRef& C, d
 
 // ---- multi-GPU (tne_comm.cu): in-place sum over the ranks of `n` complex elements at a device pointer
 int comm_allreduce_ptr(tne_ctx* ctx, cplx* p, int64_t n);
+int comm_allreduce_many(tne_ctx* ctx, int n, cplx* const* ptrs, const int64_t* counts);   // one grouped NCCL call
 // `nblocks` contiguous blocks of `block` complex elements at p, block b owned by rank b % world:
 // reduce-scatter: on return the blocks a rank owns hold the sum over ranks (the others are unspecified);
 // all-gather: every rank contributes the blocks it owns, on return all blocks are complete everywhere.
@@ -240,5 +245,6 @@ void comm_destroy(tne_ctx* ctx);   // ncclCommDestroy of the context's communica
 
 // ---- elementwise helpers used across units ---------------------------------------------
 int launch_fill_zero(tne_ctx* ctx, cplx* p, int64_t n);
+int launch_fill_value(tne_ctx* ctx, cplx* p, int64_t n, double re, double im);
 int launch_scale_inplace(tne_ctx* ctx, cplx* p, int64_t n, double re, double im);
 int launch_axpy_dev(tne_ctx* ctx, cplx* y, const cplx* x, int64_t n, const cplx* alpha_dev);

@@ -41,6 +41,9 @@ struct Val {
     int leaf = -1;         // leaf index for sliced views
     int64_t slice_base = 0;  // element offset added per slice (filled at run time)
     bool persistent = false;  // touched by more than one segment: lives in the checkpoint arena
+    // where `ext` comes from, so that a cached program can be re-bound to the buffers of a later call:
+    // 0 none, 1 leaf[bind_index], 2 replacement tensor (canonical index), 3 value output, 4 seed, 5 gradient[bind_index]
+    int bind_kind = 0, bind_index = 0;
 };
 
 enum OpKind { OP_CONTRACT = 0, OP_AXPY = 1, OP_ZERO = 2 };
@@ -121,6 +124,7 @@ struct Builder {
     int n_terms = 0;
     const tne_term* terms = nullptr;
     int cur_node = 0;                      // node the ops being emitted belong to
+    std::map<int64_t, int> repl_id;        // replacement handle -> canonical index (order of first appearance over the terms)
 
     Builder(tne_ctx* c, Program& p, const tne_tree* t) : ctx(c), P(p), tree(t) {}
 
@@ -186,6 +190,7 @@ int build_forward(Builder& B, const tne_buf* leaves, const int32_t* leaf_conj, b
         int v = P.new_val(labels, dims);
         P.vals[v].strides = strides;
         P.vals[v].ext = b->ptr();
+        P.vals[v].bind_kind = 1; P.vals[v].bind_index = i;
         P.vals[v].conj = leaf_conj ? leaf_conj[i] != 0 : false;
         P.vals[v].leaf = i;
         P.written[v] = true;
@@ -210,6 +215,7 @@ int build_forward(Builder& B, const tne_buf* leaves, const int32_t* leaf_conj, b
             int v = P.new_val(base.labels, base.dims);
             P.vals[v].strides = base.strides;
             P.vals[v].ext = b->ptr();
+            P.vals[v].bind_kind = 2; P.vals[v].bind_index = B.repl_id.at(t.repl[r]);
             P.vals[v].conj = base.conj;
             P.vals[v].leaf = lf;
             P.written[v] = true;
@@ -1084,6 +1090,78 @@ struct Exec {
 }  // namespace
 
 // ---------------------------------------------------------------------------------------
+// compiled programs and their cache
+// ---------------------------------------------------------------------------------------
+namespace {
+
+// Everything tne_expect_terms builds on the host for one (tree, leaf shapes, term pattern, gradient request, options):
+// the op lists, the phases with their classified launch plans and the memory plan.  Device pointers enter only through
+// Val::ext of the external values, which are re-bound per call -- a TDVP driver evaluates the same program every step.
+struct Compiled {
+    Program P;
+    Exec E;
+    std::vector<std::vector<int32_t>> leaf_labels;
+    std::vector<int32_t> sliced;
+    int root = -1, seed_val = -1;
+    std::vector<int> grad_vals;
+    int64_t peak = 0;
+    explicit Compiled(tne_ctx* c) : P(), E((P.ctx = c, P)) {}
+};
+
+template <typename T>
+void key_put(std::string& k, const T* p, size_t n) { k.append(reinterpret_cast<const char*>(p), n * sizeof(T)); }
+template <typename T>
+void key_put1(std::string& k, T v) { key_put(k, &v, 1); }
+
+// byte string that determines the compiled program
+int program_key(tne_ctx* ctx, const tne_tree* T, const tne_buf* leaves, const int32_t* leaf_conj, int n_terms, const tne_term* terms,
+                const std::map<int64_t, int>& repl_id, int n_grad, const int32_t* grad_leaves, std::string& k) {
+    k.clear();
+    key_put1(k, T->n_leaves); key_put1(k, T->n_nodes); key_put1(k, T->n_sliced); key_put1(k, T->shard_rank); key_put1(k, T->shard_world);
+    key_put1(k, T->seg_shard); key_put1(k, T->n_segments);
+    if (T->n_leaves <= 0 || T->n_nodes < 0) return tne_fail(ctx, TNE_ERR_INVALID, "empty tree");
+    int nlab = 0;
+    for (int i = 0; i < T->n_leaves; ++i) nlab += T->leaf_rank[i];
+    key_put(k, T->leaf_rank, T->n_leaves); key_put(k, T->leaf_labels, nlab);
+    key_put(k, T->node_children, 2 * (size_t)T->n_nodes); key_put(k, T->node_out_rank, T->n_nodes);
+    int nout = 0;
+    for (int j = 0; j < T->n_nodes; ++j) nout += T->node_out_rank[j];
+    key_put(k, T->node_out_labels, nout);
+    if (T->n_sliced > 0) key_put(k, T->sliced_labels, T->n_sliced);
+    if (T->n_segments > 1 && T->seg_first_node) {
+        key_put(k, T->seg_first_node, T->n_segments);
+        if (T->seg_sliced_off) {
+            key_put(k, T->seg_sliced_off, T->n_segments + 1);
+            key_put(k, T->seg_sliced_labels, T->seg_sliced_off[T->n_segments]);
+        }
+    }
+    for (int i = 0; i < T->n_leaves; ++i) {
+        Buf* b = buf_get(ctx, leaves[i]);
+        if (!b) return TNE_ERR_INVALID;
+        key_put1(k, (int32_t)b->dims.size());
+        key_put(k, b->dims.data(), b->dims.size());
+        key_put1(k, (int32_t)(leaf_conj ? leaf_conj[i] != 0 : 0));
+    }
+    key_put1(k, n_terms);
+    for (int t = 0; t < n_terms; ++t) {
+        key_put1(k, terms[t].n_repl);
+        for (int r = 0; r < terms[t].n_repl; ++r) { key_put1(k, terms[t].leaf[r]); key_put1(k, (int32_t)repl_id.at(terms[t].repl[r])); }
+        key_put1(k, terms[t].coef_re); key_put1(k, terms[t].coef_im);
+    }
+    key_put1(k, n_grad);
+    if (n_grad > 0) key_put(k, grad_leaves, n_grad);
+    const int64_t opts[] = {ctx->opt_force_generic, ctx->opt_debug, ctx->opt_pad, ctx->opt_no_rows, ctx->opt_no_pdl, ctx->opt_no_site2, ctx->opt_no_fuse,
+                            ctx->opt_no_permute, ctx->opt_no_gemm, ctx->opt_no_site2b, ctx->opt_absorb_tma, ctx->opt_no_reduce_tma, ctx->opt_rs_comm,
+                            (int64_t)ctx->world, (int64_t)ctx->rank, ctx->mem_limit};
+    key_put(k, opts, sizeof(opts) / sizeof(opts[0]));
+    return TNE_OK;
+}
+
+constexpr size_t PLAN_CACHE_MAX = 6;
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------
 // C ABI
 // ---------------------------------------------------------------------------------------
 extern "C" int tne_expect_terms(tne_ctx* ctx, const tne_tree* tree, const tne_buf* leaves, const int32_t* leaf_conj,
@@ -1092,87 +1170,163 @@ extern "C" int tne_expect_terms(tne_ctx* ctx, const tne_tree* tree, const tne_bu
     TNE_ENTER(ctx);
     if (!tree || !leaves || !value_out) return tne_fail(ctx, TNE_ERR_INVALID, "null argument");
     if (n_grad > 0 && !grads_out) return tne_fail(ctx, TNE_ERR_INVALID, "grads_out is null");
-    Program P;
-    P.ctx = ctx;
-    Builder B(ctx, P, tree);
-    B.n_terms = n_terms;
-    B.terms = terms;
-    int root = -1;
-    TNE_TRY(build_forward(B, leaves, leaf_conj, true, &root));
-    P.root_val = root;
-    Exec E(P);
-    E.seg_shard = tree->seg_shard != 0 && ctx->world > 1;
-    if (E.seg_shard && tree->n_sliced > 0)
-        return tne_fail(ctx, TNE_ERR_UNSUPPORTED, "seg_shard cannot be combined with globally sliced labels");
-    TNE_TRY(E.assign_segments(tree));
+    if (n_terms > 0 && !terms) return tne_fail(ctx, TNE_ERR_INVALID, "terms is null");
+    // replacement tensors by order of first appearance: terms that share a handle share a pattern of the dynamic programme
+    std::map<int64_t, int> repl_id;
+    std::vector<tne_buf> repl_handles;
+    for (int k = 0; k < n_terms; ++k) {
+        if (terms[k].n_repl < 0 || terms[k].n_repl > 4) return tne_fail(ctx, TNE_ERR_INVALID, "term %d: n_repl must be 0..4", k);
+        for (int r = 0; r < terms[k].n_repl; ++r)
+            if (!repl_id.count(terms[k].repl[r])) { repl_id[terms[k].repl[r]] = (int)repl_handles.size(); repl_handles.push_back(terms[k].repl[r]); }
+    }
+    std::string key;
+    TNE_TRY(program_key(ctx, tree, leaves, leaf_conj, n_terms, terms, repl_id, n_grad, grad_leaves, key));
+    std::shared_ptr<Compiled> cp;
+    const bool use_cache = !ctx->opt_no_plan_cache && !ctx->plan_only && ctx->opt_debug <= 2;
+    if (use_cache)
+        for (auto it = ctx->plan_cache.begin(); it != ctx->plan_cache.end(); ++it)
+            if (it->first == key) {
+                cp = std::static_pointer_cast<Compiled>(it->second);
+                ctx->plan_cache.splice(ctx->plan_cache.begin(), ctx->plan_cache, it);   // most recently used first
+                break;
+            }
+    const bool fresh = !cp;
+    if (fresh) cp = std::make_shared<Compiled>(ctx);
+    Program& P = cp->P;
+    Exec& E = cp->E;
 
     // outputs live in user-visible buffers, cleared once; every write into them accumulates
     // (over global slices, segment slices and repeated contributions alike)
     std::vector<tne_buf> owned;
     auto fail_cleanup = [&](int rc) { for (auto h : owned) tne_free(ctx, h); return rc; };
-    tne_buf hval;
-    TNE_TRY(buf_new(ctx, P.vals[root].dims, &hval));
-    owned.push_back(hval);
+    std::vector<tne_buf> hgrads;
+    tne_buf hval = 0, hseed = 0;
+
+    if (fresh) {
+        Builder B(ctx, P, tree);
+        B.n_terms = n_terms;
+        B.terms = terms;
+        B.repl_id = repl_id;
+        int root = -1;
+        TNE_TRY(build_forward(B, leaves, leaf_conj, true, &root));
+        P.root_val = root;
+        cp->root = root;
+        cp->leaf_labels = B.leaf_labels;
+        cp->sliced = B.sliced;
+        E.seg_shard = tree->seg_shard != 0 && ctx->world > 1;
+        if (E.seg_shard && tree->n_sliced > 0)
+            return tne_fail(ctx, TNE_ERR_UNSUPPORTED, "seg_shard cannot be combined with globally sliced labels");
+        TNE_TRY(E.assign_segments(tree));
+        TNE_TRY(buf_new(ctx, P.vals[root].dims, &hval));
+        owned.push_back(hval);
+        P.vals[root].ext = buf_get(ctx, hval)->ptr();
+        P.vals[root].bind_kind = 3;
+        if (n_grad > 0) {
+            if (P.vals[root].nelem != 1) return fail_cleanup(tne_fail(ctx, TNE_ERR_UNSUPPORTED, "gradients need a scalar output"));
+            int rc = buf_new(ctx, {}, &hseed);
+            if (rc) return fail_cleanup(rc);
+            owned.push_back(hseed);
+            int seed_val = P.new_val({}, {});
+            P.vals[seed_val].ext = buf_get(ctx, hseed)->ptr();
+            P.vals[seed_val].bind_kind = 4;
+            P.written[seed_val] = true;
+            cp->seed_val = seed_val;
+            for (int g = 0; g < n_grad; ++g) {
+                int lf = grad_leaves[g];
+                if (lf < 0 || lf >= tree->n_leaves) return fail_cleanup(tne_fail(ctx, TNE_ERR_INVALID, "gradient requested for unknown leaf %d", lf));
+                Buf* lb = buf_get(ctx, leaves[lf]);
+                tne_buf hg;
+                rc = buf_new(ctx, lb->dims, &hg);
+                if (rc) return fail_cleanup(rc);
+                owned.push_back(hg);
+                hgrads.push_back(hg);
+                int lv = B.nodes[lf].var[Key()];
+                P.vals[lv].needs_grad = true;
+                Val gv;
+                gv.labels = P.vals[lv].labels;
+                gv.dims = P.vals[lv].dims;
+                gv.strides = P.vals[lv].strides;
+                gv.nelem = P.vals[lv].nelem;
+                gv.ext = buf_get(ctx, hg)->ptr();
+                gv.bind_kind = 5; gv.bind_index = g;
+                gv.leaf = lf;
+                P.vals.push_back(gv);
+                P.written.push_back(true);
+                P.vals[lv].grad = (int)P.vals.size() - 1;
+                cp->grad_vals.push_back(P.vals[lv].grad);
+            }
+            build_backward(P, root, seed_val);
+        }
+        {
+            int rc = E.build(tree, n_grad > 0);
+            if (rc) return fail_cleanup(rc);
+        }
+        {
+            int w = E.seg_shard ? ctx->world : 1;
+            if (ctx->plan_only && ctx->opt_rs_comm > 1) w = (int)ctx->opt_rs_comm;   // planner: rs_comm = the world size to plan for
+            E.plan_comm(w);
+        }
+        if (ctx->opt_debug > 2 || ctx->plan_only) E.dump_final();
+        if (ctx->plan_only)
+            return fail_cleanup(tne_fail(ctx, TNE_ERR_UNSUPPORTED, "planner context (TNE_PLAN_ONLY): program built and dumped, nothing computed"));
+        cp->peak = E.persist_bytes + E.temp_bytes;
+        if (use_cache) {
+            ctx->plan_cache.emplace_front(key, std::static_pointer_cast<void>(cp));
+            while (ctx->plan_cache.size() > PLAN_CACHE_MAX) ctx->plan_cache.pop_back();
+        }
+    } else {
+        // cached program: new output buffers, then every external value is re-bound to this call's buffers
+        int rc = buf_new(ctx, P.vals[cp->root].dims, &hval);
+        if (rc) return rc;
+        owned.push_back(hval);
+        if (n_grad > 0) {
+            rc = buf_new(ctx, {}, &hseed);
+            if (rc) return fail_cleanup(rc);
+            owned.push_back(hseed);
+            for (int g = 0; g < n_grad; ++g) {
+                tne_buf hg;
+                rc = buf_new(ctx, buf_get(ctx, leaves[grad_leaves[g]])->dims, &hg);
+                if (rc) return fail_cleanup(rc);
+                owned.push_back(hg);
+                hgrads.push_back(hg);
+            }
+        }
+        for (auto& v : P.vals) {
+            switch (v.bind_kind) {
+                case 1: v.ext = buf_get(ctx, leaves[v.bind_index])->ptr(); break;
+                case 2: {
+                    Buf* b = buf_get(ctx, repl_handles[v.bind_index]);
+                    if (!b) return fail_cleanup(TNE_ERR_INVALID);
+                    if (b->dims != buf_get(ctx, leaves[v.leaf])->dims)
+                        return fail_cleanup(tne_fail(ctx, TNE_ERR_INVALID, "replacement for leaf %d has a different shape", v.leaf));
+                    v.ext = b->ptr();
+                    break;
+                }
+                case 3: v.ext = buf_get(ctx, hval)->ptr(); break;
+                case 4: v.ext = buf_get(ctx, hseed)->ptr(); break;
+                case 5: v.ext = buf_get(ctx, hgrads[v.bind_index])->ptr(); break;
+                default: break;
+            }
+            v.slice_base = 0;
+        }
+        P.flops = P.bytes = P.re_flops = 0;
+        P.n_contract = 0;
+    }
+    ctx->plan_cache_hits += fresh ? 0 : 1;
+    const int root = cp->root;
     {
         Buf* vb = buf_get(ctx, hval);
-        P.vals[root].ext = vb->ptr();
         int rc = launch_fill_zero(ctx, vb->ptr(), vb->nelem);
         if (rc) return fail_cleanup(rc);
     }
-    std::vector<tne_buf> hgrads;
-    tne_buf hseed = 0;
     if (n_grad > 0) {
-        if (P.vals[root].nelem != 1) return fail_cleanup(tne_fail(ctx, TNE_ERR_UNSUPPORTED, "gradients need a scalar output"));
-        int rc = buf_new(ctx, {}, &hseed);
-        if (rc) return fail_cleanup(rc);
-        owned.push_back(hseed);
-        cplx s = make_double2(seed_re, seed_im);
-        TNE_CUDA(ctx, cudaMemcpyAsync(buf_get(ctx, hseed)->ptr(), &s, sizeof(cplx), cudaMemcpyHostToDevice, ctx->stream));
-        TNE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        int seed_val = P.new_val({}, {});
-        P.vals[seed_val].ext = buf_get(ctx, hseed)->ptr();
-        P.written[seed_val] = true;
-        for (int g = 0; g < n_grad; ++g) {
-            int lf = grad_leaves[g];
-            if (lf < 0 || lf >= tree->n_leaves) return fail_cleanup(tne_fail(ctx, TNE_ERR_INVALID, "gradient requested for unknown leaf %d", lf));
-            Buf* lb = buf_get(ctx, leaves[lf]);
-            tne_buf hg;
-            rc = buf_new(ctx, lb->dims, &hg);
-            if (rc) return fail_cleanup(rc);
-            owned.push_back(hg);
-            Buf* gb = buf_get(ctx, hg);
-            rc = launch_fill_zero(ctx, gb->ptr(), gb->nelem);
-            if (rc) return fail_cleanup(rc);
-            hgrads.push_back(hg);
-            int lv = B.nodes[lf].var[Key()];
-            P.vals[lv].needs_grad = true;
-            Val gv;
-            gv.labels = P.vals[lv].labels;
-            gv.dims = P.vals[lv].dims;
-            gv.strides = P.vals[lv].strides;
-            gv.nelem = P.vals[lv].nelem;
-            gv.ext = gb->ptr();
-            gv.leaf = lf;
-            P.vals.push_back(gv);
-            P.written.push_back(true);
-            P.vals[lv].grad = (int)P.vals.size() - 1;
-        }
-        build_backward(P, root, seed_val);
-    }
-    {
-        int rc = E.build(tree, n_grad > 0);
+        // the cotangent seed is written by a kernel (no host synchronisation: planning of the next call overlaps this one)
+        int rc = launch_fill_value(ctx, buf_get(ctx, hseed)->ptr(), 1, seed_re, seed_im);
+        for (size_t g = 0; g < hgrads.size() && !rc; ++g) rc = launch_fill_zero(ctx, buf_get(ctx, hgrads[g])->ptr(), buf_get(ctx, hgrads[g])->nelem);
         if (rc) return fail_cleanup(rc);
     }
-    {
-        int w = E.seg_shard ? ctx->world : 1;
-        if (ctx->plan_only && ctx->opt_rs_comm > 1) w = (int)ctx->opt_rs_comm;   // planner: rs_comm = the world size to plan for
-        E.plan_comm(w);
-    }
-    if (ctx->opt_debug > 2 || ctx->plan_only) E.dump_final();
-    if (ctx->plan_only)
-        return fail_cleanup(tne_fail(ctx, TNE_ERR_UNSUPPORTED, "planner context (TNE_PLAN_ONLY): program built and dumped, nothing computed"));
     const int64_t budget = ctx->mem_limit - ctx->in_use;
-    const int64_t peak = E.persist_bytes + E.temp_bytes;
+    const int64_t peak = cp->peak;
     if (peak > budget)
         return fail_cleanup(tne_fail(ctx, TNE_ERR_OOM,
                                      "tree program needs %lld bytes of workspace (%lld checkpoints + %lld per-segment) but the budget is %lld; "
@@ -1189,7 +1343,7 @@ extern "C" int tne_expect_terms(tne_ctx* ctx, const tne_tree* tree, const tne_bu
     for (int s = 0; s < tree->n_sliced; ++s) {
         bool found = false;
         for (int i = 0; i < tree->n_leaves && !found; ++i) {
-            int q = find_in(B.leaf_labels[i], tree->sliced_labels[s]);
+            int q = find_in(cp->leaf_labels[i], tree->sliced_labels[s]);
             if (q >= 0) { ssz[s] = buf_get(ctx, leaves[i])->dims[q]; found = true; }
         }
         if (!found) return fail_cleanup(tne_fail(ctx, TNE_ERR_INVALID, "sliced label %d is not on any leaf", (int)tree->sliced_labels[s]));
@@ -1205,11 +1359,11 @@ extern "C" int tne_expect_terms(tne_ctx* ctx, const tne_tree* tree, const tne_bu
             for (int s = 0; s < tree->n_sliced; ++s) { idx[s] = rem % ssz[s]; rem /= ssz[s]; }
             for (auto& v : P.vals) {
                 if (v.leaf < 0) continue;
-                const auto& full = B.leaf_labels[v.leaf];
+                const auto& full = cp->leaf_labels[v.leaf];
                 Buf* lb = buf_get(ctx, leaves[v.leaf]);
                 int64_t st = 1, base = 0;
                 for (size_t q = 0; q < full.size(); ++q) {
-                    int s = find_in(B.sliced, full[q]);
+                    int s = find_in(cp->sliced, full[q]);
                     if (s >= 0) base += idx[s] * st;
                     st *= lb->dims[q];
                 }
@@ -1219,16 +1373,18 @@ extern "C" int tne_expect_terms(tne_ctx* ctx, const tne_tree* tree, const tne_bu
         int rc = E.run();
         if (rc) return fail_cleanup(rc);
     }
-    if (E.seg_shard) {   // outputs are complete on every rank on return
-        int rc = comm_allreduce_ptr(ctx, buf_get(ctx, hval)->ptr(), buf_get(ctx, hval)->nelem);
-        for (size_t g = 0; g < hgrads.size() && !rc; ++g) rc = comm_allreduce_ptr(ctx, buf_get(ctx, hgrads[g])->ptr(), buf_get(ctx, hgrads[g])->nelem);
+    if (E.seg_shard) {   // outputs are complete on every rank on return: one grouped NCCL call
+        std::vector<cplx*> ptrs = {buf_get(ctx, hval)->ptr()};
+        std::vector<int64_t> ns = {buf_get(ctx, hval)->nelem};
+        for (auto h : hgrads) { ptrs.push_back(buf_get(ctx, h)->ptr()); ns.push_back(buf_get(ctx, h)->nelem); }
+        int rc = comm_allreduce_many(ctx, (int)ptrs.size(), ptrs.data(), ns.data());
         if (rc) return fail_cleanup(rc);
     }
     ctx->stats[0] = P.flops; ctx->stats[1] = P.bytes; ctx->stats[2] = (double)P.n_contract;
     ctx->stats[3] = (double)peak; ctx->stats[4] = P.re_flops; ctx->stats[5] = (double)P.vals.size();
     if (ctx->opt_debug) {
-        fprintf(stderr, "[tne] program: %zu fwd ops, %zu bwd ops, %zu phases, workspace %.3f GiB (checkpoints %.3f + segment %.3f), flops %.3e (+%.3e recomputed), %lld launches\n",
-                P.fwd.size(), P.bwd.size(), E.phases.size(), peak / 1073741824.0, E.persist_bytes / 1073741824.0,
+        fprintf(stderr, "[tne] program%s: %zu fwd ops, %zu bwd ops, %zu phases, workspace %.3f GiB (checkpoints %.3f + segment %.3f), flops %.3e (+%.3e recomputed), %lld launches\n",
+                fresh ? "" : " (cached plan)", P.fwd.size(), P.bwd.size(), E.phases.size(), peak / 1073741824.0, E.persist_bytes / 1073741824.0,
                 E.temp_bytes / 1073741824.0, P.flops, P.re_flops, (long long)P.n_contract);
         if (ctx->opt_debug > 1)
             for (auto& ph : E.phases)
@@ -1238,6 +1394,7 @@ extern "C" int tne_expect_terms(tne_ctx* ctx, const tne_tree* tree, const tne_bu
     if (hseed) tne_free(ctx, hseed);
     *value_out = hval;
     for (int g = 0; g < n_grad; ++g) grads_out[g] = hgrads[g];
+    (void)root;
     return TNE_OK;
 }
 

@@ -443,3 +443,37 @@ def test_globally_sliced_inner_product_sums_to_the_golden(tne):
     # a slice is a PEPS with dimension-1 legs; two different bra / ket slices give one off-diagonal term
     one = tne.slice_bonds(p, bonds, (1, 0))
     assert sum(1 in t.shape for t in one.vertex_tensors) == L
+
+
+def test_plan_cache_rebinds_buffers(tne):
+    """tne_expect_terms caches compiled programs: a second PEPS of the same shape (different values, different buffers)
+    is served from the cache and matches a freshly planned evaluation bit for bit; a different Hamiltonian misses."""
+    ctx = tne.context()
+    L, D = 4, 3
+    g = tne.grid([L, L])
+    order, segs = tne.sweep_plan(g, L)
+    h = tne.rydberg_hamiltonian(g, 10.0, 0.2, 0.3)
+    pa = tne.rand_simplepeps(g, D, np.random.default_rng(1), optimizer=order, segments=segs)
+    pb = tne.rand_simplepeps(g, D, np.random.default_rng(2), optimizer=order, segments=segs)
+    ctx.set_option("no_plan_cache", 1)
+    try:
+        ya, fa = tne.energy_and_gradient(pa, h)
+        yb, fb = tne.energy_and_gradient(pb, h)
+        ya, fa, yb, fb = ya.to_numpy(), fa.to_numpy(), yb.to_numpy(), fb.to_numpy()
+        assert ctx.plan_cache_info()[0] == 0
+    finally:
+        ctx.set_option("no_plan_cache", 0)
+    _, h0 = ctx.plan_cache_info()
+    y1, f1 = tne.energy_and_gradient(pa, h)         # plans (norm programme + energy programme)
+    n1, h1 = ctx.plan_cache_info()
+    y2, f2 = tne.energy_and_gradient(pb, h)         # same shapes, other buffers: served from the cache
+    n2, h2 = ctx.plan_cache_info()
+    y3, f3 = tne.energy_and_gradient(pa, h)
+    assert n1 >= 2 and n2 == n1 and h1 == h0 and h2 - h1 >= 2
+    assert np.array_equal(y1.to_numpy(), ya) and np.array_equal(f1.to_numpy(), fa)
+    assert np.array_equal(y2.to_numpy(), yb) and np.array_equal(f2.to_numpy(), fb)
+    assert np.array_equal(y3.to_numpy(), ya) and np.array_equal(f3.to_numpy(), fa)
+    assert not np.array_equal(fa, fb)
+    h2_ = tne.rydberg_hamiltonian(g, 7.0, 0.2, 0.3)   # other coefficients: a different programme
+    tne.energy_and_gradient(pa, h2_)
+    assert ctx.plan_cache_info()[0] > n2
