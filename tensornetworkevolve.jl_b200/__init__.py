@@ -14,9 +14,9 @@ from .einsum import EinCode, NestedEinsum, SlicedEinsum, optimize_code
 from .graphs import SimpleGraph, grid, graph_from_edges
 from .peps import (PEPS, SimplePEPS, VidalPEPS, zero_simplepeps, zero_vidalpeps, rand_simplepeps, rand_vidalpeps,
                    statetensor, statevec, vec, getvlabel, getphysicallabel, newlabel, findbondtensor, virtualbonds,
-                   apply_onbond_, apply_onbond_batch_, apply_sweep_, apply_onsite_, apply_onsite, inner_product, norm, normalize_, variables,
+                   apply_onbond_, apply_onbond_batch_, apply_sweep_, apply_sweep_batch_, apply_onsite_, apply_onsite, inner_product, norm, normalize_, variables,
                    load_variables_, load_variables, expect, nsite, replace_tensors, conj, sweep_plan, slice_bonds, inner_product_sliced)
-from .tebd import rydberg_tebd_, rydberg_tebd_sweep_, rydberg_hamiltonian
+from .tebd import rydberg_tebd_, rydberg_tebd_sweep_, rydberg_tebd_sweep_batch_, rydberg_tebd_batch_, rydberg_hamiltonian
 from .tensorad import DiffTensor, gradient
 from .timeevolve import fvec, iloss2, normalized_overlap, apply_smatrix, sr_step, wrap_difftensor, energy_and_gradient
 from .stateio import save_peps, load_peps

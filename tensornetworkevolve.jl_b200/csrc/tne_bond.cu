@@ -11,6 +11,8 @@
 #include <algorithm>
 #include <cmath>
 
+#include <unordered_set>
+
 #include "tne_internal.h"
 
 namespace {
@@ -484,6 +486,7 @@ struct BondBatch {
     std::vector<BondDev> dev;      // stays alive until the batch has been fetched (source of an async H2D copy)
     tne_buf hmeta = 0, hdev = 0;
     int n = 0;
+    std::vector<tne_buf> slabs;    // speculative sweeps: the scratch of all jobs is carved out of a few big blocks
 };
 
 // builds the device descriptors and launches the bond kernel for `n_jobs` site-disjoint jobs; does not synchronise
@@ -498,6 +501,9 @@ static int bond_enqueue(tne_ctx* ctx, int n_jobs, const tne_bond_job* in, BondBa
     tne_buf& hmeta = bb.hmeta;
     TNE_TRY(buf_new(ctx, {(int64_t)(2 * n_jobs + 1)}, &hmeta));   // kept (as int in .x slot) and error per job
     char* meta = reinterpret_cast<char*>(buf_get(ctx, hmeta)->ptr());
+    cplx* slab_ptr = nullptr;
+    int64_t slab_left = 0;
+    bb.slabs.clear();
     for (int k = 0; k < n_jobs; ++k) {
         const tne_bond_job& jb = in[k];
         BondDev& d = dev[k];
@@ -535,14 +541,36 @@ static int bond_enqueue(tne_ctx* ctx, int n_jobs, const tne_bond_job* in, BondBa
         d.Dmax = jb.Dmax; d.eps = jb.eps; d.vidal = jb.vidal;
         d.Dcap = std::min(4 * Ds, std::min(2 * hj[k].O[0], 2 * hj[k].O[1]));
         d.Dcap = std::max(1, std::min(d.Dcap, std::max(1, (int)jb.Dmax)));
-        for (int side = 0; side < 2; ++side) {
-            TNE_TRY(buf_new(ctx, {(int64_t)hj[k].O[side] * 2 * Ds}, &hj[k].q[side]));
-            TNE_TRY(buf_new(ctx, {(int64_t)2 * hj[k].O[side] * d.Dcap}, &hj[k].uv[side]));
-            d.Q[side] = buf_get(ctx, hj[k].q[side])->ptr();
-            d.UV[side] = buf_get(ctx, hj[k].uv[side])->ptr();
+        if (direct) {
+            // scratch from a bump allocator over big blocks: one pool operation per ~4 MiB instead of five per gate
+            auto carve = [&](int64_t elems, cplx** out) -> int {
+                elems = (elems + 15) / 16 * 16;                       // 256-byte granules
+                if (slab_left < elems) {
+                    tne_buf hs;
+                    const int64_t chunk = std::max<int64_t>(elems, 1 << 18);
+                    TNE_TRY(buf_new(ctx, {chunk}, &hs));
+                    bb.slabs.push_back(hs);
+                    slab_ptr = buf_get(ctx, hs)->ptr();
+                    slab_left = chunk;
+                }
+                *out = slab_ptr;
+                slab_ptr += elems; slab_left -= elems;
+                return TNE_OK;
+            };
+            for (int side = 0; side < 2; ++side) {
+                TNE_TRY(carve((int64_t)hj[k].O[side] * 2 * Ds, &d.Q[side]));
+                TNE_TRY(carve((int64_t)2 * hj[k].O[side] * d.Dcap, &d.UV[side]));
+            }
+        } else {
+            for (int side = 0; side < 2; ++side) {
+                TNE_TRY(buf_new(ctx, {(int64_t)hj[k].O[side] * 2 * Ds}, &hj[k].q[side]));
+                TNE_TRY(buf_new(ctx, {(int64_t)2 * hj[k].O[side] * d.Dcap}, &hj[k].uv[side]));
+                d.Q[side] = buf_get(ctx, hj[k].q[side])->ptr();
+                d.UV[side] = buf_get(ctx, hj[k].uv[side])->ptr();
+            }
+            TNE_TRY(buf_new(ctx, {(int64_t)d.Dcap}, &hj[k].s));
+            d.S = buf_get(ctx, hj[k].s)->ptr();
         }
-        TNE_TRY(buf_new(ctx, {(int64_t)d.Dcap}, &hj[k].s));
-        d.S = buf_get(ctx, hj[k].s)->ptr();
         if (direct) {   // speculative sweep: allocate the final tensors now (bond leg = Dcap) and let the kernel fill them
             for (int side = 0; side < 2; ++side) {
                 std::vector<int64_t> od = hj[k].dims[side];
@@ -671,7 +699,7 @@ extern "C" int tne_tebd_sweep(tne_ctx* ctx, int n_sites, tne_buf* sites, int n_b
     const std::vector<tne_buf> bonds0(bonds, bonds + (vidal ? n_bonds : 0));
     for (int attempt = 0; attempt < 2; ++attempt) {
         const bool speculative = attempt == 0;
-        std::vector<tne_buf> cur_s = sites0, cur_b = bonds0, created;
+        std::vector<tne_buf> cur_s = sites0, cur_b = bonds0, created, scratch;
         std::vector<BondBatch> batches(n_levels);
         std::vector<std::vector<int>> cap(n_levels);
         bool ok = true;
@@ -706,6 +734,8 @@ extern "C" int tne_tebd_sweep(tne_ctx* ctx, int n_sites, tne_buf* sites, int n_b
                 if (rc) break;
             }
             cap[lv].resize(ids.size());
+            for (auto hs : bb.slabs) scratch.push_back(hs);
+            bb.slabs.clear();
             for (size_t q = 0; q < ids.size() && rc == TNE_OK; ++q) {
                 tne_sweep_gate& g = gates[ids[q]];
                 HostJob& h = bb.hj[q];
@@ -713,11 +743,11 @@ extern "C" int tne_tebd_sweep(tne_ctx* ctx, int n_sites, tne_buf* sites, int n_b
                 cap[lv][q] = D;
                 if (!speculative) { g.kept = kept[q]; g.trunc_err = err[q]; }
                 tne_buf ti = 0, tj = 0, sb = 0;
-                if (speculative) {   // the kernel wrote the final tensors itself
+                if (speculative) {   // the kernel writes the final tensors itself
                     cur_s[g.site_i] = direct[3 * q]; cur_s[g.site_j] = direct[3 * q + 1];
                     if (vidal) cur_b[g.bond] = direct[3 * q + 2];
-                    for (int side = 0; side < 2; ++side) { tne_free(ctx, h.q[side]); tne_free(ctx, h.uv[side]); }
-                    tne_free(ctx, h.s);
+                    // the launches are deferred: the scratch of this level must not go back to the pool before its kernel is
+                    // enqueued (a later buf_new -- the descriptor table itself -- could be handed the same block)
                     continue;
                 }
                 rc = bond_place(ctx, h.uv[0], h.dims[0], h.axis[0], D, &ti);
@@ -759,6 +789,8 @@ extern "C" int tne_tebd_sweep(tne_ctx* ctx, int n_sites, tne_buf* sites, int n_b
                 }
             }
         }
+        for (auto h : scratch) tne_free(ctx, h);   // stream-ordered pool: safe once the kernels that use them are enqueued
+        scratch.clear();
         if (rc == TNE_OK && speculative) {   // one synchronisation for the whole sweep: were all the caps reached?
             for (int lv = 0; lv < n_levels && rc == TNE_OK; ++lv) {
                 std::vector<int> kept;
@@ -779,12 +811,10 @@ extern "C" int tne_tebd_sweep(tne_ctx* ctx, int n_sites, tne_buf* sites, int n_b
         }
         if (ok) {
             // hand the final tensors out; intermediate generations (a site touched by several gates) are released
-            for (auto h : created) {
-                bool live = false;
-                for (int i = 0; i < n_sites && !live; ++i) live = cur_s[i] == h;
-                for (size_t i = 0; i < cur_b.size() && !live; ++i) live = cur_b[i] == h;
-                if (!live) tne_free(ctx, h);
-            }
+            std::unordered_set<tne_buf> live(cur_s.begin(), cur_s.end());     // (a scan per handle was quadratic in the replica count)
+            live.insert(cur_b.begin(), cur_b.end());
+            for (auto h : created)
+                if (!live.count(h)) tne_free(ctx, h);
             for (int i = 0; i < n_sites; ++i) sites[i] = cur_s[i];
             for (size_t i = 0; i < cur_b.size(); ++i) bonds[i] = cur_b[i];
             return TNE_OK;

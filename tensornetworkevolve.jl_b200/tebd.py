@@ -68,6 +68,40 @@ def rydberg_tebd_sweep_(reg, g, C, delta, omega, dt):  # src/tebd.jl:15-23
     return reg
 
 
+def _sweep_plan_for(reg, g, C, delta, omega, dt):
+    cache = {}
+
+    def gate(src, dst):
+        key = (g.degree(src), g.degree(dst))
+        if key not in cache:
+            cache[key] = yao.time_evolve(bond_hamiltonian(C, delta, omega, key[0], key[1]), dt)
+        return cache[key]
+    key = (float(C), float(delta), float(omega), float(dt), tuple(g.edges()))
+    cached = getattr(reg, "_sweep_plan", None)
+    if cached is None or cached[0] != key:
+        plan = P.SweepPlan(reg, [(src, dst, np.reshape(gate(src, dst), (2, 2, 2, 2), order="F")) for src, dst in g.edges()])
+        cached = (key, plan)
+        reg._sweep_plan = cached
+    return cached[1]
+
+
+def rydberg_tebd_sweep_batch_(regs, g, C, delta, omega, dt):
+    """``rydberg_tebd_sweep!`` (src/tebd.jl:15-23) of R replica PEPS with one structure in ONE library call: the R copies of
+    every gate run in the same wavefront launch (``peps.apply_sweep_batch_``).  Replica r ends up with exactly the tensors
+    ``rydberg_tebd_sweep_(regs[r], ...)`` gives."""
+    regs = list(regs)
+    P.apply_sweep_batch_(regs, _sweep_plan_for(regs[0], g, C, delta, omega, dt))
+    return regs
+
+
+def rydberg_tebd_batch_(regs, g, *, t, C, delta, omega, nstep):
+    """``rydberg_tebd!`` (src/tebd.jl:25-38, nstep-1 sweeps) for R replicas."""
+    dt = t / nstep
+    for _ in range(nstep - 1):
+        rydberg_tebd_sweep_batch_(regs, g, C, delta, omega, dt)
+    return regs
+
+
 def rydberg_tebd_(reg, g=None, *, t, C, delta, omega, nstep):  # src/tebd.jl:25-38
     if g is None:
         g = SimpleGraph(P.nsite(reg))

@@ -43,7 +43,7 @@ def apply_smatrix(peps, v1, v2, x, memo=None):  # src/timeevolve.jl:15-52
     ``memo``: a dict the caller keeps across calls with the SAME ``v1`` and ``v2`` (the matvecs of one GMRES solve in
     ``sr_step``): the x-independent pieces -- ``<psi2|psi2>`` and the norm programme of ``v1`` (value + pullbacks) -- are then
     contracted once instead of once per product."""
-    if es.FUSED_TREES and peps.kind == "simple":
+    if es.FUSED_TREES:   # SimplePEPS and VidalPEPS alike: the state is multilinear in the bond vectors too
         return _apply_smatrix_fused(peps, v1, v2, x, memo)
     fused = es.FUSED_TREES
     es.FUSED_TREES = False

@@ -477,3 +477,18 @@ def test_plan_cache_rebinds_buffers(tne):
     h2_ = tne.rydberg_hamiltonian(g, 7.0, 0.2, 0.3)   # other coefficients: a different programme
     tne.energy_and_gradient(pa, h2_)
     assert ctx.plan_cache_info()[0] > n2
+
+
+def test_tdvp_drivers_reject_vidal_like_the_reference(tne):
+    """``load_variables`` (the AD version) exists for SimplePEPS only (src/peps.jl:212): ``iloss2`` / ``fvec`` /
+    ``normalized_overlap`` / ``apply_smatrix`` on a VidalPEPS are MethodErrors in the reference and TypeErrors here -- there is
+    no Vidal metric-vector product to accelerate."""
+    g = OG.test_graph()
+    op1 = oracle_peps(g, 2, 21, kind="vidal", Dmax=4)
+    dp1 = device_peps_like(tne, op1, g, 2, Dmax=4)
+    assert dp1.kind == "vidal"
+    v = OP.variables(op1)
+    with pytest.raises(TypeError):
+        tne.apply_smatrix(dp1, tne.DiffTensor(v.copy()), tne.DiffTensor(v.copy()), tne.DiffTensor(v.copy(), requires_grad=False))
+    with pytest.raises(TypeError):
+        tne.normalized_overlap(dp1, tne.DiffTensor(v.copy()), tne.DiffTensor(v.copy()))

@@ -135,3 +135,37 @@ def test_tebd_sweep_from_product_state_exact_ranks(tne, kind):
             assert dp.bond_tensors[b].shape == np.shape(op.bond_tensors[b])
             assert rel(dp.bond_tensors[b].to_numpy(), op.bond_tensors[b]) < 1e-8
     assert len(tne.peps.LOG) == len(OP.LOG)
+
+
+@pytest.mark.parametrize("kind", ["simple", "vidal"])
+def test_replica_batched_sweeps_match_single_sweeps(tne, kind):
+    """R replica PEPS through ONE tne_tebd_sweep call per sweep (rydberg_tebd_batch_): the R copies of a gate share a
+    wavefront launch, every replica ends with exactly the tensors of its own rydberg_tebd_ run (same kernel, same
+    inputs), and a batched sweep issues as many launches as a single one."""
+    L, D, R = 4, 3, 5
+    g = tne.grid([L, L])
+    mk = tne.rand_simplepeps if kind == "simple" else tne.rand_vidalpeps
+    par = dict(t=0.09, C=10.0, delta=0.2, omega=0.3, nstep=4)
+    singles = [mk(g, D, np.random.default_rng(100 + r)) for r in range(R)]
+    batch = [mk(g, D, np.random.default_rng(100 + r)) for r in range(R)]
+    ctx = tne.context()
+    for q in singles:
+        tne.rydberg_tebd_(q, g, **par)
+    l0 = ctx.launch_count()
+    tne.rydberg_tebd_(mk(g, D, np.random.default_rng(7)), g, **par)
+    l_single = ctx.launch_count() - l0
+    l0 = ctx.launch_count()
+    tne.rydberg_tebd_batch_(batch, g, **par)
+    l_batch = ctx.launch_count() - l0
+    assert l_batch == l_single
+    for a, b in zip(singles, batch):
+        for x, y in zip(a.alltensors(), b.alltensors()):
+            assert x.shape == y.shape and np.array_equal(x.to_numpy(), y.to_numpy())
+    # product-state start: some bonds keep fewer singular values than the cap, the whole batch is redone with exact ranks
+    zs = [(tne.zero_simplepeps if kind == "simple" else tne.zero_vidalpeps)(g, D) for _ in range(2)]
+    z1 = (tne.zero_simplepeps if kind == "simple" else tne.zero_vidalpeps)(g, D)
+    tne.rydberg_tebd_batch_(zs, g, **par)
+    tne.rydberg_tebd_(z1, g, **par)
+    for q in zs:
+        for x, y in zip(q.alltensors(), z1.alltensors()):
+            assert x.shape == y.shape and np.array_equal(x.to_numpy(), y.to_numpy())
