@@ -492,6 +492,26 @@ def run_gpu(args):
         st = ctx.program_stats()
         extras["norm_7x7_D4"] = {"ms": nms, "flops": st["flops"], "tflops": st["flops"] / (nms * 1e-3) / 1e12, "log10_norm": float(np.log10(abs(nv.item()))),
                                  "note": "exact <psi|psi> of a 7x7 D=4 PEPS (one contraction, forward only)"}
+    if not args.no_extras:
+        # TEBD does not shard inside one PEPS (replicas only): R independent 8x8 D=4 PEPS per GPU go through ONE
+        # tne_tebd_sweep call per sweep (the R copies of a gate share a wavefront launch); N GPUs run N x R replicas, no communication
+        try:
+            gt2 = T.grid([8, 8])
+            rep = {}
+            for Rr in (8, 32):
+                reps = [T.rand_simplepeps(gt2, 4, np.random.default_rng(seed_for(8, 4) + 1000 * rank + r)) for r in range(Rr)]
+                bs = lambda: T.rydberg_tebd_sweep_batch_(reps, gt2, C_, DELTA_, OMEGA_, 0.03)
+                bs(); bs()
+                rms, _, _ = timed(lambda: [bs() for _ in range(3)], 1)
+                rms /= 3
+                rep["R%d" % Rr] = {"ms_per_batched_sweep": rms, "peps_sweeps_per_s_all_gpus": world * Rr / (rms * 1e-3),
+                                   "bond_updates_per_s_all_gpus": world * Rr * gt2.ne() / (rms * 1e-3)}
+                del reps
+            rep["note"] = ("replica-batched rydberg_tebd_sweep! of 8x8 D=4 PEPS: R replicas per GPU in one library call per sweep (28 wavefront launches of R x 4 "
+                           "CTAs), %d GPU(s) x R replicas, max over ranks; a single PEPS: see tebd_sweep_8x8_D4" % world)
+            extras["tebd_replicas_8x8_D4"] = rep
+        except Exception as e:
+            extras["tebd_replicas_error"] = repr(e)
     if not args.no_extras and (world > 1 or os.environ.get("TNE_BENCH_BIG") == "1"):
         # BASELINE configs[3] / configs[4] on N GPUs: exact norms of big lattices with the two-bond sliced sweep
         # (sweep_plan(slice_first_row=True)): every column loops over the bond entering its last site and the bond leaving

@@ -135,3 +135,36 @@ except T.TneError:
     assert len(rows) == 9, res.stderr[-2000:]
     ar, rs, ag = (sum(int(r[k]) for r in rows) for k in range(3))
     assert ar == 0 and rs == 32 and ag == 40
+
+
+def test_two_bond_sweep_fits_the_8x8_d4_norm_on_cpu():
+    """sweep_plan(slice_first_row=True) through the planner context: the exact 8x8 D=4 norm needs two 64 GiB boundaries +
+    12 GiB (140 GiB: one B200) instead of 320 GiB, at +1.5 % flops; planned for 8 ranks every boundary is combined by a
+    reduce-scatter (each rank only needs the slices it will read), never an all-reduce."""
+    code = r'''
+import os, sys
+os.environ["TNE_PLAN_ONLY"] = "1"
+sys.path.insert(0, %r)
+import numpy as np
+import tne_b200 as T
+from tne_b200 import peps as P, einsum as es
+ctx = T.context(); ctx.set_option("debug", 2); ctx.set_option("rs_comm", 8)
+L, D = 8, 4
+g = T.grid([L, L]); order, segs = T.sweep_plan(g, L, slice_first_row=True)
+assert segs[0] == (1, [g.nv() + 1 + list(g.edges()).index((1, 9))]) and len(segs) == L and all(len(ls) == 2 for _, ls in segs[1:-1]) and len(segs[-1][1]) == 1
+p = T.zero_simplepeps(g, D, optimizer=order, segments=segs)
+p.code_inner_product.seg_shard = True
+leaves = [P._dev(t) for t in p.alltensors()] * 2
+try:
+    es.contract_tree_device(p.code_inner_product, leaves, [1] * 64 + [0] * 64)
+except T.TneError as e:
+    print("REFUSED", e)
+''' % ROOT
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert "REFUSED" in res.stdout, res.stdout + res.stderr[-1500:]
+    m = re.search(r"\[tne-plan\] (\d+) phases, (\d+) launches, ([0-9.e+]+) flops, workspace ([0-9.]+) GiB \(checkpoints ([0-9.]+) \+ segment ([0-9.]+)\)", res.stderr)
+    assert m, res.stderr[-1500:]
+    assert int(m.group(1)) == 8 and abs(float(m.group(3)) - 1.374e15) / 1.374e15 < 0.01
+    assert float(m.group(4)) == 140.0 and float(m.group(5)) == 128.0
+    comm = re.findall(r"checkpoints combined by all-reduce (\d+) \(([0-9.]+) GiB\), reduce-scatter (\d+) \(([0-9.]+) GiB\)", res.stderr)
+    assert len(comm) == 7 and all(c[0] == "0" and c[2] == "1" and float(c[3]) == 64.0 for c in comm), comm
