@@ -85,6 +85,19 @@ int comm_allreduce_ptr(tne_ctx* ctx, cplx* p, int64_t n) {
     return TNE_OK;
 }
 
+// All collectives issued between the two calls form ONE NCCL group (nested groups are legal: the outermost end launches):
+// the checkpoints of a column go out as one fused operation instead of one launch per tensor.
+int comm_group_begin(tne_ctx* ctx) {
+    if (ctx->world <= 1 || !ctx->nccl) return TNE_OK;
+    int rc = g_nccl.group_start();
+    return rc == 0 ? TNE_OK : tne_fail(ctx, TNE_ERR_NCCL, "ncclGroupStart failed: %s", g_nccl.errstr ? g_nccl.errstr(rc) : "?");
+}
+int comm_group_end(tne_ctx* ctx) {
+    if (ctx->world <= 1 || !ctx->nccl) return TNE_OK;
+    int rc = g_nccl.group_end();
+    return rc == 0 ? TNE_OK : tne_fail(ctx, TNE_ERR_NCCL, "ncclGroupEnd failed: %s", g_nccl.errstr ? g_nccl.errstr(rc) : "?");
+}
+
 int comm_allreduce_many(tne_ctx* ctx, int n, cplx* const* ptrs, const int64_t* counts) {
     if (ctx->world <= 1 || n <= 0) return TNE_OK;
     if (!ctx->nccl) return tne_fail(ctx, TNE_ERR_NCCL, "tne_comm_init has not been called");

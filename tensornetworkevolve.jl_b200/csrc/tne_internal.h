@@ -236,6 +236,8 @@ void contract_cost(const TensorRef& A, const TensorRef& B, const TensorRef& C, d
 // ---- multi-GPU (tne_comm.cu): in-place sum over the ranks of `n` complex elements at a device pointer
 int comm_allreduce_ptr(tne_ctx* ctx, cplx* p, int64_t n);
 int comm_allreduce_many(tne_ctx* ctx, int n, cplx* const* ptrs, const int64_t* counts);   // one grouped NCCL call
+int comm_group_begin(tne_ctx* ctx);   // collectives until comm_group_end form one NCCL group
+int comm_group_end(tne_ctx* ctx);
 // `nblocks` contiguous blocks of `block` complex elements at p, block b owned by rank b % world:
 // reduce-scatter: on return the blocks a rank owns hold the sum over ranks (the others are unspecified);
 // all-gather: every rank contributes the blocks it owns, on return all blocks are complete everywhere.

@@ -492,3 +492,28 @@ def test_tdvp_drivers_reject_vidal_like_the_reference(tne):
         tne.apply_smatrix(dp1, tne.DiffTensor(v.copy()), tne.DiffTensor(v.copy()), tne.DiffTensor(v.copy(), requires_grad=False))
     with pytest.raises(TypeError):
         tne.normalized_overlap(dp1, tne.DiffTensor(v.copy()), tne.DiffTensor(v.copy()))
+
+
+def test_treesa_sliced_codes_on_device(tne):
+    """The reference's ``optimizer = TreeSA(nslices = 3)`` (test/peps.jl:9): annealed contraction orders with a SlicedEinsum
+    around them, for the state-tensor code and the inner-product code.  The known answers of test/peps.jl:9-19 on the test
+    graph, and <psi|psi> of the 4x4 D=3 golden PEPS through a TreeSA tree with 2 sliced labels."""
+    gt = tne.graph_from_edges(5, OG.test_graph().edges())
+    p = tne.zero_vidalpeps(gt, 2, optimizer="treesa", nslices=3)
+    assert isinstance(p.code_inner_product, tne.SlicedEinsum) and len(p.code_inner_product.slicing) == 3
+    x = np.zeros(32, dtype=complex); x[0] = 1
+    assert np.allclose(tne.vec(p), x)
+    tne.apply_onsite_(p, 1, np.array([[0, 1], [1, 0]], dtype=complex))
+    x = np.zeros(32, dtype=complex); x[1] = 1
+    assert np.allclose(tne.vec(p), x)
+    q = tne.rand_vidalpeps(gt, 2, np.random.default_rng(3), optimizer="treesa", nslices=3)
+    tne.normalize_(q)
+    assert abs(tne.norm(q).item() - 1) < 1e-12
+    gold = _gold("grid_4x4_D3.npz")
+    L, D = 4, 3
+    g = tne.grid([L, L])
+    ps = tne.rand_simplepeps(g, D, np.random.default_rng(seed_for(L, D)), optimizer="treesa", nslices=2)
+    assert np.array_equal(tne.variables(ps).to_numpy(), gold["variables"])
+    assert rel(tne.inner_product(ps, ps).to_numpy(), gold["inner"]) < TOL
+    h = tne.rydberg_hamiltonian(g, 10.0, 0.2, 0.3)
+    assert rel(tne.expect(h, ps, ps).to_numpy(), gold["energy"]) < TOL
