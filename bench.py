@@ -248,6 +248,8 @@ def run_gpu(args):
     rs_comm = world > 1 and os.environ.get("TNE_RS_COMM", "1") == "1"
     if rs_comm:   # reduce-scatter / all-gather of the column checkpoints (half the NVLink bytes of the all-reduce; TNE_RS_COMM=0 disables)
         ctx.set_option("rs_comm", 1)
+    if os.environ.get("TNE_COMM_OVERLAP") == "0":   # all-gathers of the reverse pass on the compute stream instead of behind the next column's recompute
+        ctx.set_option("comm_overlap", 0)
     if world > 1:
         T.array.init_comm(ctx, dist, rank, world)
     L, D = args.L, args.D
@@ -582,8 +584,9 @@ def run_gpu(args):
             "dtype": "c128 (f64)", "data": "synthetic",
             "config": {"workload": workload_string(L, D),
                        "plan": "boundary sweep, one checkpointed segment per column, D^2 segment-local slices",
-                       "parallelism": "1 GPU" if world == 1 else ("segment-local bond slices dealt to %d GPUs, NCCL %s of column checkpoints, all-reduce of the outputs"
-                                                                       % (world, "reduce-scatter / all-gather" if rs_comm else "all-reduce")),
+                       "parallelism": "1 GPU" if world == 1 else ("segment-local bond slices dealt to %d GPUs, NCCL %s of column checkpoints (one group per column%s), all-reduce of the outputs"
+                                                                       % (world, "reduce-scatter / all-gather" if rs_comm else "all-reduce",
+                                                                          ", all-gathers on a second stream behind the next column's recompute" if rs_comm and os.environ.get("TNE_COMM_OVERLAP") != "0" else "")),
                        "l2": "no flush needed: a step streams a %.0f GiB workspace (>> 126 MB L2)" % (ctx.mem_info()["workspace"] / 2 ** 30),
                        "seed": seed_for(L, D)},
             "executed_tflops_per_gpu": tot_flops / (prof_ms * 1e-3) / 1e12 if prof_ms else None,

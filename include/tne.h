@@ -64,7 +64,7 @@ int tne_plan_cache_info(tne_ctx* ctx, int64_t* entries, int64_t* hits);
 /* option knobs: "force_generic_kernel", "debug", "profile" (1: bracket every contraction launch with a
  * CUDA-event pair on the context's stream; read the totals with tne_profile_collect), "absorb_tma" (1: use the
  * TMA-staged absorb kernel where it applies), "no_reduce_tma" (1: register-fed reduce kernel), "pad",
- * "no_permute" (1: unary permutations run on the FMA contraction kernel instead of the tiled transpose), "no_gemm" (1: general dense nodes run on the FMA kernel instead of the tiled DMMA GEMM), "no_plan_cache" (1: re-plan every tree call), "no_site2" / "no_site2b" / "no_fuse" (1: never fuse the two steps of a site / the contributions into one output: the step-by-step
+ * "no_permute" (1: unary permutations run on the FMA contraction kernel instead of the tiled transpose), "no_gemm" (1: general dense nodes run on the FMA kernel instead of the tiled DMMA GEMM), "no_plan_cache" (1: re-plan every tree call), "comm_overlap" (0: the all-gathers of the multi-GPU reverse pass stay on the compute stream), "no_site2" / "no_site2b" / "no_fuse" (1: never fuse the two steps of a site / the contributions into one output: the step-by-step
  * launch plan), "rs_comm" (1: multi-GPU checkpoints are combined by reduce-scatter / all-gather instead of all-reduce).
  * A context created with TNE_PLAN_ONLY=1 in the environment on a machine WITHOUT a device is a planner: tree programs are
  * built, costed and dumped to stderr, no kernel ever runs, tne_download and the tree entry points fail. */

@@ -27,6 +27,9 @@ struct NcclApi {
 };
 NcclApi g_nccl;
 
+// collectives go to the compute stream unless the tree executor has routed them to its communication stream
+inline cudaStream_t comm_stream_of(tne_ctx* ctx) { return ctx->comm_active ? ctx->comm_active : ctx->stream; }
+
 int load_nccl(tne_ctx* ctx) {
     if (g_nccl.lib) return TNE_OK;
     const char* names[] = {"libnccl.so.2", "libnccl.so"};
@@ -80,7 +83,7 @@ int comm_allreduce_ptr(tne_ctx* ctx, cplx* p, int64_t n) {
     if (ctx->world <= 1 || n <= 0) return TNE_OK;
     if (!ctx->nccl) return tne_fail(ctx, TNE_ERR_NCCL, "tne_comm_init has not been called");
     const int NCCL_DOUBLE = 8, NCCL_SUM = 0;
-    int rc = g_nccl.allreduce(p, p, (size_t)(2 * n), NCCL_DOUBLE, NCCL_SUM, ctx->nccl, ctx->stream);
+    int rc = g_nccl.allreduce(p, p, (size_t)(2 * n), NCCL_DOUBLE, NCCL_SUM, ctx->nccl, comm_stream_of(ctx));
     if (rc != 0) return tne_fail(ctx, TNE_ERR_NCCL, "ncclAllReduce failed: %s", g_nccl.errstr ? g_nccl.errstr(rc) : "?");
     return TNE_OK;
 }
@@ -104,7 +107,7 @@ int comm_allreduce_many(tne_ctx* ctx, int n, cplx* const* ptrs, const int64_t* c
     const int NCCL_DOUBLE = 8, NCCL_SUM = 0;
     int rc = g_nccl.group_start();
     for (int i = 0; i < n && rc == 0; ++i)
-        if (counts[i] > 0) rc = g_nccl.allreduce(ptrs[i], ptrs[i], (size_t)(2 * counts[i]), NCCL_DOUBLE, NCCL_SUM, ctx->nccl, ctx->stream);
+        if (counts[i] > 0) rc = g_nccl.allreduce(ptrs[i], ptrs[i], (size_t)(2 * counts[i]), NCCL_DOUBLE, NCCL_SUM, ctx->nccl, comm_stream_of(ctx));
     int rc2 = g_nccl.group_end();
     if (rc != 0 || rc2 != 0) return tne_fail(ctx, TNE_ERR_NCCL, "ncclAllReduce failed: %s", g_nccl.errstr ? g_nccl.errstr(rc ? rc : rc2) : "?");
     return TNE_OK;
@@ -124,8 +127,8 @@ static int comm_blocks(tne_ctx* ctx, cplx* p, int64_t block, int64_t nblocks, bo
     for (int64_t j = 0; j < nblocks / ctx->world && rc == 0; ++j) {
         cplx* base = p + j * ctx->world * block;
         cplx* mine = base + (int64_t)ctx->rank * block;
-        rc = gather ? g_nccl.all_gather(mine, base, count, NCCL_DOUBLE, ctx->nccl, ctx->stream)
-                    : g_nccl.reduce_scatter(base, mine, count, NCCL_DOUBLE, NCCL_SUM, ctx->nccl, ctx->stream);
+        rc = gather ? g_nccl.all_gather(mine, base, count, NCCL_DOUBLE, ctx->nccl, comm_stream_of(ctx))
+                    : g_nccl.reduce_scatter(base, mine, count, NCCL_DOUBLE, NCCL_SUM, ctx->nccl, comm_stream_of(ctx));
     }
     int rc2 = g_nccl.group_end();
     if (rc != 0 || rc2 != 0)
@@ -144,7 +147,7 @@ extern "C" int tne_allreduce_sum(tne_ctx* ctx, int n, const tne_buf* bufs) {
     for (int i = 0; i < n && rc == 0; ++i) {
         Buf* b = buf_get(ctx, bufs[i]);
         if (!b) { g_nccl.group_end(); return TNE_ERR_INVALID; }
-        rc = g_nccl.allreduce(b->ptr(), b->ptr(), (size_t)(2 * b->nelem), NCCL_DOUBLE, NCCL_SUM, ctx->nccl, ctx->stream);
+        rc = g_nccl.allreduce(b->ptr(), b->ptr(), (size_t)(2 * b->nelem), NCCL_DOUBLE, NCCL_SUM, ctx->nccl, comm_stream_of(ctx));
     }
     int rc2 = g_nccl.group_end();
     if (rc != 0 || rc2 != 0) return tne_fail(ctx, TNE_ERR_NCCL, "ncclAllReduce failed: %s", g_nccl.errstr ? g_nccl.errstr(rc ? rc : rc2) : "?");

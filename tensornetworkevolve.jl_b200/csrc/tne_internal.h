@@ -69,6 +69,10 @@ struct tne_ctx {
     int64_t opt_absorb_tma = 0;            // 1: TMA-staged absorb kernel where applicable (default: register-fed)
     int64_t opt_no_reduce_tma = 0;         // 1: register-fed reduce kernel instead of the TMA-staged one
     int64_t opt_rs_comm = 0;               // 1: reduce-scatter / all-gather of column checkpoints instead of all-reduce (tne_tree.cu)
+    int64_t opt_comm_overlap = 1;          // 1: the all-gathers of the reverse pass run on a second stream behind the next column's recompute
+    cudaStream_t comm_stream = nullptr;    // created on first use
+    cudaStream_t comm_active = nullptr;    // stream the collectives of tne_comm.cu are issued on right now (nullptr: the compute stream)
+    cudaEvent_t ev_comm_ready = nullptr, ev_comm_done = nullptr;
     struct ProfRec { cudaEvent_t e0, e1; int cls; double flops, bytes; };
     std::vector<ProfRec> prof;              // pending event pairs
     std::vector<cudaEvent_t> event_pool;

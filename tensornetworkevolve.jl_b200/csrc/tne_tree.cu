@@ -1019,11 +1019,17 @@ struct Exec {
 
     bool seg_shard = false;   // deal segment-local slices to the ranks; all-reduce the checkpoints of sliced segments
 
+    std::set<int> pending;    // checkpoints whose all-gather is in flight on the communication stream
+
     int run() {
         const int world = seg_shard ? std::max(1, ctx->world) : 1, rank = seg_shard ? ctx->rank : 0;
+        pending.clear();
         for (auto& ph : phases) {
             const bool sharded = world > 1 && ph.nsl > 1;
-            for (int v : ph.zero_at_start) TNE_TRY(launch_fill_zero(ctx, base_ptr(ph, v), extent_of(P.vals[v])));
+            for (int v : ph.zero_at_start) {
+                if (pending.count(v)) { TNE_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_comm_done, 0)); pending.clear(); }
+                TNE_TRY(launch_fill_zero(ctx, base_ptr(ph, v), extent_of(P.vals[v])));
+            }
             std::vector<int64_t> idx(ph.sliced.size(), 0);
             for (int64_t it = 0; it < ph.nsl; ++it) {
                 if (sharded && it % world != rank) continue;
@@ -1038,6 +1044,11 @@ struct Exec {
                 };
                 for (auto& po : ph.ops) {
                     if (po.first_slice_only && it > 0) continue;
+                    if (!pending.empty()) {
+                        bool hit = pending.count(po.op.out) > 0 || (po.s2b && pending.count(po.s2b_dB1) > 0);
+                        if (!hit) for (int v : po.inputs()) if (v >= 0 && pending.count(v)) { hit = true; break; }
+                        if (hit) { TNE_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_comm_done, 0)); pending.clear(); }
+                    }
                     // replicated segment: every rank computes the same thing; only rank 0 may add to the outputs
                     if (world > 1 && !sharded && rank != 0 && P.vals[po.op.out].ext) continue;
                     if (po.s2) {
@@ -1075,22 +1086,52 @@ struct Exec {
                 }
             }
             if (sharded && !ph.zero_at_start.empty()) {
-                // all checkpoints of the column in ONE NCCL group: a single fused launch instead of one (or two) per tensor
-                TNE_TRY(comm_group_begin(ctx));
-                int rc = TNE_OK;
-                for (int v : ph.zero_at_start) {
-                    auto ci = ph.comm.find(v);
-                    const int kind = ci == ph.comm.end() ? 0 : ci->second.kind;
-                    if (kind == 1) rc = comm_reduce_scatter_blocks(ctx, base_ptr(ph, v), ci->second.block, ci->second.nblocks);
-                    else if (kind == 2) rc = comm_all_gather_blocks(ctx, base_ptr(ph, v), ci->second.block, ci->second.nblocks);
-                    else rc = comm_allreduce_ptr(ctx, base_ptr(ph, v), extent_of(P.vals[v]));
-                    if (rc) break;
+                // All checkpoints of the column in ONE NCCL group (a single fused launch instead of one or two per tensor).
+                // The all-gathers (cotangent checkpoints of the reverse pass: every rank wrote the slices it owns) are not
+                // needed before the next column's reverse ops, which come after that column's recompute: they run on a second
+                // stream, the compute stream waits for them right before the first op that touches one of the tensors.
+                const bool overlap = ctx->opt_comm_overlap && ctx->opt_rs_comm;
+                for (int pass = 0; pass < 2; ++pass) {          // pass 0: compute stream (all-reduce, reduce-scatter); pass 1: all-gathers
+                    std::vector<int> todo;
+                    for (int v : ph.zero_at_start) {
+                        auto ci = ph.comm.find(v);
+                        const int kind = ci == ph.comm.end() ? 0 : ci->second.kind;
+                        if ((kind == 2) == (pass == 1)) todo.push_back(v);
+                    }
+                    if (todo.empty()) continue;
+                    const bool side = pass == 1 && overlap;
+                    if (side) {
+                        if (!pending.empty()) { TNE_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_comm_done, 0)); pending.clear(); }
+                        if (!ctx->comm_stream) {
+                            TNE_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
+                            TNE_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_comm_ready, cudaEventDisableTiming));
+                            TNE_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_comm_done, cudaEventDisableTiming));
+                        }
+                        TNE_CUDA(ctx, cudaEventRecord(ctx->ev_comm_ready, ctx->stream));
+                        TNE_CUDA(ctx, cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_comm_ready, 0));
+                        ctx->comm_active = ctx->comm_stream;
+                    }
+                    int rc = comm_group_begin(ctx);
+                    for (int v : todo) {
+                        if (rc) break;
+                        auto ci = ph.comm.find(v);
+                        const int kind = ci == ph.comm.end() ? 0 : ci->second.kind;
+                        if (kind == 1) rc = comm_reduce_scatter_blocks(ctx, base_ptr(ph, v), ci->second.block, ci->second.nblocks);
+                        else if (kind == 2) rc = comm_all_gather_blocks(ctx, base_ptr(ph, v), ci->second.block, ci->second.nblocks);
+                        else rc = comm_allreduce_ptr(ctx, base_ptr(ph, v), extent_of(P.vals[v]));
+                    }
+                    const int rc2 = comm_group_end(ctx);
+                    ctx->comm_active = nullptr;
+                    if (rc) return rc;
+                    TNE_TRY(rc2);
+                    if (side) {
+                        TNE_CUDA(ctx, cudaEventRecord(ctx->ev_comm_done, ctx->comm_stream));
+                        pending.insert(todo.begin(), todo.end());
+                    }
                 }
-                const int rc2 = comm_group_end(ctx);
-                if (rc) return rc;
-                TNE_TRY(rc2);
             }
         }
+        if (!pending.empty()) { TNE_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_comm_done, 0)); pending.clear(); }
         return TNE_OK;
     }
 };
