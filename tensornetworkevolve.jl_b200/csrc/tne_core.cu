@@ -286,6 +286,7 @@ extern "C" int tne_set_option(tne_ctx* ctx, const char* key, int64_t value) {
     else if (k == "no_site2b") ctx->opt_no_site2b = value;
     else if (k == "no_gemm") ctx->opt_no_gemm = value;
     else if (k == "comm_overlap") ctx->opt_comm_overlap = value;
+    else if (k == "tape_gib") ctx->opt_tape_gib = value;
     else if (k == "no_plan_cache") { ctx->opt_no_plan_cache = value; if (value) ctx->plan_cache.clear(); }
     else if (k == "no_permute") ctx->opt_no_permute = value;
     else if (k == "no_rows") ctx->opt_no_rows = value;

@@ -69,6 +69,7 @@ struct tne_ctx {
     int64_t opt_absorb_tma = 0;            // 1: TMA-staged absorb kernel where applicable (default: register-fed)
     int64_t opt_no_reduce_tma = 0;         // 1: register-fed reduce kernel instead of the TMA-staged one
     int64_t opt_rs_comm = 0;               // 1: reduce-scatter / all-gather of column checkpoints instead of all-reduce (tne_tree.cu)
+    int64_t opt_tape_gib = -1;             // forward tapes kept for the reverse pass: -1 whatever memory is left, 0 none, n > 0: n GiB
     int64_t opt_comm_overlap = 1;          // 1: the all-gathers of the reverse pass run on a second stream behind the next column's recompute
     cudaStream_t comm_stream = nullptr;    // created on first use
     cudaStream_t comm_active = nullptr;    // stream the collectives of tne_comm.cu are issued on right now (nullptr: the compute stream)

@@ -398,12 +398,15 @@ struct PView {               // how one value looks inside one phase (segment-lo
     int64_t off = 0;                  // byte offset: temp arena (temp) or checkpoint arena
     bool dep = false;                 // differs from slice to slice
     int64_t nelem = 1;
+    bool tape = false;                // kept from the forward phase for the reverse phase of a retained (segment, slice) unit
+    int64_t tape_off = 0;             // byte offset inside the unit's tape block
 };
 
 struct PhaseOp {
     Op op;
     ContractPlan plan;
     bool first_slice_only = false;
+    bool skip_if_retained = false;     // recompute op whose result a retained unit still has from its forward phase
     bool dead = false;                 // merged into a later op
     // further contributions into the same output, fused into one launch (gett_absorb_multi)
     struct Extra { int a, b; ContractPlan plan; };
@@ -441,6 +444,10 @@ struct Phase {
     struct Comm { int kind = 0; int64_t block = 0, nblocks = 0; };
     std::map<int, Comm> comm;
     int64_t temp_bytes = 0;
+    // tape retention: byte offset of the tape block of slice `it` of this segment (-1: the unit is recomputed), shared by
+    // the forward and the reverse phase of the segment; tape_unit_bytes: size of one block
+    std::vector<int64_t> unit_tape_base;
+    int64_t tape_unit_bytes = 0;
 };
 
 struct Interval { int id; int64_t bytes; int first, last; int64_t off; };
@@ -478,7 +485,8 @@ struct Exec {
     Program& P;
     tne_ctx* ctx;
     std::vector<Phase> phases;
-    int64_t persist_bytes = 0, temp_bytes = 0;
+    int64_t persist_bytes = 0, temp_bytes = 0, tape_bytes = 0;
+    int tape_units = 0, tape_units_possible = 0;
     std::map<int32_t, int64_t> label_size;
     std::set<int> ever_zeroed;   // checkpoints are cleared by the first phase that writes them only
     Exec(Program& p) : P(p), ctx(p.ctx) {}
@@ -952,12 +960,78 @@ struct Exec {
         return rc;
     }
 
-    cplx* base_ptr(const Phase& ph, int v) const {
+    cplx* base_ptr(const Phase& ph, int v, int64_t tape_base = -1) const {
         const Val& val = P.vals[v];
         if (val.ext) return val.ext + val.slice_base;
         const PView& pv = ph.views.at(v);
         char* ws = reinterpret_cast<char*>(ctx->ws);
+        if (pv.tape && tape_base >= 0) return reinterpret_cast<cplx*>(ws + persist_bytes + temp_bytes + tape_base + pv.tape_off);
         return reinterpret_cast<cplx*>(pv.temp ? ws + persist_bytes + pv.off : ws + val.offset);
+    }
+
+    // Tape retention.  The reverse phase of a sliced segment re-runs the segment's forward ops for every slice because the
+    // tapes of all (segment, slice) units do not fit together (860 GB at 6x6 D=4).  Whatever DOES fit in the memory that is
+    // left keeps its tape: the forward values the reverse ops read (the boundaries before every site, not the twice-larger
+    // bra intermediates) are written to a block of their own per retained unit and the unit's recompute ops are skipped.
+    // One B200 holds ~10 of the 64 units of the benchmark; with the slices dealt to 8 ranks every rank holds ALL of its 8-9
+    // units and the recompute (27 % of the executed flops) disappears.
+    void plan_tape(int64_t budget, int world, int rank) {
+        tape_bytes = 0; tape_units = 0; tape_units_possible = 0;
+        if (budget <= 0) return;
+        for (size_t pb = 0; pb < phases.size(); ++pb) {
+            Phase& B = phases[pb];
+            if (!B.backward) continue;
+            bool has_re = false;
+            for (auto& po : B.ops) if (po.op.recompute) has_re = true;
+            if (!has_re) continue;
+            size_t pf = phases.size();
+            for (size_t q = 0; q < pb; ++q) if (phases[q].seg == B.seg && !phases[q].backward) pf = q;
+            if (pf == phases.size()) continue;
+            Phase& F = phases[pf];
+            if (F.nsl != B.nsl) continue;
+            // values the reverse ops (not the recompute ops) read that the forward phase materialises per slice
+            std::set<int> fwd_written;
+            for (auto& po : F.ops) fwd_written.insert(po.op.out);
+            std::set<int> need;
+            bool ok = true;
+            for (auto& po : B.ops) {
+                if (po.op.recompute) continue;
+                for (int v : po.inputs()) {
+                    if (v < 0) continue;
+                    const PView& pv = B.views.at(v);
+                    if (!pv.temp || (!pv.dep && B.nsl > 1)) continue;    // slice-independent values of a sliced segment are cheap: recomputed
+                    bool made_here = false;        // produced by a recompute op of this phase (i.e. a forward value)?
+                    for (auto& pr : B.ops) if (pr.op.recompute && pr.op.out == v) made_here = true;
+                    if (!made_here) continue;      // a cotangent or another reverse value
+                    if (!fwd_written.count(v) || !F.views.count(v) || !F.views.at(v).temp) { ok = false; break; }
+                    need.insert(v);
+                }
+                if (!ok) break;
+            }
+            if (!ok || need.empty()) continue;
+            int64_t off = 0;
+            for (int v : need) {
+                PView& vb = B.views.at(v);
+                PView& vf = F.views.at(v);
+                vb.tape = vf.tape = true;
+                vb.tape_off = vf.tape_off = off;
+                off += round512(vb.nelem * (int64_t)sizeof(cplx));
+            }
+            for (auto& po : B.ops)
+                if (po.op.recompute && (B.views.at(po.op.out).dep || B.nsl == 1) && B.views.at(po.op.out).temp) po.skip_if_retained = true;
+            F.tape_unit_bytes = B.tape_unit_bytes = off;
+            F.unit_tape_base.assign(F.nsl, -1);
+            const bool sharded = world > 1 && F.nsl > 1;
+            for (int64_t it = 0; it < F.nsl; ++it) {
+                if (sharded && it % world != rank) continue;
+                ++tape_units_possible;
+                if (tape_bytes + off > budget) continue;
+                F.unit_tape_base[it] = tape_bytes;
+                tape_bytes += off;
+                ++tape_units;
+            }
+            B.unit_tape_base = F.unit_tape_base;
+        }
     }
 
     // one line per launch group of the final (fused) phases: what runs, how often, with which algorithmic cost
@@ -966,7 +1040,9 @@ struct Exec {
         long long tot_launches = 0;
         for (auto& ph : phases)
             for (auto& po : ph.ops) {
-                const long long n = po.first_slice_only ? 1 : ph.nsl;
+                long long n = po.first_slice_only ? 1 : ph.nsl;
+                if (po.skip_if_retained)
+                    for (auto tb : ph.unit_tape_base) if (tb >= 0) --n;     // units that kept their tape do not recompute
                 double fl = (po.s2 || po.s2b) ? po.s2_flops : po.plan.flops;
                 for (auto& ex : po.extra) fl += ex.plan.flops;
                 tot_flops += fl * (double)n;
@@ -974,6 +1050,9 @@ struct Exec {
             }
         fprintf(stderr, "[tne-plan] %zu phases, %lld launches, %.4e flops, workspace %.3f GiB (checkpoints %.3f + segment %.3f)\n", phases.size(),
                 tot_launches, tot_flops, (persist_bytes + temp_bytes) / 1073741824.0, persist_bytes / 1073741824.0, temp_bytes / 1073741824.0);
+        if (tape_units_possible > 0)
+            fprintf(stderr, "[tne-plan] tape retention: %d of this rank's %d (segment, slice) units keep their forward tape (%.3f GiB), the others are recomputed\n",
+                    tape_units, tape_units_possible, tape_bytes / 1073741824.0);
         for (size_t pi = 0; pi < phases.size(); ++pi) {
             const Phase& ph = phases[pi];
             if (ph.nsl <= 1 || ph.zero_at_start.empty()) continue;
@@ -1035,15 +1114,17 @@ struct Exec {
                 if (sharded && it % world != rank) continue;
                 int64_t rem = it;
                 for (size_t s = 0; s < idx.size(); ++s) { idx[s] = rem % ph.ssz[s]; rem /= ph.ssz[s]; }
+                const int64_t tbase = ph.unit_tape_base.empty() ? -1 : ph.unit_tape_base[it];
                 auto ptr_of = [&](int v) -> cplx* {
                     if (v < 0) return ctx->one_dev;
-                    cplx* p = base_ptr(ph, v);
+                    cplx* p = base_ptr(ph, v, tbase);
                     const PView& pv = ph.views.at(v);
                     for (size_t s = 0; s < idx.size(); ++s) p += idx[s] * pv.sl_stride[s];
                     return p;
                 };
                 for (auto& po : ph.ops) {
                     if (po.first_slice_only && it > 0) continue;
+                    if (po.skip_if_retained && tbase >= 0) continue;      // the unit kept this value from its forward phase
                     if (!pending.empty()) {
                         bool hit = pending.count(po.op.out) > 0 || (po.s2b && pending.count(po.s2b_dB1) > 0);
                         if (!hit) for (int v : po.inputs()) if (v >= 0 && pending.count(v)) { hit = true; break; }
@@ -1200,7 +1281,7 @@ int program_key(tne_ctx* ctx, const tne_tree* T, const tne_buf* leaves, const in
     key_put1(k, n_grad);
     if (n_grad > 0) key_put(k, grad_leaves, n_grad);
     const int64_t opts[] = {ctx->opt_force_generic, ctx->opt_debug, ctx->opt_pad, ctx->opt_no_rows, ctx->opt_no_pdl, ctx->opt_no_site2, ctx->opt_no_fuse,
-                            ctx->opt_no_permute, ctx->opt_no_gemm, ctx->opt_no_site2b, ctx->opt_absorb_tma, ctx->opt_no_reduce_tma, ctx->opt_rs_comm,
+                            ctx->opt_no_permute, ctx->opt_no_gemm, ctx->opt_no_site2b, ctx->opt_absorb_tma, ctx->opt_no_reduce_tma, ctx->opt_rs_comm, ctx->opt_tape_gib,
                             (int64_t)ctx->world, (int64_t)ctx->rank, ctx->mem_limit};
     key_put(k, opts, sizeof(opts) / sizeof(opts[0]));
     return TNE_OK;
@@ -1315,10 +1396,21 @@ extern "C" int tne_expect_terms(tne_ctx* ctx, const tne_tree* tree, const tne_bu
             if (ctx->plan_only && ctx->opt_rs_comm > 1) w = (int)ctx->opt_rs_comm;   // planner: rs_comm = the world size to plan for
             E.plan_comm(w);
         }
+        {
+            // memory left after the checkpoints and the per-segment arena keeps forward tapes (reverse mode only)
+            int64_t tb = 0;
+            if (n_grad > 0 && ctx->opt_tape_gib != 0) {
+                const int64_t margin = (int64_t)6 << 30;
+                tb = ctx->opt_tape_gib > 0 ? (ctx->opt_tape_gib << 30) : ctx->mem_limit - ctx->in_use - E.persist_bytes - E.temp_bytes - margin;
+                if (ctx->plan_only && ctx->opt_tape_gib < 0) tb = ((int64_t)151 << 30) - E.persist_bytes - E.temp_bytes - margin;   // planner: a B200
+            }
+            const int w = E.seg_shard ? ctx->world : 1;
+            E.plan_tape(tb, (ctx->plan_only && ctx->opt_rs_comm > 1) ? (int)ctx->opt_rs_comm : w, E.seg_shard ? ctx->rank : 0);
+        }
         if (ctx->opt_debug > 2 || ctx->plan_only) E.dump_final();
         if (ctx->plan_only)
             return fail_cleanup(tne_fail(ctx, TNE_ERR_UNSUPPORTED, "planner context (TNE_PLAN_ONLY): program built and dumped, nothing computed"));
-        cp->peak = E.persist_bytes + E.temp_bytes;
+        cp->peak = E.persist_bytes + E.temp_bytes + E.tape_bytes;
         if (use_cache) {
             ctx->plan_cache.emplace_front(key, std::static_pointer_cast<void>(cp));
             while (ctx->plan_cache.size() > PLAN_CACHE_MAX) ctx->plan_cache.pop_back();

@@ -517,3 +517,29 @@ def test_treesa_sliced_codes_on_device(tne):
     assert rel(tne.inner_product(ps, ps).to_numpy(), gold["inner"]) < TOL
     h = tne.rydberg_hamiltonian(g, 10.0, 0.2, 0.3)
     assert rel(tne.expect(h, ps, ps).to_numpy(), gold["energy"]) < TOL
+
+
+def test_tape_retention_is_bit_identical(tne):
+    """Forward tapes of as many (segment, slice) units as fit in memory are kept for the reverse pass instead of being
+    recomputed (option tape_gib: -1 auto, 0 off): the same kernels on the same inputs, so energy and force do not change
+    by a bit, and fewer contractions run."""
+    ctx = tne.context()
+    L, D = 4, 4
+    g = tne.grid([L, L])
+    order, segs = tne.sweep_plan(g, L)
+    p = tne.rand_simplepeps(g, D, np.random.default_rng(seed_for(L, D)), optimizer=order, segments=segs)
+    h = tne.rydberg_hamiltonian(g, 10.0, 0.2, 0.3)
+    out = {}
+    for gib in (0, -1, 1):
+        ctx.set_option("tape_gib", gib)
+        try:
+            y, f = tne.energy_and_gradient(p, h)
+            out[gib] = (y.to_numpy(), f.to_numpy(), ctx.program_stats())
+        finally:
+            ctx.set_option("tape_gib", -1)
+    for gib in (-1, 1):
+        assert np.array_equal(out[gib][0], out[0][0]) and np.array_equal(out[gib][1], out[0][1])
+    # everything fits at this size: only the slice-independent crumbs (tiny leaf-level ops) are still recomputed
+    assert out[-1][2]["recompute_flops"] < 1e-3 * out[0][2]["recompute_flops"] and out[0][2]["recompute_flops"] > 0.2 * out[0][2]["flops"]
+    assert out[-1][2]["contractions"] < out[0][2]["contractions"]
+    assert out[-1][2]["flops"] == out[0][2]["flops"]
