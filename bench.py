@@ -583,7 +583,8 @@ def run_gpu(args):
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "c128 (f64)", "data": "synthetic",
             "config": {"workload": workload_string(L, D),
-                       "plan": "boundary sweep, one checkpointed segment per column, D^2 segment-local slices",
+                       "plan": "boundary sweep, one checkpointed segment per column, D^2 segment-local slices; forward tapes of as many (column, slice) units as fit in "
+                               "the remaining HBM are kept for the reverse pass, the others recomputed (recompute_flops_per_step_per_gpu)",
                        "parallelism": "1 GPU" if world == 1 else ("segment-local bond slices dealt to %d GPUs, NCCL %s of column checkpoints (one group per column%s), all-reduce of the outputs"
                                                                        % (world, "reduce-scatter / all-gather" if rs_comm else "all-reduce",
                                                                           ", all-gathers on a second stream behind the next column's recompute" if rs_comm and os.environ.get("TNE_COMM_OVERLAP") != "0" else "")),

@@ -168,3 +168,21 @@ except T.TneError as e:
     assert float(m.group(4)) == 140.0 and float(m.group(5)) == 128.0
     comm = re.findall(r"checkpoints combined by all-reduce (\d+) \(([0-9.]+) GiB\), reduce-scatter (\d+) \(([0-9.]+) GiB\)", res.stderr)
     assert len(comm) == 7 and all(c[0] == "0" and c[2] == "1" and float(c[3]) == 64.0 for c in comm), comm
+
+
+def test_tape_retention_plan_on_cpu():
+    """plan_tape through the planner context (a 151 GiB budget stands in for a B200): one rank keeps the forward tapes of 12 of
+    the 64 (column, slice) units of the 6x6 D=4 <H>+grad programme and skips their recompute launches; planned for 8 ranks
+    every one of a rank's 8 units fits; tape_gib = 0 restores the all-recompute plan."""
+    base = _plan("6", "4", "tape_gib=0", "--raw")
+    auto = _plan("6", "4", "--raw")
+    m0 = re.search(r"\[tne-plan\] (\d+) phases, (\d+) launches, ([0-9.e+]+) flops", base)
+    m1 = re.search(r"\[tne-plan\] (\d+) phases, (\d+) launches, ([0-9.e+]+) flops", auto)
+    assert m0 and m1, auto[-1500:]
+    assert "tape retention" not in base
+    t = re.search(r"tape retention: (\d+) of this rank's (\d+) \(segment, slice\) units keep their forward tape \(([0-9.]+) GiB\)", auto)
+    assert t and int(t.group(1)) == 12 and int(t.group(2)) == 65 and 115.0 < float(t.group(3)) <= 121.0, auto[-1500:]
+    assert float(m0.group(3)) == 7.8777e13 and 7.4e13 < float(m1.group(3)) < 7.5e13 and int(m1.group(2)) < int(m0.group(2))
+    w8 = _plan("6", "4", "rs_comm=8", "--raw")
+    t8 = re.search(r"tape retention: (\d+) of this rank's (\d+)", w8)
+    assert t8 and t8.group(1) == t8.group(2) == "9", w8[-1500:]
