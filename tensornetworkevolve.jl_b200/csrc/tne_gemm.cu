@@ -33,8 +33,8 @@ constexpr int GM_ASTR = GM_TK + 4;            // complex per A row in shared mem
 constexpr int GM_BSTR = 2 * GM_TK + 4;        // doubles per B' row (conflict-free 64-bit fragment reads)
 
 // WM x WN warps; a warp owns (TM / WM) rows = MT m-tiles and (TN / WN) complex columns = NTW n-tiles of 4
-template <int TM, int TN, int WM, int WN>
-__global__ void __launch_bounds__(32 * WM * WN) gett_gemm(const __grid_constant__ GettDesc d, const cplx* __restrict__ A,
+template <int TM, int TN, int WM, int WN, int MINB = 1>
+__global__ void __launch_bounds__(32 * WM * WN, MINB) gett_gemm(const __grid_constant__ GettDesc d, const cplx* __restrict__ A,
                                                          const cplx* __restrict__ B, cplx* __restrict__ C) {
     constexpr int NTHR = 32 * WM * WN;
     constexpr int MT = TM / WM / 8, NTW = TN / WN / 4;
@@ -176,19 +176,19 @@ size_t gemm_smem() {
     return (size_t)2 * TM * GM_ASTR * sizeof(cplx) + (size_t)2 * 2 * TN * GM_BSTR * sizeof(double) + (size_t)(2 * TM + 2 * TN) * sizeof(long long) + 128;
 }
 
-template <int TM, int TN, int WM, int WN>
+template <int TM, int TN, int WM, int WN, int MINB = 1>
 int launch_gemm(tne_ctx* ctx, const ContractPlan& plan, const cplx* A, const cplx* B, cplx* C) {
-    ensure_smem_attr(ctx, gett_gemm<TM, TN, WM, WN>, (int)gemm_smem<TM, TN>());
-    dim3 grid(plan.gx, plan.gy, plan.gz);
-    gett_gemm<TM, TN, WM, WN><<<grid, 32 * WM * WN, gemm_smem<TM, TN>(), ctx->stream>>>(plan.d, A, B, C);
+    ensure_smem_attr(ctx, gett_gemm<TM, TN, WM, WN, MINB>, (int)gemm_smem<TM, TN>());
+    dim3 grid((unsigned)((plan.d.Msz + TM - 1) / TM), (unsigned)((plan.d.Nsz + TN - 1) / TN), plan.gz);
+    gett_gemm<TM, TN, WM, WN, MINB><<<grid, 32 * WM * WN, gemm_smem<TM, TN>(), ctx->stream>>>(plan.d, A, B, C);
     TNE_LAUNCH_CHECK(ctx);
     return TNE_OK;
 }
 
 }  // namespace
 
-// plan->aux[0]: tile variant (0: 64 x 32, 1: 64 x 16, 2: 128 x 64 -- 32 accumulator tiles per warp, one CTA per SM: for
-// contractions large enough to fill the chip with such tiles)
+// plan->aux[0]: tile variant (0: 64 x 32, 1: 64 x 16, 2: 128 x 64 with 16 warps, one CTA per SM: for contractions large
+// enough to fill the chip with such tiles)
 bool gemm_plan(tne_ctx* ctx, ContractPlan* plan) {
     const GettDesc& d = plan->d;
     if (ctx->opt_no_gemm == 1) return false;
@@ -211,7 +211,10 @@ bool gemm_plan(tne_ctx* ctx, ContractPlan* plan) {
 }
 
 int gemm_run(tne_ctx* ctx, const ContractPlan& plan, const cplx* A, const cplx* B, cplx* C) {
-    if (plan.aux[0] == 2) return launch_gemm<128, 64, 4, 2>(ctx, plan, A, B, C);
+    // 128 x 64 tile: 16 warps (4 x 4, 8 accumulator tiles each, <= 128 registers) hide the per-chunk barrier better than 8 warps
+    // with 32 tiles each: 24.7-25.6 vs 21.7-22.5 TFLOP/s on N = K = 256 / 4096^3 (tools/gemm_time.py; option no_gemm = 3: 8 warps)
+    if (plan.aux[0] == 2 && ctx->opt_no_gemm == 3) return launch_gemm<128, 64, 4, 2>(ctx, plan, A, B, C);
+    if (plan.aux[0] == 2) return launch_gemm<128, 64, 4, 4>(ctx, plan, A, B, C);
     if (plan.aux[0] == 0) return launch_gemm<64, 32, 4, 2>(ctx, plan, A, B, C);
     return launch_gemm<64, 16, 8, 1>(ctx, plan, A, B, C);
 }

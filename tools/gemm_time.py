@@ -30,7 +30,7 @@ for L, D, opt_name in ((5, 4, "greedy"), (6, 4, "paired")):
     del p
 for name, ixs, shapes, iy in cases:
     xs = [T.B200Array.from_numpy(crand(*s)) for s in shapes]
-    for opt in (0, 2, 1):      # 0: tiled DMMA GEMM (big tiles where they fill the chip), 2: small tiles only, 1: FMA kernel
+    for opt in (0, 3, 2, 1):   # 0: tiled DMMA GEMM (16-warp big tile), 3: 8-warp big tile, 2: small tiles only, 1: FMA kernel; 0: tiled DMMA GEMM (big tiles where they fill the chip), 2: small tiles only, 1: FMA kernel
         ctx.set_option("no_gemm", opt)
         T.einsum.einsum(ixs, xs, iy); ctx.sync()
         ctx.set_option("profile", 1); ctx.profile_collect()
