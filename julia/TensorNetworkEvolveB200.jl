@@ -332,6 +332,72 @@ function TensorNetworkEvolve.rydberg_tebd_sweep!(peps::PEPS{T}, g, C::Real, Δ::
     return peps
 end
 
+# R replica PEPS of ONE structure through ONE tne_tebd_sweep call (mirror of peps.py::apply_sweep_batch_): the site / bond tables
+# are concatenated and the gate list is tiled with offset indices; the library's wavefront levelling then puts the R copies of a
+# gate into the same launch.  TEBD does not shard inside one PEPS: this is how it fills a GPU (and N GPUs: R / N replicas per rank).
+function TensorNetworkEvolve.rydberg_tebd_sweep!(pepses::AbstractVector{<:PEPS{T}}, g, C::Real, Δ::Real, Ω::Real, δt) where T
+    all(on_device, pepses) || return map(p -> TensorNetworkEvolve.rydberg_tebd_sweep!(p, g, C, Δ, Ω, δt), pepses)
+    p0 = first(pepses)
+    vidal = p0 isa VidalPEPS
+    nv, nb, R = length(p0.vertex_tensors), length(p0.virtual_labels), length(pepses)
+    bondidx = Dict(l => Int32(k - 1) for (k, l) in enumerate(p0.virtual_labels))
+    one = SweepGate[]
+    for e in edges(g)
+        i, j = src(e), dst(e)
+        hij = cterm(C) + put(2, 1 => xterm(Ω / degree(g, i))) + put(2, 2 => xterm(Ω / degree(g, j))) +
+              put(2, 1 => zterm(Δ / degree(g, i))) + put(2, 2 => zterm(Δ / degree(g, j)))
+        m = Matrix(mat(time_evolve(hij, δt)))
+        li, lj = p0.vertex_labels[i], p0.vertex_labels[j]
+        shared = only(li ∩ lj)
+        lam(ls) = ntuple(a -> (vidal && 1 < a <= length(ls)) ? bondidx[ls[a]] : Int32(-1), 32)
+        flat = reinterpret(Cdouble, vec(ComplexF64.(m)))
+        push!(one, SweepGate(i - 1, j - 1, findfirst(==(shared), li) - 1, findfirst(==(shared), lj) - 1, bondidx[shared],
+                             ntuple(k -> flat[k], 32), lam(li), lam(lj), 0, 0.0))
+    end
+    shift(t, d) = map(x -> x >= 0 ? Int32(x + d) : x, t)
+    gates = SweepGate[SweepGate(q.site_i + (r - 1) * nv, q.site_j + (r - 1) * nv, q.axis_i, q.axis_j, q.bond + (r - 1) * nb, q.gate,
+                                shift(q.lambda_i, (r - 1) * nb), shift(q.lambda_j, (r - 1) * nb), 0, 0.0) for r in 1:R for q in one]
+    old_sites = Int64[t.handle for p in pepses for t in p.vertex_tensors]
+    sites = copy(old_sites)
+    old_bonds = vidal ? Int64[t.handle for p in pepses for t in p.bond_tensors] : Int64[0]
+    bonds = copy(old_bonds)
+    check(ccall((:tne_tebd_sweep, LIB[]), Cint,
+                (Ptr{Cvoid}, Cint, Ptr{Int64}, Cint, Ptr{Int64}, Cint, Ptr{SweepGate}, Cint, Cdouble, Cint),
+                CTX[], length(sites), sites, vidal ? length(bonds) : 0, bonds, length(gates), gates, p0.Dmax, p0.ϵ, vidal))
+    ng = length(one)
+    for (r, peps) in enumerate(pepses)
+        shapes = [collect(size(t)) for t in peps.vertex_tensors]
+        blen = Dict{Int,Int}()
+        for (q, e) in enumerate(edges(g))
+            gq = gates[(r - 1) * ng + q]
+            gq.trunc_err >= 0 && @info "truncation error is $(gq.trunc_err)"
+            shapes[src(e)][gq.axis_i + 1] = gq.kept
+            shapes[dst(e)][gq.axis_j + 1] = gq.kept
+            blen[one[q].bond + 1] = gq.kept
+        end
+        for s in 1:nv
+            k = (r - 1) * nv + s
+            sites[k] == old_sites[k] && continue
+            peps.vertex_tensors[s] = B200Array{T,length(shapes[s])}(sites[k], Tuple(shapes[s]))
+        end
+        if vidal
+            for b in 1:nb
+                k = (r - 1) * nb + b
+                bonds[k] == old_bonds[k] && continue
+                peps.bond_tensors[b] = B200Array{T,1}(bonds[k], (blen[b],))
+            end
+        end
+    end
+    return pepses
+end
+
+# compiled-programme cache of the tree entry points (tne_plan_cache_info): (programmes held, calls served from the cache)
+function plan_cache_info()
+    n, h = Ref{Int64}(0), Ref{Int64}(0)
+    check(ccall((:tne_plan_cache_info, LIB[]), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}), CTX[], n, h))
+    return n[], h[]
+end
+
 to_b200(peps::PEPS) = replace_tensors(peps, B200Array.(alltensors(peps)))
 
 end # module
