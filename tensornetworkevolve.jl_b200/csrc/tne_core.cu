@@ -202,6 +202,10 @@ extern "C" int tne_ctx_destroy(tne_ctx* ctx) {
     }
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->comm_stream) { cudaStreamSynchronize(ctx->comm_stream); cudaStreamDestroy(ctx->comm_stream); }
+    if (ctx->ev_comm_ready) cudaEventDestroy(ctx->ev_comm_ready);
+    if (ctx->ev_comm_done) cudaEventDestroy(ctx->ev_comm_done);
+    ctx->plan_cache.clear();
     comm_destroy(ctx);
     for (auto& kv : ctx->bufs) if (kv.second.block) kv.second.block->ctx = nullptr;  // freed below
     std::vector<void*> ptrs;

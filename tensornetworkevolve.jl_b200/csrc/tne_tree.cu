@@ -1320,6 +1320,12 @@ extern "C" int tne_expect_terms(tne_ctx* ctx, const tne_tree* tree, const tne_bu
                 ctx->plan_cache.splice(ctx->plan_cache.begin(), ctx->plan_cache, it);   // most recently used first
                 break;
             }
+    // a cached programme planned its tape blocks against the memory that was free THEN: if that no longer fits, plan again
+    if (cp && cp->E.tape_bytes > 0 && cp->peak > ctx->mem_limit - ctx->in_use) {
+        for (auto it = ctx->plan_cache.begin(); it != ctx->plan_cache.end(); ++it)
+            if (it->first == key) { ctx->plan_cache.erase(it); break; }
+        cp.reset();
+    }
     const bool fresh = !cp;
     if (fresh) cp = std::make_shared<Compiled>(ctx);
     Program& P = cp->P;
