@@ -110,7 +110,12 @@ def _optimized_code(alllabels, physical_labels, virtual_labels, max_ind, nflavor
                     return k
             raise ValueError("site %d is not in the contraction order" % site)
         segs = [(pos_of(site), [l for b in bonds for l in (b, rep[b])]) for site, bonds in segments]
-    code_ip = es.optimize_code(ixs, [], size_dict, optimizer, nslices, segments=segs)
+    # optimizer = "sweep": the bra and the ket copy of a tensor are absorbed one right after the other; segments = "auto" /
+    # "auto2": checkpointed segments and segment-local slices derived from the network (einsum.sweep_segments)
+    nl = len(alllabels)
+    if isinstance(segments, str):
+        segs = segments
+    code_ip = es.optimize_code(ixs, [], size_dict, optimizer, nslices, segments=segs, groups=[[i, nl + i] for i in range(nl)])
     return code_st, code_ip
 
 

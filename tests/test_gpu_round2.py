@@ -543,3 +543,27 @@ def test_tape_retention_is_bit_identical(tne):
     assert out[-1][2]["recompute_flops"] < 1e-3 * out[0][2]["recompute_flops"] and out[0][2]["recompute_flops"] > 0.2 * out[0][2]["flops"]
     assert out[-1][2]["contractions"] < out[0][2]["contractions"]
     assert out[-1][2]["flops"] == out[0][2]["flops"]
+
+
+def test_automatic_sweep_plan_on_device(tne):
+    """optimizer="sweep" with segments="auto" / "auto2" (order, checkpointed segments and free slices derived from the network,
+    no hand-built plan): energy + force of the 4x4 D=3 golden PEPS and <psi|psi> of the 8x8 D=2 / 5x5 D=4 goldens; a
+    rectangular 3x5 lattice against the reference-default greedy tree."""
+    gold = _gold("grid_4x4_D3.npz")
+    L, D = 4, 3
+    g = tne.grid([L, L])
+    p = tne.rand_simplepeps(g, D, np.random.default_rng(seed_for(L, D)), optimizer="sweep", segments="auto")
+    assert len(p.code_inner_product.segments) == L
+    h = tne.rydberg_hamiltonian(g, 10.0, 0.2, 0.3)
+    y, f = tne.energy_and_gradient(p, h)
+    assert rel(y.to_numpy(), gold["iloss2"]) < TOL and rel(f.to_numpy(), gold["fvec"]) < TOL
+    for (L2, D2, name) in ((8, 2, "grid_8x8_D2_norm.npz"), (5, 4, "grid_5x5_D4.npz")):
+        g2 = tne.grid([L2, L2])
+        q = tne.rand_simplepeps(g2, D2, np.random.default_rng(seed_for(L2, D2)), optimizer="sweep", segments="auto2")
+        assert rel(tne.inner_product(q, q).to_numpy(), _gold(name)["inner"]) < TOL
+    g3 = tne.grid([3, 5])
+    a = tne.rand_simplepeps(g3, 3, np.random.default_rng(9), optimizer="sweep", segments="auto")
+    b = tne.replace_tensors(tne.zero_simplepeps(g3, 3, optimizer="greedy"), a.alltensors())
+    assert rel(tne.inner_product(a, a).to_numpy(), tne.inner_product(b, b).to_numpy()) < TOL
+    assert rel(tne.expect(tne.rydberg_hamiltonian(g3, 10.0, 0.2, 0.3), a, a).to_numpy(),
+               tne.expect(tne.rydberg_hamiltonian(g3, 10.0, 0.2, 0.3), b, b).to_numpy()) < TOL
