@@ -480,6 +480,10 @@ def run_gpu(args):
         nsw = 5
         tms, tl, _ = timed(lambda: [sweep() for _ in range(nsw)], 1)
         tms /= nsw
+        multi = lambda: T.rydberg_tebd_(pt, gt, t=0.03 * 11, C=C_, delta=DELTA_, omega=OMEGA_, nstep=11)
+        multi()
+        mms10, _, _ = timed(multi, 1)
+        extras["tebd_10_sweeps_one_call_8x8_D4"] = {"ms_per_sweep": mms10 / 10, "note": "rydberg_tebd! with nstep = 11: its 10 sweeps enqueued back to back by one tne_tebd_sweeps call, ranks verified once"}
         extras["tebd_sweep_8x8_D4"] = {"ms": tms, "bonds": gt.ne(), "bonds_per_s": gt.ne() / (tms * 1e-3), "wavefronts": len(T.tebd.wavefronts(gt.edges())),
                                        "note": "one rydberg_tebd_sweep! (mean of %d): 112 bond gates in one tne_tebd_sweep call (28 wavefront launches, no host "
                                                "sync in between), QR-reduced Jacobi SVD truncation to D=4, latency-bound" % nsw}
@@ -502,10 +506,11 @@ def run_gpu(args):
             rep = {}
             for Rr in (8, 32):
                 reps = [T.rand_simplepeps(gt2, 4, np.random.default_rng(seed_for(8, 4) + 1000 * rank + r)) for r in range(Rr)]
-                bs = lambda: T.rydberg_tebd_sweep_batch_(reps, gt2, C_, DELTA_, OMEGA_, 0.03)
-                bs(); bs()
-                rms, _, _ = timed(lambda: [bs() for _ in range(3)], 1)
-                rms /= 3
+                nsw = 5     # rydberg_tebd! with nstep = 6: its 5 sweeps go out in ONE tne_tebd_sweeps call (no sync between the sweeps)
+                bs = lambda: T.rydberg_tebd_batch_(reps, gt2, t=0.03 * (nsw + 1), C=C_, delta=DELTA_, omega=OMEGA_, nstep=nsw + 1)
+                bs()
+                rms, _, _ = timed(bs, 1)
+                rms /= nsw
                 rep["R%d" % Rr] = {"ms_per_batched_sweep": rms, "peps_sweeps_per_s_all_gpus": world * Rr / (rms * 1e-3),
                                    "bond_updates_per_s_all_gpus": world * Rr * gt2.ne() / (rms * 1e-3)}
                 del reps

@@ -223,6 +223,13 @@ typedef struct {
 
 int tne_tebd_sweep(tne_ctx* ctx, int n_sites, tne_buf* sites, int n_bonds, tne_buf* bonds, int n_gates,
                    tne_sweep_gate* gates, int Dmax, double eps, int vidal);
+/* rydberg_tebd! (src/tebd.jl:25-38): `n_sweeps` identical sweeps back to back in one call.  All of them are enqueued
+ * speculatively (no host synchronisation between wavefronts OR between sweeps) and verified once; a sweep whose ranks did not
+ * reach their caps is redone exactly and the rest is enqueued again.  `kept_all` / `err_all` ([n_sweeps * n_gates], sweep-major;
+ * may be NULL) receive the kept rank and the truncation error of every gate of every sweep; the gates' own output fields hold
+ * those of the last sweep. */
+int tne_tebd_sweeps(tne_ctx* ctx, int n_sites, tne_buf* sites, int n_bonds, tne_buf* bonds, int n_gates,
+                    tne_sweep_gate* gates, int Dmax, double eps, int vidal, int n_sweeps, int32_t* kept_all, double* err_all);
 
 /* ---- multi-GPU: sum of partial energies / gradients (serial `sum` at src/peps.jl:470) ------
  * comm is created from an NCCL unique id broadcast by the host program. */

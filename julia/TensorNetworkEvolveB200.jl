@@ -284,8 +284,7 @@ end
 on_device(peps::PEPS) = all(t -> t isa B200Array, alltensors(peps))
 # `PEPS{T,NF,LT}` has three parameters (src/peps.jl:4) and the array type is not one of them: dispatch on the abstract type and
 # look at the tensors; anything that is not on the device takes the reference's own method (src/tebd.jl:15-23)
-function TensorNetworkEvolve.rydberg_tebd_sweep!(peps::PEPS{T}, g, C::Real, Δ::Real, Ω::Real, δt) where T
-    on_device(peps) || return invoke(TensorNetworkEvolve.rydberg_tebd_sweep!, Tuple{Any,Any,Real,Real,Real,Any}, peps, g, C, Δ, Ω, δt)
+function sweep_gates(peps::PEPS, g, C::Real, Δ::Real, Ω::Real, δt)
     vidal = peps isa VidalPEPS
     bondidx = Dict(l => Int32(k - 1) for (k, l) in enumerate(peps.virtual_labels))
     gates = SweepGate[]
@@ -301,20 +300,31 @@ function TensorNetworkEvolve.rydberg_tebd_sweep!(peps::PEPS{T}, g, C::Real, Δ::
         push!(gates, SweepGate(i - 1, j - 1, findfirst(==(shared), li) - 1, findfirst(==(shared), lj) - 1, bondidx[shared],
                                ntuple(k -> flat[k], 32), lam(li), lam(lj), 0, 0.0))
     end
+    return gates
+end
+
+# `n_sweeps` identical sweeps in ONE library call (tne_tebd_sweeps): every wavefront of every sweep is enqueued without a host
+# synchronisation, the kept ranks are verified once at the end
+function run_sweeps!(peps::PEPS{T}, g, gates::Vector{SweepGate}, n_sweeps::Integer) where T
+    vidal = peps isa VidalPEPS
     old_sites = Int64[t.handle for t in peps.vertex_tensors]
     sites = copy(old_sites)
     old_bonds = vidal ? Int64[t.handle for t in peps.bond_tensors] : Int64[0]
     bonds = copy(old_bonds)
-    check(ccall((:tne_tebd_sweep, LIB[]), Cint,
-                (Ptr{Cvoid}, Cint, Ptr{Int64}, Cint, Ptr{Int64}, Cint, Ptr{SweepGate}, Cint, Cdouble, Cint),
-                CTX[], length(sites), sites, vidal ? length(bonds) : 0, bonds, length(gates), gates, peps.Dmax, peps.ϵ, vidal))
+    errs = zeros(Cdouble, length(gates) * n_sweeps)
+    check(ccall((:tne_tebd_sweeps, LIB[]), Cint,
+                (Ptr{Cvoid}, Cint, Ptr{Int64}, Cint, Ptr{Int64}, Cint, Ptr{SweepGate}, Cint, Cdouble, Cint, Cint, Ptr{Int32}, Ptr{Cdouble}),
+                CTX[], length(sites), sites, vidal ? length(bonds) : 0, bonds, length(gates), gates, peps.Dmax, peps.ϵ, vidal,
+                n_sweeps, C_NULL, errs))
+    for err in errs
+        err >= 0 && @info "truncation error is $(err)"                                         # src/peps.jl:386
+    end
     # final shapes first (the last gate on a bond decides its rank), then exactly ONE new wrapper per tensor whose handle
     # changed: two wrappers over one handle would free it twice (mirror of peps.py::apply_sweep_)
     shapes = [collect(size(t)) for t in peps.vertex_tensors]
     blen = Dict{Int,Int}()
     for (q, e) in enumerate(edges(g))
         gq = gates[q]
-        gq.trunc_err >= 0 && @info "truncation error is $(gq.trunc_err)"                       # src/peps.jl:386
         shapes[src(e)][gq.axis_i + 1] = gq.kept
         shapes[dst(e)][gq.axis_j + 1] = gq.kept
         blen[gq.bond + 1] = gq.kept
@@ -329,6 +339,18 @@ function TensorNetworkEvolve.rydberg_tebd_sweep!(peps::PEPS{T}, g, C::Real, Δ::
             peps.bond_tensors[b] = B200Array{T,1}(bonds[b], (blen[b],))
         end
     end
+    return peps
+end
+
+function TensorNetworkEvolve.rydberg_tebd_sweep!(peps::PEPS{T}, g, C::Real, Δ::Real, Ω::Real, δt) where T
+    on_device(peps) || return invoke(TensorNetworkEvolve.rydberg_tebd_sweep!, Tuple{Any,Any,Real,Real,Real,Any}, peps, g, C, Δ, Ω, δt)
+    return run_sweeps!(peps, g, sweep_gates(peps, g, C, Δ, Ω, δt), 1)
+end
+
+# rydberg_tebd! (src/tebd.jl:25-38): its nstep - 1 sweeps (sic, src/tebd.jl:27) in one call
+function TensorNetworkEvolve.rydberg_tebd!(peps::PEPS{T}, g::SimpleGraph; t::Real, C::Real, Δ::Real, Ω::Real, nstep::Int) where T
+    on_device(peps) || return invoke(TensorNetworkEvolve.rydberg_tebd!, Tuple{Any,SimpleGraph}, peps, g; t = t, C = C, Δ = Δ, Ω = Ω, nstep = nstep)
+    nstep > 1 && run_sweeps!(peps, g, sweep_gates(peps, g, C, Δ, Ω, t / nstep), nstep - 1)
     return peps
 end
 

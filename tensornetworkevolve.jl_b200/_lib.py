@@ -118,6 +118,8 @@ SYMBOLS = {
     "tne_apply_onbond_batched": (C.c_int, [C.c_void_p, C.c_int, _P(TneBondJob)]),
     "tne_tebd_sweep": (C.c_int, [C.c_void_p, C.c_int, _P(C.c_int64), C.c_int, _P(C.c_int64), C.c_int, _P(TneSweepGate),
                                  C.c_int, C.c_double, C.c_int]),
+    "tne_tebd_sweeps": (C.c_int, [C.c_void_p, C.c_int, _P(C.c_int64), C.c_int, _P(C.c_int64), C.c_int, _P(TneSweepGate),
+                                  C.c_int, C.c_double, C.c_int, C.c_int, _P(C.c_int32), _P(C.c_double)]),
     "tne_nccl_unique_id": (C.c_int, [C.c_void_p]),
     "tne_comm_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "tne_allreduce_sum": (C.c_int, [C.c_void_p, C.c_int, _P(C.c_int64)]),

@@ -667,22 +667,177 @@ extern "C" int tne_apply_onbond_batched(tne_ctx* ctx, int n_jobs, tne_bond_job* 
     return TNE_OK;
 }
 
-// One whole TEBD sweep (src/tebd.jl:15-23) in one call.  The reference applies the gates strictly one after the other;
-// gates on disjoint sites commute exactly (truncation included), so the sequence is levelled into wavefronts of
-// site-disjoint gates (a gate's level = 1 + the highest level of an earlier gate on one of its sites) and every
-// wavefront is one launch.  The rank a bond keeps is data dependent (src/peps.jl:383-390), but a generic gate always
-// truncates to the cap min(Dmax, 4 Ds, 2 O_i, 2 O_j): the sweep is therefore enqueued SPECULATIVELY with kept = cap, with
-// no host synchronisation between wavefronts, and the kept ranks are checked once at the end.  If any bond kept fewer
-// (singular values below eps), the speculative outputs are dropped and the sweep is redone wavefront by wavefront with
-// the exact ranks (the inputs are immutable buffers, so nothing has to be restored).
-extern "C" int tne_tebd_sweep(tne_ctx* ctx, int n_sites, tne_buf* sites, int n_bonds, tne_buf* bonds, int n_gates,
-                              tne_sweep_gate* gates, int Dmax, double eps, int vidal) {
+// Whole TEBD sweeps (src/tebd.jl:15-23, and the nstep - 1 of them of src/tebd.jl:25-38) in one call.  The reference applies the
+// gates strictly one after the other; gates on disjoint sites commute exactly (truncation included), so the sequence is levelled
+// into wavefronts of site-disjoint gates (a gate's level = 1 + the highest level of an earlier gate on one of its sites) and every
+// wavefront is one launch.  The rank a bond keeps is data dependent (src/peps.jl:383-390), but a generic gate always truncates to
+// the cap min(Dmax, 4 Ds, 2 O_i, 2 O_j): ALL sweeps are therefore enqueued SPECULATIVELY with kept = cap, with no host
+// synchronisation between wavefronts or between sweeps, and the kept ranks are checked once at the end.  If a bond of sweep k
+// kept fewer (singular values below eps), the speculative results from sweep k on are dropped, sweep k is redone wavefront by
+// wavefront with the exact ranks (the inputs are immutable buffers, so nothing has to be restored) and the rest is enqueued again.
+namespace {
+
+struct SweepCtx {
+    tne_ctx* ctx;
+    int n_sites, n_bonds, n_gates, Dmax, vidal, n_levels;
+    double eps;
+    const tne_sweep_gate* gates;
+    std::vector<std::vector<int>> by_level;
+};
+
+struct SweepRun {                        // one sweep whose kernels are enqueued and whose ranks are not verified yet
+    std::vector<BondBatch> batches;      // per level: descriptors + meta buffer
+    std::vector<std::vector<int>> cap;
+    std::vector<tne_buf> created;        // every tensor the sweep allocated (final ones and intermediate generations)
+    std::vector<tne_buf> in_s, in_b, out_s, out_b;
+    std::vector<BondDev> all_dev;
+    tne_buf hall = 0;
+};
+
+void fill_job(const SweepCtx& S, const tne_sweep_gate& g, const std::vector<tne_buf>& cur_s, const std::vector<tne_buf>& cur_b, tne_bond_job& jb) {
+    memset(&jb, 0, sizeof(jb));
+    jb.ti = cur_s[g.site_i]; jb.tj = cur_s[g.site_j];
+    jb.axis_i = g.axis_i; jb.axis_j = g.axis_j;
+    memcpy(jb.gate, g.gate, sizeof(jb.gate));
+    jb.Dmax = S.Dmax; jb.eps = S.eps; jb.vidal = S.vidal;
+    if (S.vidal)
+        for (int a = 1; a < TNE_MAX_RANK; ++a) {
+            if (g.lambda_i[a] >= 0 && g.lambda_i[a] < S.n_bonds) jb.lambda_i[a] = cur_b[g.lambda_i[a]];
+            if (g.lambda_j[a] >= 0 && g.lambda_j[a] < S.n_bonds) jb.lambda_j[a] = cur_b[g.lambda_j[a]];
+        }
+}
+
+void free_batches(tne_ctx* ctx, SweepRun& R) {
+    for (auto& bb : R.batches) { if (bb.hmeta) tne_free(ctx, bb.hmeta); if (bb.hdev) tne_free(ctx, bb.hdev); bb.hmeta = bb.hdev = 0; }
+    if (R.hall) { tne_free(ctx, R.hall); R.hall = 0; }
+}
+
+// enqueue one sweep speculatively (kept = cap): descriptors of all wavefronts in ONE upload, then the launches back to back
+int sweep_enqueue(const SweepCtx& S, const std::vector<tne_buf>& in_s, const std::vector<tne_buf>& in_b, SweepRun& R) {
+    tne_ctx* ctx = S.ctx;
+    R.in_s = in_s; R.in_b = in_b;
+    std::vector<tne_buf> cur_s = in_s, cur_b = in_b, scratch;
+    R.batches.assign(S.n_levels, BondBatch());
+    R.cap.assign(S.n_levels, std::vector<int>());
+    int rc = TNE_OK;
+    for (int lv = 0; lv < S.n_levels && rc == TNE_OK; ++lv) {
+        const std::vector<int>& ids = S.by_level[lv];
+        std::vector<tne_bond_job> jobs(ids.size());
+        for (size_t q = 0; q < ids.size(); ++q) fill_job(S, S.gates[ids[q]], cur_s, cur_b, jobs[q]);
+        BondBatch& bb = R.batches[lv];
+        std::vector<tne_buf> direct;
+        rc = bond_enqueue(ctx, (int)jobs.size(), jobs.data(), bb, &direct, true);
+        for (auto h : direct) R.created.push_back(h);
+        // the launches are deferred: the scratch of this level must not go back to the pool before its kernel is enqueued
+        // (a later buf_new -- the descriptor table itself -- could be handed the same block)
+        for (auto hs : bb.slabs) scratch.push_back(hs);
+        bb.slabs.clear();
+        if (rc) break;
+        R.cap[lv].resize(ids.size());
+        for (size_t q = 0; q < ids.size(); ++q) {
+            const tne_sweep_gate& g = S.gates[ids[q]];
+            R.cap[lv][q] = bb.dev[q].Dcap;
+            cur_s[g.site_i] = direct[3 * q]; cur_s[g.site_j] = direct[3 * q + 1];
+            if (S.vidal) cur_b[g.bond] = direct[3 * q + 2];
+        }
+    }
+    if (rc == TNE_OK) {
+        std::vector<size_t> off(S.n_levels + 1, 0);
+        for (int lv = 0; lv < S.n_levels; ++lv) off[lv + 1] = off[lv] + R.batches[lv].dev.size();
+        R.all_dev.reserve(off[S.n_levels]);
+        for (int lv = 0; lv < S.n_levels; ++lv) R.all_dev.insert(R.all_dev.end(), R.batches[lv].dev.begin(), R.batches[lv].dev.end());
+        rc = buf_new(ctx, {(int64_t)((R.all_dev.size() * sizeof(BondDev) + 15) / 16)}, &R.hall);
+        if (rc == TNE_OK) {
+            BondDev* base = reinterpret_cast<BondDev*>(buf_get(ctx, R.hall)->ptr());
+            cudaError_t e = cudaMemcpyAsync(base, R.all_dev.data(), R.all_dev.size() * sizeof(BondDev), cudaMemcpyHostToDevice, ctx->stream);
+            if (e != cudaSuccess) rc = tne_fail(ctx, TNE_ERR_CUDA, "descriptor upload failed: %s", cudaGetErrorString(e));
+            for (int lv = 0; lv < S.n_levels && rc == TNE_OK; ++lv) {
+                bond_kernel<<<(unsigned)R.batches[lv].dev.size(), BOND_THREADS, bond_smem_bytes(), ctx->stream>>>(base + off[lv]);
+                ctx->launches++;
+                e = cudaGetLastError();
+                if (e != cudaSuccess) rc = tne_fail(ctx, TNE_ERR_CUDA, "bond kernel launch failed: %s", cudaGetErrorString(e));
+            }
+        }
+    }
+    for (auto h : scratch) tne_free(ctx, h);   // stream-ordered pool: safe once the kernels that use them are enqueued
+    R.out_s = cur_s; R.out_b = cur_b;
+    return rc;
+}
+
+// read the ranks of an enqueued sweep back (synchronises); ok = every bond reached its cap and nothing was non-finite
+int sweep_verify(const SweepCtx& S, SweepRun& R, int32_t* kept_out, double* err_out, bool* ok) {
+    *ok = true;
+    for (int lv = 0; lv < S.n_levels; ++lv) {
+        std::vector<int> kept;
+        std::vector<double> err;
+        TNE_TRY(bond_fetch(S.ctx, R.batches[lv], kept, err));
+        for (size_t q = 0; q < S.by_level[lv].size(); ++q) {
+            const int gi = S.by_level[lv][q];
+            kept_out[gi] = kept[q]; err_out[gi] = err[q];
+            if (kept[q] != R.cap[lv][q] || std::isnan(err[q])) *ok = false;   // NaN: decided by the exact-rank pass
+        }
+    }
+    if (R.hall) { tne_free(S.ctx, R.hall); R.hall = 0; }
+    return TNE_OK;
+}
+
+// one sweep wavefront by wavefront with the exact ranks (one synchronisation per wavefront)
+int sweep_exact(const SweepCtx& S, const std::vector<tne_buf>& in_s, const std::vector<tne_buf>& in_b, std::vector<tne_buf>& out_s,
+                std::vector<tne_buf>& out_b, std::vector<tne_buf>& created, int32_t* kept_out, double* err_out) {
+    tne_ctx* ctx = S.ctx;
+    std::vector<tne_buf> cur_s = in_s, cur_b = in_b;
+    int rc = TNE_OK;
+    for (int lv = 0; lv < S.n_levels && rc == TNE_OK; ++lv) {
+        const std::vector<int>& ids = S.by_level[lv];
+        std::vector<tne_bond_job> jobs(ids.size());
+        for (size_t q = 0; q < ids.size(); ++q) fill_job(S, S.gates[ids[q]], cur_s, cur_b, jobs[q]);
+        BondBatch bb;
+        rc = bond_enqueue(ctx, (int)jobs.size(), jobs.data(), bb);
+        if (rc) break;
+        std::vector<int> kept;
+        std::vector<double> err;
+        rc = bond_fetch(ctx, bb, kept, err);
+        if (rc) break;
+        for (size_t q = 0; q < ids.size() && rc == TNE_OK; ++q) {
+            const tne_sweep_gate& g = S.gates[ids[q]];
+            HostJob& h = bb.hj[q];
+            const int D = kept[q];
+            kept_out[ids[q]] = kept[q]; err_out[ids[q]] = err[q];
+            tne_buf ti = 0, tj = 0, sb = 0;
+            rc = bond_place(ctx, h.uv[0], h.dims[0], h.axis[0], D, &ti);
+            if (!rc) { created.push_back(ti); rc = bond_place(ctx, h.uv[1], h.dims[1], h.axis[1], D, &tj); }
+            if (!rc) { created.push_back(tj); rc = buf_new(ctx, {(int64_t)D}, &sb); }
+            if (!rc) {
+                created.push_back(sb);
+                if (D > 0) {
+                    cudaError_t e = cudaMemcpyAsync(buf_get(ctx, sb)->ptr(), buf_get(ctx, h.s)->ptr(), (size_t)D * sizeof(cplx), cudaMemcpyDeviceToDevice, ctx->stream);
+                    if (e != cudaSuccess) rc = tne_fail(ctx, TNE_ERR_CUDA, "copy of the singular values failed: %s", cudaGetErrorString(e));
+                }
+                cur_s[g.site_i] = ti; cur_s[g.site_j] = tj;
+                if (S.vidal) cur_b[g.bond] = sb;
+            }
+            for (int side = 0; side < 2; ++side) { tne_free(ctx, h.q[side]); tne_free(ctx, h.uv[side]); }
+            tne_free(ctx, h.s);
+        }
+        for (size_t q = 0; q < err.size() && rc == TNE_OK; ++q)
+            if (std::isnan(err[q])) rc = tne_fail(ctx, TNE_ERR_INVALID, "tebd sweep gate %d: non-finite values in the site tensors", ids[q]);
+    }
+    out_s = cur_s; out_b = cur_b;
+    return rc;
+}
+
+}  // namespace
+
+extern "C" int tne_tebd_sweeps(tne_ctx* ctx, int n_sites, tne_buf* sites, int n_bonds, tne_buf* bonds, int n_gates,
+                               tne_sweep_gate* gates, int Dmax, double eps, int vidal, int n_sweeps, int32_t* kept_all, double* err_all) {
     TNE_ENTER(ctx);
-    if (n_gates <= 0) return TNE_OK;
+    if (n_gates <= 0 || n_sweeps <= 0) return TNE_OK;
     if (!sites || !gates || (vidal && !bonds)) return tne_fail(ctx, TNE_ERR_INVALID, "null argument");
+    SweepCtx S;
+    S.ctx = ctx; S.n_sites = n_sites; S.n_bonds = n_bonds; S.n_gates = n_gates; S.Dmax = Dmax; S.vidal = vidal; S.eps = eps; S.gates = gates;
     // wavefront levels, order-preserving
     std::vector<int> site_level(n_sites, -1), level(n_gates, 0);
-    int n_levels = 0;
+    S.n_levels = 0;
     for (int gi = 0; gi < n_gates; ++gi) {
         const tne_sweep_gate& g = gates[gi];
         if (g.site_i < 0 || g.site_i >= n_sites || g.site_j < 0 || g.site_j >= n_sites || g.site_i == g.site_j)
@@ -690,138 +845,74 @@ extern "C" int tne_tebd_sweep(tne_ctx* ctx, int n_sites, tne_buf* sites, int n_b
         if (vidal && (g.bond < 0 || g.bond >= n_bonds)) return tne_fail(ctx, TNE_ERR_INVALID, "sweep gate %d: bad bond index", gi);
         level[gi] = 1 + std::max(site_level[g.site_i], site_level[g.site_j]);
         site_level[g.site_i] = site_level[g.site_j] = level[gi];
-        n_levels = std::max(n_levels, level[gi] + 1);
+        S.n_levels = std::max(S.n_levels, level[gi] + 1);
     }
-    std::vector<std::vector<int>> by_level(n_levels);
-    for (int gi = 0; gi < n_gates; ++gi) by_level[level[gi]].push_back(gi);
+    S.by_level.assign(S.n_levels, std::vector<int>());
+    for (int gi = 0; gi < n_gates; ++gi) S.by_level[level[gi]].push_back(gi);
+    ensure_smem_attr(ctx, bond_kernel, (int)bond_smem_bytes());
 
-    const std::vector<tne_buf> sites0(sites, sites + n_sites);
-    const std::vector<tne_buf> bonds0(bonds, bonds + (vidal ? n_bonds : 0));
-    for (int attempt = 0; attempt < 2; ++attempt) {
-        const bool speculative = attempt == 0;
-        std::vector<tne_buf> cur_s = sites0, cur_b = bonds0, created, scratch;
-        std::vector<BondBatch> batches(n_levels);
-        std::vector<std::vector<int>> cap(n_levels);
-        bool ok = true;
-        int rc = TNE_OK;
-        auto drop_created = [&]() { for (auto h : created) tne_free(ctx, h); created.clear(); };
-        for (int lv = 0; lv < n_levels && rc == TNE_OK; ++lv) {
-            const std::vector<int>& ids = by_level[lv];
-            std::vector<tne_bond_job> jobs(ids.size());
-            for (size_t q = 0; q < ids.size(); ++q) {
-                const tne_sweep_gate& g = gates[ids[q]];
-                tne_bond_job& jb = jobs[q];
-                memset(&jb, 0, sizeof(jb));
-                jb.ti = cur_s[g.site_i]; jb.tj = cur_s[g.site_j];
-                jb.axis_i = g.axis_i; jb.axis_j = g.axis_j;
-                memcpy(jb.gate, g.gate, sizeof(jb.gate));
-                jb.Dmax = Dmax; jb.eps = eps; jb.vidal = vidal;
-                if (vidal)
-                    for (int a = 1; a < TNE_MAX_RANK; ++a) {
-                        if (g.lambda_i[a] >= 0 && g.lambda_i[a] < n_bonds) jb.lambda_i[a] = cur_b[g.lambda_i[a]];
-                        if (g.lambda_j[a] >= 0 && g.lambda_j[a] < n_bonds) jb.lambda_j[a] = cur_b[g.lambda_j[a]];
-                    }
-            }
-            BondBatch& bb = batches[lv];
-            std::vector<tne_buf> direct;
-            rc = bond_enqueue(ctx, (int)jobs.size(), jobs.data(), bb, speculative ? &direct : nullptr, speculative);
-            for (auto h : direct) created.push_back(h);
-            if (rc) break;
-            std::vector<int> kept;
-            std::vector<double> err;
-            if (!speculative) {
-                rc = bond_fetch(ctx, bb, kept, err);
-                if (rc) break;
-            }
-            cap[lv].resize(ids.size());
-            for (auto hs : bb.slabs) scratch.push_back(hs);
-            bb.slabs.clear();
-            for (size_t q = 0; q < ids.size() && rc == TNE_OK; ++q) {
-                tne_sweep_gate& g = gates[ids[q]];
-                HostJob& h = bb.hj[q];
-                const int D = speculative ? bb.dev[q].Dcap : kept[q];
-                cap[lv][q] = D;
-                if (!speculative) { g.kept = kept[q]; g.trunc_err = err[q]; }
-                tne_buf ti = 0, tj = 0, sb = 0;
-                if (speculative) {   // the kernel writes the final tensors itself
-                    cur_s[g.site_i] = direct[3 * q]; cur_s[g.site_j] = direct[3 * q + 1];
-                    if (vidal) cur_b[g.bond] = direct[3 * q + 2];
-                    // the launches are deferred: the scratch of this level must not go back to the pool before its kernel is
-                    // enqueued (a later buf_new -- the descriptor table itself -- could be handed the same block)
-                    continue;
-                }
-                rc = bond_place(ctx, h.uv[0], h.dims[0], h.axis[0], D, &ti);
-                if (!rc) { created.push_back(ti); rc = bond_place(ctx, h.uv[1], h.dims[1], h.axis[1], D, &tj); }
-                if (!rc) { created.push_back(tj); rc = buf_new(ctx, {(int64_t)D}, &sb); }
-                if (!rc) {
-                    created.push_back(sb);
-                    if (D > 0)
-                        TNE_CUDA(ctx, cudaMemcpyAsync(buf_get(ctx, sb)->ptr(), buf_get(ctx, h.s)->ptr(), (size_t)D * sizeof(cplx),
-                                                      cudaMemcpyDeviceToDevice, ctx->stream));
-                    cur_s[g.site_i] = ti; cur_s[g.site_j] = tj;
-                    if (vidal) cur_b[g.bond] = sb;
-                }
-                for (int side = 0; side < 2; ++side) { tne_free(ctx, h.q[side]); tne_free(ctx, h.uv[side]); }
-                tne_free(ctx, h.s);
-            }
-            for (size_t q = 0; q < err.size() && rc == TNE_OK; ++q)
-                if (std::isnan(err[q])) rc = tne_fail(ctx, TNE_ERR_INVALID, "tebd sweep gate %d: non-finite values in the site tensors", ids[q]);
+    std::vector<int32_t> kept_loc((size_t)n_sweeps * n_gates, 0);
+    std::vector<double> err_loc((size_t)n_sweeps * n_gates, 0.0);
+    std::vector<tne_buf> cur_s(sites, sites + n_sites), cur_b(bonds, bonds + (vidal ? n_bonds : 0));
+    std::unordered_set<tne_buf> mine;          // every live tensor this call allocated; whatever is not handed out is freed at the end
+    auto drop = [&](const std::vector<tne_buf>& hs) { for (auto h : hs) if (mine.erase(h)) tne_free(ctx, h); };
+    int rc = TNE_OK;
+    int sw = 0;
+    while (sw < n_sweeps && rc == TNE_OK) {
+        // enqueue all remaining sweeps speculatively, back to back
+        std::vector<SweepRun> runs((size_t)(n_sweeps - sw));
+        std::vector<tne_buf> st_s = cur_s, st_b = cur_b;
+        size_t enq = 0;
+        for (; enq < runs.size() && rc == TNE_OK; ++enq) {
+            rc = sweep_enqueue(S, st_s, st_b, runs[enq]);
+            for (auto h : runs[enq].created) mine.insert(h);
+            st_s = runs[enq].out_s; st_b = runs[enq].out_b;
         }
-        std::vector<BondDev> all_dev;      // alive until the first fetch has synchronised the stream
-        tne_buf hall = 0;
-        if (rc == TNE_OK && speculative) {
-            // ONE descriptor upload for the whole sweep, then the wavefront launches back to back: between two launches the
-            // host does nothing but the launch itself
-            std::vector<size_t> off(n_levels + 1, 0);
-            for (int lv = 0; lv < n_levels; ++lv) off[lv + 1] = off[lv] + batches[lv].dev.size();
-            all_dev.reserve(off[n_levels]);
-            for (int lv = 0; lv < n_levels; ++lv) all_dev.insert(all_dev.end(), batches[lv].dev.begin(), batches[lv].dev.end());
-            rc = buf_new(ctx, {(int64_t)((all_dev.size() * sizeof(BondDev) + 15) / 16)}, &hall);
-            if (rc == TNE_OK) {
-                BondDev* base = reinterpret_cast<BondDev*>(buf_get(ctx, hall)->ptr());
-                cudaError_t e = cudaMemcpyAsync(base, all_dev.data(), all_dev.size() * sizeof(BondDev), cudaMemcpyHostToDevice, ctx->stream);
-                if (e != cudaSuccess) rc = tne_fail(ctx, TNE_ERR_CUDA, "descriptor upload failed: %s", cudaGetErrorString(e));
-                for (int lv = 0; lv < n_levels && rc == TNE_OK; ++lv) {
-                    bond_kernel<<<(unsigned)batches[lv].dev.size(), BOND_THREADS, bond_smem_bytes(), ctx->stream>>>(base + off[lv]);
-                    ctx->launches++;
-                    e = cudaGetLastError();
-                    if (e != cudaSuccess) rc = tne_fail(ctx, TNE_ERR_CUDA, "bond kernel launch failed: %s", cudaGetErrorString(e));
-                }
-            }
+        if (rc != TNE_OK) { for (auto& R : runs) free_batches(ctx, R); break; }
+        // verify in order (the first fetch synchronises the stream)
+        size_t good = 0;
+        for (; good < runs.size(); ++good) {
+            bool ok = false;
+            rc = sweep_verify(S, runs[good], kept_loc.data() + (size_t)(sw + good) * n_gates, err_loc.data() + (size_t)(sw + good) * n_gates, &ok);
+            if (rc != TNE_OK || !ok) break;
         }
-        for (auto h : scratch) tne_free(ctx, h);   // stream-ordered pool: safe once the kernels that use them are enqueued
-        scratch.clear();
-        if (rc == TNE_OK && speculative) {   // one synchronisation for the whole sweep: were all the caps reached?
-            for (int lv = 0; lv < n_levels && rc == TNE_OK; ++lv) {
-                std::vector<int> kept;
-                std::vector<double> err;
-                rc = bond_fetch(ctx, batches[lv], kept, err);
-                for (size_t q = 0; q < by_level[lv].size() && rc == TNE_OK; ++q) {
-                    tne_sweep_gate& g = gates[by_level[lv][q]];
-                    g.kept = kept[q]; g.trunc_err = err[q];
-                    if (kept[q] != cap[lv][q] || std::isnan(err[q])) ok = false;   // NaN: decided by the exact-rank pass
-                }
-            }
-        }
-        if (hall) { cudaStreamSynchronize(ctx->stream); tne_free(ctx, hall); }
-        if (rc != TNE_OK) {
-            for (auto& bb : batches) { if (bb.hmeta) tne_free(ctx, bb.hmeta); if (bb.hdev) tne_free(ctx, bb.hdev); }
-            drop_created();
-            return rc;
-        }
-        if (ok) {
-            // hand the final tensors out; intermediate generations (a site touched by several gates) are released
-            std::unordered_set<tne_buf> live(cur_s.begin(), cur_s.end());     // (a scan per handle was quadratic in the replica count)
-            live.insert(cur_b.begin(), cur_b.end());
-            for (auto h : created)
-                if (!live.count(h)) tne_free(ctx, h);
-            for (int i = 0; i < n_sites; ++i) sites[i] = cur_s[i];
-            for (size_t i = 0; i < cur_b.size(); ++i) bonds[i] = cur_b[i];
-            return TNE_OK;
-        }
-        drop_created();   // a bond kept fewer singular values than its cap: redo with exact ranks
+        if (rc != TNE_OK) { for (auto& R : runs) free_batches(ctx, R); break; }
+        if (good > 0) { cur_s = runs[good - 1].out_s; cur_b = runs[good - 1].out_b; }
+        if (good == runs.size()) { sw = n_sweeps; break; }
+        // sweep sw + good kept fewer singular values than its cap somewhere: its results and everything after it are void
+        for (size_t k = good; k < runs.size(); ++k) { free_batches(ctx, runs[k]); drop(runs[k].created); }
+        std::vector<tne_buf> out_s, out_b, created;
+        rc = sweep_exact(S, cur_s, cur_b, out_s, out_b, created, kept_loc.data() + (size_t)(sw + good) * n_gates,
+                         err_loc.data() + (size_t)(sw + good) * n_gates);
+        for (auto h : created) mine.insert(h);
+        if (rc != TNE_OK) break;
+        cur_s = out_s; cur_b = out_b;
+        sw += (int)good + 1;
     }
-    return tne_fail(ctx, TNE_ERR_UNSUPPORTED, "tebd sweep: exact-rank pass did not complete");
+    if (rc != TNE_OK) {
+        cudaStreamSynchronize(ctx->stream);
+        for (auto h : std::vector<tne_buf>(mine.begin(), mine.end())) tne_free(ctx, h);
+        return rc;
+    }
+    // hand the final tensors out; every intermediate generation is released
+    std::unordered_set<tne_buf> live(cur_s.begin(), cur_s.end());
+    live.insert(cur_b.begin(), cur_b.end());
+    for (auto h : mine)
+        if (!live.count(h)) tne_free(ctx, h);
+    for (int i = 0; i < n_sites; ++i) sites[i] = cur_s[i];
+    for (size_t i = 0; i < cur_b.size(); ++i) bonds[i] = cur_b[i];
+    for (int gi = 0; gi < n_gates; ++gi) {
+        gates[gi].kept = kept_loc[(size_t)(n_sweeps - 1) * n_gates + gi];
+        gates[gi].trunc_err = err_loc[(size_t)(n_sweeps - 1) * n_gates + gi];
+    }
+    if (kept_all) memcpy(kept_all, kept_loc.data(), kept_loc.size() * sizeof(int32_t));
+    if (err_all) memcpy(err_all, err_loc.data(), err_loc.size() * sizeof(double));
+    return TNE_OK;
+}
+
+extern "C" int tne_tebd_sweep(tne_ctx* ctx, int n_sites, tne_buf* sites, int n_bonds, tne_buf* bonds, int n_gates,
+                              tne_sweep_gate* gates, int Dmax, double eps, int vidal) {
+    return tne_tebd_sweeps(ctx, n_sites, sites, n_bonds, bonds, n_gates, gates, Dmax, eps, vidal, 1, nullptr, nullptr);
 }
 
 // LinearAlgebra.svd(A) + truncation for a matrix: the same kernel on the trivial "bond" whose sites are

@@ -558,11 +558,13 @@ class SweepPlan:
         self.view = view
 
 
-def apply_sweep_(peps, gates):
+def apply_sweep_(peps, gates, n_sweeps=1):
     """``apply_onbond!`` for a whole sequence ``[(i, j, mat), ...]`` (one TEBD sweep, src/tebd.jl:16-21) in ONE library
     call: ``tne_tebd_sweep`` levels the sequence into wavefronts of site-disjoint gates and enqueues them without any
     host synchronisation in between.  Results and the ``LOG`` order are those of the sequential loop.  ``gates`` may be a
-    prepared :class:`SweepPlan` (the drivers reuse one plan for all sweeps)."""
+    prepared :class:`SweepPlan` (the drivers reuse one plan for all sweeps).  ``n_sweeps > 1``: the same sequence that many
+    times back to back (``rydberg_tebd!``'s loop, src/tebd.jl:27-29) in one ``tne_tebd_sweeps`` call: no host round trip and
+    no synchronisation between the sweeps either."""
     plan = gates if isinstance(gates, SweepPlan) else SweepPlan(peps, gates)
     n = len(plan.sites)
     if n == 0:
@@ -576,13 +578,21 @@ def apply_sweep_(peps, gates):
     sites = (C.c_int64 * nv)(*[t.handle for t in old_sites])
     old_bonds = [_dev(t) for t in peps.bond_tensors] if vidal else []
     bonds = (C.c_int64 * max(1, nb))(*([t.handle for t in old_bonds] if vidal else [0]))
-    ctx.check(ctx.L.tne_tebd_sweep(ctx.h, nv, sites, nb if vidal else 0, bonds, n, plan.arr, int(peps.Dmax), float(peps.eps),
-                                   1 if vidal else 0))
+    n_sweeps = int(n_sweeps)
+    if n_sweeps < 1:
+        return peps
+    kept_all = (C.c_int32 * (n * n_sweeps))()
+    err_all = (C.c_double * (n * n_sweeps))()
+    ctx.check(ctx.L.tne_tebd_sweeps(ctx.h, nv, sites, nb if vidal else 0, bonds, n, plan.arr, int(peps.Dmax), float(peps.eps),
+                                    1 if vidal else 0, n_sweeps, kept_all, err_all))
     # shapes: the bond a gate rewrote now has the rank it kept (the last gate on a bond wins)
     shapes = [list(t.shape) for t in old_sites]
     blen = {}
     kept, err = plan.view["kept"].tolist(), plan.view["trunc_err"].tolist()
     ax_i, ax_j, bnd = plan.view["axis_i"].tolist(), plan.view["axis_j"].tolist(), plan.view["bond"].tolist()
+    for e in list(err_all)[:n * (n_sweeps - 1)]:      # the @info lines of the earlier sweeps, in the sequential order
+        if e >= 0:
+            LOG.append("truncation error is %r" % e)
     for q, (i, j) in enumerate(plan.sites):
         shapes[i - 1][ax_i[q]] = kept[q]
         shapes[j - 1][ax_j[q]] = kept[q]
@@ -599,7 +609,7 @@ def apply_sweep_(peps, gates):
     return peps
 
 
-def apply_sweep_batch_(pepses, gates):
+def apply_sweep_batch_(pepses, gates, n_sweeps=1):
     """One sweep ``[(i, j, mat), ...]`` applied to R independent PEPS of the SAME structure (replicas: an ensemble of
     initial states / parameter points) in ONE ``tne_tebd_sweep`` call.  The site and bond tables of the replicas are
     concatenated and the gate list is tiled with offset indices; the library's wavefront levelling then puts the R copies
@@ -641,8 +651,15 @@ def apply_sweep_batch_(pepses, gates):
     sites = (C.c_int64 * (nv * R))(*[t.handle for t in old_sites])
     old_bonds = [_dev(t) for q in pepses for t in q.bond_tensors] if vidal else []
     bonds = (C.c_int64 * max(1, nb * R))(*([t.handle for t in old_bonds] if vidal else [0]))
-    ctx.check(ctx.L.tne_tebd_sweep(ctx.h, nv * R, sites, nb * R if vidal else 0, bonds, n * R, arr, int(p0.Dmax), float(p0.eps),
-                                   1 if vidal else 0))
+    n_sweeps = int(n_sweeps)
+    if n_sweeps < 1:
+        return pepses
+    err_all = (C.c_double * (n * R * n_sweeps))()
+    ctx.check(ctx.L.tne_tebd_sweeps(ctx.h, nv * R, sites, nb * R if vidal else 0, bonds, n * R, arr, int(p0.Dmax), float(p0.eps),
+                                    1 if vidal else 0, n_sweeps, None, err_all))
+    for e in list(err_all)[:n * R * (n_sweeps - 1)]:
+        if e >= 0:
+            LOG.append("truncation error is %r" % e)
     kept, err = view["kept"].tolist(), view["trunc_err"].tolist()
     ax_i, ax_j, bnd = plan.view["axis_i"].tolist(), plan.view["axis_j"].tolist(), plan.view["bond"].tolist()
     for r, q in enumerate(pepses):

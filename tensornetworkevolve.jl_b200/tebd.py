@@ -97,8 +97,8 @@ def rydberg_tebd_sweep_batch_(regs, g, C, delta, omega, dt):
 def rydberg_tebd_batch_(regs, g, *, t, C, delta, omega, nstep):
     """``rydberg_tebd!`` (src/tebd.jl:25-38, nstep-1 sweeps) for R replicas."""
     dt = t / nstep
-    for _ in range(nstep - 1):
-        rydberg_tebd_sweep_batch_(regs, g, C, delta, omega, dt)
+    regs = list(regs)
+    P.apply_sweep_batch_(regs, _sweep_plan_for(regs[0], g, C, delta, omega, dt), n_sweeps=nstep - 1)
     return regs
 
 
@@ -108,8 +108,12 @@ def rydberg_tebd_(reg, g=None, *, t, C, delta, omega, nstep):  # src/tebd.jl:25-
         for i, j in P.virtualbonds(reg):
             g.add_edge(i, j)
     dt = t / nstep
-    for _ in range(nstep - 1):  # sic: nstep-1 sweeps (src/tebd.jl:27)
-        rydberg_tebd_sweep_(reg, g, C, delta, omega, dt)
+    if isinstance(reg, yao.ArrayReg):
+        for _ in range(nstep - 1):  # sic: nstep-1 sweeps (src/tebd.jl:27)
+            rydberg_tebd_sweep_(reg, g, C, delta, omega, dt)
+        return reg
+    # device PEPS: all nstep - 1 sweeps in ONE library call (tne_tebd_sweeps: no host round trip between the sweeps)
+    P.apply_sweep_(reg, _sweep_plan_for(reg, g, C, delta, omega, dt), n_sweeps=nstep - 1)
     return reg
 
 

@@ -169,3 +169,32 @@ def test_replica_batched_sweeps_match_single_sweeps(tne, kind):
     for q in zs:
         for x, y in zip(q.alltensors(), z1.alltensors()):
             assert x.shape == y.shape and np.array_equal(x.to_numpy(), y.to_numpy())
+
+
+@pytest.mark.parametrize("kind", ["simple", "vidal"])
+def test_multi_sweep_call_matches_sweep_by_sweep(tne, kind):
+    """tne_tebd_sweeps: rydberg_tebd!'s nstep - 1 sweeps enqueued back to back in ONE call (no synchronisation between sweeps,
+    ranks verified once) give bit for bit the tensors, and the same truncation log, as one call per sweep -- for a random
+    state with growing bonds (every sweep reaches its cap) and from a product state (early sweeps keep fewer singular values:
+    the speculative chain is cut, that sweep redone exactly and the rest enqueued again)."""
+    L, D = 3, 2
+    g = tne.grid([L, L])
+    par = dict(C=10.0, delta=0.2, omega=0.3)
+    for start in ("random", "product"):
+        kw = dict(Dmax=6, eps=1e-10)
+        if start == "random":
+            mk = lambda: (tne.rand_simplepeps if kind == "simple" else tne.rand_vidalpeps)(g, D, np.random.default_rng(5), **kw)
+        else:
+            mk = lambda: (tne.zero_simplepeps if kind == "simple" else tne.zero_vidalpeps)(g, D, **kw)
+        a, b = mk(), mk()
+        tne.peps.LOG.clear()
+        for _ in range(5):
+            tne.rydberg_tebd_sweep_(a, g, dt=0.3 / 6, **par)
+        log_a = list(tne.peps.LOG)
+        tne.peps.LOG.clear()
+        tne.rydberg_tebd_(b, g, t=0.3, nstep=6, **par)          # the same 5 sweeps of dt = 0.3 / 6 in one library call
+        log_b = list(tne.peps.LOG)
+        assert [t.shape for t in a.alltensors()] == [t.shape for t in b.alltensors()], start
+        for x, y in zip(a.alltensors(), b.alltensors()):
+            assert np.array_equal(x.to_numpy(), y.to_numpy()), start
+        assert log_a == log_b, start
