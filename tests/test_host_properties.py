@@ -59,7 +59,7 @@ def test_optimisers_produce_valid_trees(net, seed):
     xs = [rng.standard_normal([sizes[l] for l in ix]) + 1j * rng.standard_normal([sizes[l] for l in ix]) for ix in ixs]
     want = _reference(ixs, iy, xs)
     costs = {}
-    for opt in ("greedy", "treesa", list(rng.permutation(len(ixs)))):
+    for opt in ("greedy", "treesa", "sweep", "auto", list(rng.permutation(len(ixs)))):
         code = es.optimize_code(ixs, iy, sizes, opt)
         costs[str(opt)] = es.tree_cost(code, sizes)[0]
         leaves = []
@@ -76,6 +76,7 @@ def test_optimisers_produce_valid_trees(net, seed):
         got = _evaluate(code, xs)
         assert got.shape == want.shape and np.allclose(got, want, rtol=1e-10, atol=1e-10)
     assert costs["treesa"] <= costs["greedy"] * (1 + 1e-12)     # annealing starts from the greedy tree and keeps the best one
+    assert costs["auto"] <= min(costs["greedy"], costs["sweep"]) * (1 + 1e-12)   # the cheaper of the two
 
 
 @settings(max_examples=100, deadline=None)
