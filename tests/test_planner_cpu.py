@@ -186,3 +186,44 @@ def test_tape_retention_plan_on_cpu():
     w8 = _plan("6", "4", "rs_comm=8", "--raw")
     t8 = re.search(r"tape retention: (\d+) of this rank's (\d+)", w8)
     assert t8 and t8.group(1) == t8.group(2) == "9", w8[-1500:]
+
+
+def test_automatic_plans_are_accepted_and_their_slices_are_free():
+    """optimizer="sweep" + segments="auto" on rectangles, a ladder, a triangular strip and a ring, through the planner context:
+    the library accepts every plan, one segment per lattice column where the boundary has minima (none on the strip / ring:
+    plain tree), and the programme executes exactly the flops of the unsliced tree -- the entering-bond slices repeat nothing."""
+    code = r'''
+import os, sys, re
+os.environ["TNE_PLAN_ONLY"] = "1"
+sys.path.insert(0, %r)
+import tne_b200 as T
+from tne_b200 import peps as P, einsum as es
+from tne_b200._lib import TneError
+ctx = T.context(); ctx.set_option("debug", 2)
+def cost(p):
+    sizes = {}
+    for vl, t in zip(p.vertex_labels, p.vertex_tensors):
+        for l, s_ in zip(vl, t.shape): sizes[l] = s_
+    for k, l in enumerate(p.virtual_labels): sizes[p.max_index + k + 1] = sizes[l]
+    return es.tree_cost(p.code_inner_product, sizes)[0]
+n = 10
+cases = [("3x4", T.grid([3, 4]), 4), ("4x6", T.grid([4, 6]), 6), ("2x7", T.grid([2, 7]), 7),
+         ("strip", T.graph_from_edges(n, [(i, i + 1) for i in range(1, n)] + [(i, i + 2) for i in range(1, n - 1)]), 0),
+         ("ring", T.graph_from_edges(8, [(i, i %% 8 + 1) for i in range(1, 9)]), 0)]
+for name, g, nseg in cases:
+    p = T.zero_simplepeps(g, 3, optimizer="sweep", segments="auto")
+    assert len(p.code_inner_product.segments or []) == nseg, (name, p.code_inner_product.segments)
+    leaves = [P._dev(t) for t in p.alltensors()] * 2
+    try:
+        es.contract_tree_device(p.code_inner_product, leaves, [1] * g.nv() + [0] * g.nv())
+        print("COMPUTED?!", name)
+    except TneError as e:
+        print("CASE", name, "%%.6e" %% cost(p), "planner context" in str(e))
+''' % ROOT
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    cases = [l.split() for l in res.stdout.splitlines() if l.startswith("CASE")]
+    assert len(cases) == 5 and all(c[3] == "True" for c in cases), res.stdout + res.stderr[-1500:]
+    planned = [float(m) for m in re.findall(r"\[tne-plan\] \d+ phases, \d+ launches, ([0-9.e+]+) flops", res.stderr)]
+    assert len(planned) == 5
+    for c, fl in zip(cases, planned):
+        assert abs(float(c[2]) - fl) <= 1e-4 * fl, (c, fl)
