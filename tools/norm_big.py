@@ -31,8 +31,11 @@ if world > 1:
 
 def big_peps(L, D):
     g = T.grid([L, L])
-    order, segs = T.sweep_plan(g, L, slice_first_row=True)
-    p = T.rand_simplepeps(g, D, np.random.default_rng(seed_for(L, D)), optimizer=order, segments=segs)
+    if os.environ.get("TNE_AUTO_PLAN") == "1":     # the same plan derived from the network alone (einsum.sweep_order / sweep_segments)
+        p = T.rand_simplepeps(g, D, np.random.default_rng(seed_for(L, D)), optimizer="sweep", segments="auto2")
+    else:
+        order, segs = T.sweep_plan(g, L, slice_first_row=True)
+        p = T.rand_simplepeps(g, D, np.random.default_rng(seed_for(L, D)), optimizer=order, segments=segs)
     if world > 1:
         p.code_inner_product.seg_shard = True
     return p
