@@ -561,6 +561,12 @@ def test_automatic_sweep_plan_on_device(tne):
         g2 = tne.grid([L2, L2])
         q = tne.rand_simplepeps(g2, D2, np.random.default_rng(seed_for(L2, D2)), optimizer="sweep", segments="auto2")
         assert rel(tne.inner_product(q, q).to_numpy(), _gold(name)["inner"]) < TOL
+    # VidalPEPS: the bond vectors are leaves of the network too (their bra / ket copies form groups of their own)
+    g4 = tne.grid([4, 4])
+    va = tne.rand_vidalpeps(g4, 2, np.random.default_rng(11), optimizer="sweep", segments="auto")
+    vb = tne.replace_tensors(tne.zero_vidalpeps(g4, 2, optimizer="greedy"), va.alltensors())
+    assert rel(tne.inner_product(va, va).to_numpy(), tne.inner_product(vb, vb).to_numpy()) < TOL
+    assert rel(tne.vec(va), tne.vec(vb)) < TOL
     g3 = tne.grid([3, 5])
     a = tne.rand_simplepeps(g3, 3, np.random.default_rng(9), optimizer="sweep", segments="auto")
     b = tne.replace_tensors(tne.zero_simplepeps(g3, 3, optimizer="greedy"), a.alltensors())
