@@ -5,6 +5,7 @@
     python tests/golden/make_golden_big.py smatrix 5 4            -> adds x / smatrix_x to grid_5x5_D4.npz
     python tests/golden/make_golden_big.py part66                 -> tests/golden/grid_6x6_D4_partial.npz
     python tests/golden/make_golden_big.py norm 8 3               -> tests/golden/grid_8x8_D3_norm.npz  (also 8 2, 10 2)
+    python tests/golden/make_golden_big.py energy66 --procs 2     -> tests/golden/grid_6x6_D4_energy.npz (all 96 <psi|h_k|psi>, ~6.5 min each)
 
 The oracle executes the reference's algorithm literally: one full contraction per Hamiltonian term
 (``src/peps.jl:469-477``) and one TensorAD tape holding every intermediate (``src/TensorAD/TensorAD.jl:131-164``).
@@ -182,6 +183,40 @@ def make_norm(L, D, memgb):
     print("[golden] wrote %s (%.1f s): inner = %r" % (path, time.time() - t, complex(inner)), flush=True)
 
 
+def energy66_piece(args):
+    """<psi|h_k|psi> of the 6x6 D=4 benchmark PEPS for one Hamiltonian term (one full oracle contraction, cached)."""
+    k, memgb = args
+    _limit_memory(memgb)
+    g, p, h = setup(6, 4)
+    hk = OY.Add(h.blocks[k])
+    r = _cached(os.path.join(WORK, "part66", "energy_%03d.npz" % k), lambda: dict(v=np.asarray(OP.expect(hk, p, p))))
+    return k, complex(r["v"])
+
+
+def make_energy66(procs, memgb):
+    """Every term of the benchmark's Hamiltonian (60 edge terms, 36 site terms) at 6x6 D=4, forward only: the fixture grows as
+    the workers finish (term_index lists what is in it), so a killed run still leaves a usable golden."""
+    import multiprocessing as mp
+    g, p, h = setup(6, 4)
+    K = len(h.blocks)
+    wd = os.path.join(WORK, "part66")
+    inner = _cached(os.path.join(wd, "inner.npz"), lambda: dict(v=np.asarray(OP.inner_product(p, p))))["v"]
+    done = {}
+    path = os.path.join(ROOT, "tests", "golden", "grid_6x6_D4_energy.npz")
+
+    def write():
+        ks = sorted(done)
+        np.savez_compressed(path + ".tmp.npz", variables=OP.variables(p), inner=inner, term_index=np.array(ks),
+                            energy_terms=np.array([done[k] for k in ks]), n_terms=np.asarray(K))
+        os.replace(path + ".tmp.npz", path)
+    cached_first = sorted(range(K), key=lambda k: not os.path.exists(os.path.join(wd, "energy_%03d.npz" % k)))
+    with mp.get_context("fork").Pool(procs, maxtasksperchild=1) as pool:
+        for k, v in pool.imap_unordered(energy66_piece, [(k, memgb) for k in cached_first], chunksize=1):
+            done[k] = v
+            write()
+            print("[golden] energy66: %d of %d terms" % (len(done), K), flush=True)
+
+
 def _write66(out, en, il, dirs, dG, dN):
     o = dict(out)
     o["energy_terms"] = np.array([complex(x) for x in en])
@@ -196,7 +231,7 @@ def _write66(out, en, il, dirs, dG, dN):
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("what", choices=["full", "smatrix", "part66", "norm"])
+    ap.add_argument("what", choices=["full", "smatrix", "part66", "norm", "energy66"])
     ap.add_argument("L", type=int, nargs="?", default=5)
     ap.add_argument("D", type=int, nargs="?", default=4)
     ap.add_argument("--procs", type=int, default=1)
@@ -209,5 +244,7 @@ if __name__ == "__main__":
         make_smatrix(a.L, a.D, a.method, a.memgb)
     elif a.what == "norm":
         make_norm(a.L, a.D, a.memgb)
+    elif a.what == "energy66":
+        make_energy66(a.procs, a.memgb)
     else:
         make_part66(a.memgb)

@@ -281,6 +281,24 @@ def test_6x6_d4_against_the_oracle(tne):
         assert abs(got - want) < 1e-9 * scale, (s, got, want)
 
 
+def test_6x6_d4_energy_of_every_generated_term(tne):
+    """<psi|h_k|psi> of the benchmark PEPS for every term the oracle has contracted so far (grid_6x6_D4_energy.npz grows up to all
+    96: 60 edge terms C P1 P1 and 36 site terms): their sum in one expect (one term-DP programme over the benchmark's plan) and
+    eight of them alone."""
+    gold = _gold("grid_6x6_D4_energy.npz")
+    L, D = 6, 4
+    g, p = _bench_peps(tne, L, D)
+    assert rel(tne.variables(p).to_numpy(), gold["variables"]) == 0.0
+    h = tne.rydberg_hamiltonian(g, 10.0, 0.2, 0.3)
+    ks = [int(k) for k in gold["term_index"]]
+    assert len(h.blocks) == int(gold["n_terms"]) and len(ks) >= 7
+    e_sub = complex(tne.expect(tne.yao.Add(*[h.blocks[k] for k in ks]), p, p).to_numpy())
+    assert abs(e_sub - complex(np.sum(gold["energy_terms"]))) < TOL * np.sum(np.abs(gold["energy_terms"]))
+    for q in sorted(set(np.linspace(0, len(ks) - 1, 8).astype(int).tolist())):
+        got = complex(tne.expect(tne.yao.Add(h.blocks[ks[q]]), p, p).to_numpy())
+        assert abs(got - complex(gold["energy_terms"][q])) < TOL * abs(complex(gold["energy_terms"][q])), ks[q]
+
+
 # -- fused reverse pass of a site (tne_site2b.cu) -------------------------------------------------------------------------
 def test_fused_reverse_site_kernel(tne):
     """D = 4 grid with the full Rydberg H: the three reverse ops of a bulk site run as ONE kernel.  Same energy and force as
