@@ -6,6 +6,7 @@
     python tests/golden/make_golden_big.py part66                 -> tests/golden/grid_6x6_D4_partial.npz
     python tests/golden/make_golden_big.py norm 8 3               -> tests/golden/grid_8x8_D3_norm.npz  (also 8 2, 10 2)
     python tests/golden/make_golden_big.py energy66 --procs 2     -> tests/golden/grid_6x6_D4_energy.npz (all 96 <psi|h_k|psi>, ~6.5 min each)
+    python tests/golden/make_golden_big.py iloss66 --procs 2      -> tests/golden/grid_6x6_D4_iloss.npz  (iloss2's cores psi^T h_k psi, spread over the terms)
 
 The oracle executes the reference's algorithm literally: one full contraction per Hamiltonian term
 (``src/peps.jl:469-477``) and one TensorAD tape holding every intermediate (``src/TensorAD/TensorAD.jl:131-164``).
@@ -217,6 +218,42 @@ def make_energy66(procs, memgb):
             print("[golden] energy66: %d of %d terms" % (len(done), K), flush=True)
 
 
+def iloss66_piece(args):
+    """iloss2's un-normalised core of one term, code(psi..., (h_k psi)...) = expect(h_k, conj(psi), psi) (src/timeevolve.jl:59)."""
+    k, memgb = args
+    _limit_memory(memgb)
+    g, p, h = setup(6, 4)
+    hk = OY.Add(h.blocks[k])
+    pc = OP.conj(p)
+    r = _cached(os.path.join(WORK, "part66", "iloss_%03d.npz" % k), lambda: dict(v=np.asarray(OP.expect(hk, pc, p))))
+    return k, complex(r["v"])
+
+
+def make_iloss66(procs, memgb):
+    """The cores of iloss2 (the quantity the benchmark differentiates) term by term at 6x6 D=4; cached pieces first, then the terms
+    in a stride-7 order so that a run cut short still covers edge and site terms of every lattice region."""
+    import multiprocessing as mp
+    g, p, h = setup(6, 4)
+    K = len(h.blocks)
+    wd = os.path.join(WORK, "part66")
+    inner = _cached(os.path.join(wd, "inner.npz"), lambda: dict(v=np.asarray(OP.inner_product(p, p))))["v"]
+    done = {}
+    path = os.path.join(ROOT, "tests", "golden", "grid_6x6_D4_iloss.npz")
+
+    def write():
+        ks = sorted(done)
+        np.savez_compressed(path + ".tmp.npz", variables=OP.variables(p), inner=inner, term_index=np.array(ks),
+                            iloss_core_terms=np.array([done[k] for k in ks]), n_terms=np.asarray(K))
+        os.replace(path + ".tmp.npz", path)
+    spread = [(7 * q) % K for q in range(K)]            # 7 and 96 are coprime: a permutation of the terms
+    order = sorted(spread, key=lambda k: not os.path.exists(os.path.join(wd, "iloss_%03d.npz" % k)))
+    with mp.get_context("fork").Pool(procs, maxtasksperchild=1) as pool:
+        for k, v in pool.imap_unordered(iloss66_piece, [(k, memgb) for k in order], chunksize=1):
+            done[k] = v
+            write()
+            print("[golden] iloss66: %d of %d terms" % (len(done), K), flush=True)
+
+
 def _write66(out, en, il, dirs, dG, dN):
     o = dict(out)
     o["energy_terms"] = np.array([complex(x) for x in en])
@@ -231,7 +268,7 @@ def _write66(out, en, il, dirs, dG, dN):
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("what", choices=["full", "smatrix", "part66", "norm", "energy66"])
+    ap.add_argument("what", choices=["full", "smatrix", "part66", "norm", "energy66", "iloss66"])
     ap.add_argument("L", type=int, nargs="?", default=5)
     ap.add_argument("D", type=int, nargs="?", default=4)
     ap.add_argument("--procs", type=int, default=1)
@@ -246,5 +283,7 @@ if __name__ == "__main__":
         make_norm(a.L, a.D, a.memgb)
     elif a.what == "energy66":
         make_energy66(a.procs, a.memgb)
+    elif a.what == "iloss66":
+        make_iloss66(a.procs, a.memgb)
     else:
         make_part66(a.memgb)

@@ -299,6 +299,26 @@ def test_6x6_d4_energy_of_every_generated_term(tne):
         assert abs(got - complex(gold["energy_terms"][q])) < TOL * abs(complex(gold["energy_terms"][q])), ks[q]
 
 
+def test_6x6_d4_iloss2_of_every_generated_core(tne):
+    """iloss2 -- the quantity the benchmark evaluates and differentiates (src/timeevolve.jl:55-60: psi^T H psi_0 / <psi|psi>, the
+    reference's double conjugation) -- restricted to the terms whose cores the oracle has contracted (grid_6x6_D4_iloss.npz, spread
+    over edge and site terms of every lattice region), through energy_and_gradient on the benchmark's plan."""
+    gold = _gold("grid_6x6_D4_iloss.npz")
+    L, D = 6, 4
+    g, p = _bench_peps(tne, L, D)
+    assert rel(tne.variables(p).to_numpy(), gold["variables"]) == 0.0
+    h = tne.rydberg_hamiltonian(g, 10.0, 0.2, 0.3)
+    ks = [int(k) for k in gold["term_index"]]
+    assert len(ks) >= 7
+    y, f = tne.energy_and_gradient(p, tne.yao.Add(*[h.blocks[k] for k in ks]))
+    n2 = abs(complex(gold["inner"]))
+    want = float(np.real(np.sum(gold["iloss_core_terms"]))) / n2
+    assert abs(float(np.real(y.to_numpy())) - want) < TOL * np.sum(np.abs(gold["iloss_core_terms"])) / n2
+    # the force of a normalised state is orthogonal to the radial direction (size-independent property of fvec)
+    v = tne.variables(p).to_numpy()
+    assert abs(np.vdot(v, 1j * f.to_numpy()).real) < 1e-9 * np.linalg.norm(v) * np.linalg.norm(f.to_numpy())
+
+
 # -- fused reverse pass of a site (tne_site2b.cu) -------------------------------------------------------------------------
 def test_fused_reverse_site_kernel(tne):
     """D = 4 grid with the full Rydberg H: the three reverse ops of a bulk site run as ONE kernel.  Same energy and force as
